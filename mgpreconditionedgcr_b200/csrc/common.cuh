@@ -1,0 +1,214 @@
+// csrc/common.cuh -- context, error plumbing, complex helpers and the deterministic block/grid reduction shared
+// by every kernel file of libmgcr_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mgcr_b200.h"
+
+// ----------------------------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------------------------
+void mgcr_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) {                                                                            \
+            mgcr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));           \
+            return e__ == cudaErrorMemoryAllocation ? MGCR_ERR_OOM : MGCR_ERR_CUDA;                          \
+        }                                                                                                    \
+    } while (0)
+
+#define MGCR_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        int s__ = (expr);                                                                                    \
+        if (s__ != MGCR_OK) return s__;                                                                      \
+    } while (0)
+
+#define ARG_CHECK(cond, ...)                                                                                 \
+    do {                                                                                                     \
+        if (!(cond)) {                                                                                       \
+            mgcr_set_error(__VA_ARGS__);                                                                     \
+            return MGCR_ERR_ARG;                                                                             \
+        }                                                                                                    \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------------------
+// complex arithmetic, written out so that every element-wise result is what the reference's std::complex
+// arithmetic gives (library built with -fmad=false: these paths are HBM-bound, fused multiply-add buys nothing)
+// ----------------------------------------------------------------------------------------------------------
+typedef double2 c128;   // .x = re, .y = im ; 16-byte aligned -> one 128-bit load/store
+
+__host__ __device__ __forceinline__ c128 cmake(double re, double im) { c128 r; r.x = re; r.y = im; return r; }
+__host__ __device__ __forceinline__ c128 cadd(c128 a, c128 b) { return cmake(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ c128 csub(c128 a, c128 b) { return cmake(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ c128 cmul(c128 a, c128 b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// conj(a) * b
+__host__ __device__ __forceinline__ c128 cmulc(c128 a, c128 b) { return cmake(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+// num / den with a real denominator (all GCR coefficients divide by a squared norm)
+__host__ __device__ __forceinline__ c128 cdivr(c128 num, double den) { return cmake(num.x / den, num.y / den); }
+
+// streaming 128-bit accesses: vectors are touched once per kernel, keep them out of L1
+__device__ __forceinline__ c128 ld_stream(const c128* p) {
+    c128 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ c128 ld_plain(const c128* p) { return *p; }
+__device__ __forceinline__ void st_stream(c128* p, c128 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// context
+// ----------------------------------------------------------------------------------------------------------
+struct ProfEntry { double ms = 0; int64_t calls = 0; double bytes = 0; };
+struct ProfPending { const char* name; double bytes; int ev; };
+
+struct mgcr_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;      // halo traffic / boundary work overlapped with interior kernels
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_scal = nullptr;
+    // reduction scratch: per-block partial sums, a ticket counter, final scalars on device and pinned host mirror
+    double* d_partials = nullptr;           // [MAX_RED_BLOCKS][MAX_RED_VALUES]
+    unsigned int* d_ticket = nullptr;
+    double* d_scratch = nullptr;            // small device scalar scratch for the BLAS-1 entry points
+    double* h_pinned = nullptr;             // pinned host mirror (256 doubles)
+    int64_t launches = 0;
+    // distributed
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+    // profiling
+    bool profile = false;
+    std::map<std::string, ProfEntry> prof;
+    std::vector<cudaEvent_t> prof_events;   // pairs
+    std::vector<ProfPending> prof_pending;
+};
+
+enum { MAX_RED_BLOCKS = 2048, MAX_RED_VALUES = 32, RED_THREADS = 256 };
+
+// grid for a grid-stride streaming kernel over n items, `per_sm` resident blocks of RED_THREADS per SM
+static inline int stream_grid(const mgcr_ctx* ctx, int64_t n, int per_sm, int items_per_thread = 1) {
+    int64_t need = (n + (int64_t)RED_THREADS * items_per_thread - 1) / ((int64_t)RED_THREADS * items_per_thread);
+    int64_t cap = (int64_t)ctx->num_sms * per_sm;
+    if (cap > MAX_RED_BLOCKS) cap = MAX_RED_BLOCKS;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// profile-aware launch bookkeeping: KLAUNCH(ctx, "name", bytes, kernel<<<...>>>(...)).  With profiling on, every
+// launch is bracketed by a pair of pooled events on the launching stream; nothing synchronises until the pool is
+// drained (mgcr_ctx_get_profile or pool exhaustion), so the timed region keeps its shape.
+void prof_begin(mgcr_ctx* ctx, const char* name, double bytes);
+void prof_end(mgcr_ctx* ctx);
+struct ProfScope {
+    mgcr_ctx* ctx;
+    ProfScope(mgcr_ctx* c, const char* n, double bytes = 0.) : ctx(c) {
+        ctx->launches++;
+        if (ctx->profile) prof_begin(ctx, n, bytes);
+    }
+    ~ProfScope() { if (ctx->profile) prof_end(ctx); }
+};
+#define KLAUNCH(ctx, name, bytes, launch_expr)                                                               \
+    do {                                                                                                     \
+        ProfScope ps__(ctx, name, bytes);                                                                    \
+        launch_expr;                                                                                         \
+    } while (0)
+
+#define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
+
+// stream-ordered device memory (cudaMallocAsync pool with an unlimited release threshold: inner solves of the
+// multigrid cycle allocate and free their Krylov workspaces on every call without touching the driver)
+int dev_alloc(mgcr_ctx* ctx, size_t bytes, void** out);
+int dev_free(mgcr_ctx* ctx, void* p);
+template <typename T> static inline int dev_alloc_t(mgcr_ctx* ctx, size_t count, T** out) {
+    return dev_alloc(ctx, count * sizeof(T), (void**)out);
+}
+
+// distributed helpers (dist.cu)
+void dist_destroy(mgcr_ctx* ctx);
+int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
+int dist_sendrecv(mgcr_ctx* ctx, const void* d_send, size_t send_bytes, int send_peer, void* d_recv, size_t recv_bytes,
+                  int recv_peer, cudaStream_t stream);
+int dist_group_begin(mgcr_ctx* ctx);
+int dist_group_end(mgcr_ctx* ctx);
+int dist_send(mgcr_ctx* ctx, const void* d_send, size_t bytes, int peer, cudaStream_t stream);
+int dist_recv(mgcr_ctx* ctx, void* d_recv, size_t bytes, int peer, cudaStream_t stream);
+int dist_allgather_host_i64(mgcr_ctx* ctx, int64_t mine, std::vector<int64_t>& all);
+
+// ----------------------------------------------------------------------------------------------------------
+// deterministic reduction: warp shuffle -> shared memory -> one partial per block -> the LAST block to finish
+// (ticket counter) sums the partials with a fixed thread assignment and a fixed tree, so the result does not depend
+// on block scheduling.  NV values are reduced at once; result[k] is written by the last block only.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// blockDim.x must be RED_THREADS.  Returns true in every thread of the last block (after results are final).
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
+                                            double* __restrict__ result) {
+    constexpr int NW = RED_THREADS / 32;
+    __shared__ double sm[NW][NV];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double s = warp_sum(v[k]);
+        if (lane == 0) sm[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += sm[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicInc(ticket, gridDim.x - 1);   // wraps back to 0 after the last block: self-resetting
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    // last block: thread t sums partials of blocks t, t+RED_THREADS, ... (fixed), then the fixed tree above
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = 0.;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) acc[k] += __ldcg(&partials[(size_t)b * NV + k]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double s = warp_sum(acc[k]);
+        if (lane == 0) sm[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += sm[w][threadIdx.x];
+        result[threadIdx.x] = s;
+    }
+    return true;
+}

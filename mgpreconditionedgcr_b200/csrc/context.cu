@@ -1,0 +1,163 @@
+// csrc/context.cu -- context lifetime, error string, stream-ordered memory, profile export.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void mgcr_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* mgcr_last_error(void) { return g_err; }
+extern "C" int mgcr_abi_version(void) { return 1; }
+
+int dev_alloc(mgcr_ctx* ctx, size_t bytes, void** out) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        mgcr_set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? MGCR_ERR_OOM : MGCR_ERR_CUDA;
+    }
+    return MGCR_OK;
+}
+
+int dev_free(mgcr_ctx* ctx, void* p) {
+    if (!p) return MGCR_OK;
+    CUDA_TRY(cudaFreeAsync(p, ctx->stream));
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_create(int device, mgcr_ctx** out) {
+    ARG_CHECK(out != nullptr, "mgcr_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        mgcr_set_error("no CUDA device available (%s); this library has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return MGCR_ERR_CUDA;
+    }
+    ARG_CHECK(device >= 0 && device < ndev, "mgcr_ctx_create: device %d out of range (have %d)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        mgcr_set_error("device %d is sm_%d%d; libmgcr_b200 carries sm_100a code only", device, prop.major, prop.minor);
+        return MGCR_ERR_CUDA;
+    }
+    mgcr_ctx* c = new mgcr_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scal, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&c->d_partials, sizeof(double) * MAX_RED_BLOCKS * MAX_RED_VALUES));
+    CUDA_TRY(cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 4));
+    CUDA_TRY(cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 4));
+    CUDA_TRY(cudaMalloc(&c->d_scratch, sizeof(double) * 256));
+    CUDA_TRY(cudaMemset(c->d_scratch, 0, sizeof(double) * 256));
+    CUDA_TRY(cudaMallocHost(&c->h_pinned, sizeof(double) * 256));
+    // keep freed blocks cached in the default pool: inner solves allocate/free workspaces on every call
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_destroy(mgcr_ctx* c) {
+    if (!c) return MGCR_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->aux_stream);
+    dist_destroy(c);
+    cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned);
+    cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_scal);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->aux_stream);
+    delete c;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_sync(mgcr_ctx* c) {
+    ARG_CHECK(c, "ctx is NULL");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_stream(mgcr_ctx* c, void** s) {
+    ARG_CHECK(c && s, "ctx/stream_out is NULL");
+    *s = (void*)c->stream;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_launch_count(mgcr_ctx* c, int64_t* n) {
+    ARG_CHECK(c && n, "ctx/count_out is NULL");
+    *n = c->launches;
+    return MGCR_OK;
+}
+
+enum { PROF_POOL_PAIRS = 8192 };
+
+static void prof_drain(mgcr_ctx* c) {
+    if (c->prof_pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (const ProfPending& p : c->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->prof_events[2 * p.ev], c->prof_events[2 * p.ev + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        ProfEntry& e = c->prof[p.name];
+        e.ms += ms; e.calls++; e.bytes += p.bytes;
+    }
+    c->prof_pending.clear();
+}
+
+void prof_begin(mgcr_ctx* c, const char* name, double bytes) {
+    if ((int)c->prof_pending.size() >= PROF_POOL_PAIRS) prof_drain(c);
+    int idx = (int)c->prof_pending.size();
+    while ((int)c->prof_events.size() < 2 * (idx + 1)) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->prof_events.push_back(e);
+    }
+    c->prof_pending.push_back({name, bytes, idx});
+    cudaEventRecord(c->prof_events[2 * idx], c->stream);
+}
+
+void prof_end(mgcr_ctx* c) {
+    int idx = c->prof_pending.back().ev;
+    cudaEventRecord(c->prof_events[2 * idx + 1], c->stream);
+}
+
+extern "C" int mgcr_ctx_set_profile(mgcr_ctx* c, int enabled) {
+    ARG_CHECK(c, "ctx is NULL");
+    prof_drain(c);
+    c->profile = enabled != 0;
+    c->prof.clear();
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_get_profile(mgcr_ctx* c, int cap, const char** names, double* ms, int64_t* calls, double* bytes, int* n_out) {
+    ARG_CHECK(c && n_out, "ctx/n_out is NULL");
+    prof_drain(c);
+    int i = 0;
+    for (auto& kv : c->prof) {
+        if (i < cap) {
+            if (names) names[i] = kv.first.c_str();
+            if (ms) ms[i] = kv.second.ms;
+            if (calls) calls[i] = kv.second.calls;
+            if (bytes) bytes[i] = kv.second.bytes;
+        }
+        i++;
+    }
+    *n_out = i;
+    return MGCR_OK;
+}

@@ -1,0 +1,158 @@
+// csrc/dist.cu -- multi-GPU plumbing: one process per GPU, NCCL over NVLink for exactly two things, the per-level
+// halo exchange (send/recv pairs in one group) and the scalar inner-product all-reduce.  Nothing in the reference
+// corresponds to this file (it is single-process); the partition follows SURVEY.md 8(e): contiguous row slabs along
+// the slowest mesh index.  NCCL is bound at run time (dlopen) so that single-GPU use has no NCCL dependency.
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+// minimal NCCL ABI (stable across 2.x): the types below match nccl.h
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclSuccess_ = 0 };
+enum { ncclInt8_ = 0, ncclChar_ = 0, ncclInt64_ = 4, ncclFloat64_ = 8 };
+enum { ncclSum_ = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.lib) return MGCR_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);   // resolves to an already loaded copy (e.g. torch's) when there is one
+        if (lib) break;
+    }
+    if (!lib) { mgcr_set_error("NCCL not found: %s", dlerror()); return MGCR_ERR_NCCL; }
+#define BIND(field, sym)                                                                          \
+    *(void**)(&g_nccl.field) = dlsym(lib, sym);                                                   \
+    if (!g_nccl.field) { mgcr_set_error("NCCL symbol %s missing", sym); return MGCR_ERR_NCCL; }
+    BIND(GetUniqueId, "ncclGetUniqueId");
+    BIND(CommInitRank, "ncclCommInitRank");
+    BIND(CommDestroy, "ncclCommDestroy");
+    BIND(AllReduce, "ncclAllReduce");
+    BIND(AllGather, "ncclAllGather");
+    BIND(Send, "ncclSend");
+    BIND(Recv, "ncclRecv");
+    BIND(GroupStart, "ncclGroupStart");
+    BIND(GroupEnd, "ncclGroupEnd");
+    BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+    g_nccl.lib = lib;
+    return MGCR_OK;
+}
+
+#define NCCL_TRY(expr)                                                                            \
+    do {                                                                                          \
+        ncclResult_t r__ = (expr);                                                                \
+        if (r__ != ncclSuccess_) {                                                                \
+            mgcr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(r__)); \
+            return MGCR_ERR_NCCL;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+extern "C" int mgcr_nccl_unique_id(void* h_id128) {
+    ARG_CHECK(h_id128, "mgcr_nccl_unique_id: NULL buffer");
+    MGCR_TRY(nccl_load());
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(h_id128, &id, 128);
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_init_dist(mgcr_ctx* ctx, int rank, int nranks, const void* h_id128) {
+    ARG_CHECK(ctx && nranks >= 1 && rank >= 0 && rank < nranks, "mgcr_ctx_init_dist: bad rank %d / %d", rank, nranks);
+    ARG_CHECK(ctx->nccl_comm == nullptr, "mgcr_ctx_init_dist: already initialised");
+    if (nranks == 1) { ctx->rank = 0; ctx->nranks = 1; return MGCR_OK; }
+    ARG_CHECK(h_id128, "mgcr_ctx_init_dist: NULL id");
+    MGCR_TRY(nccl_load());
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, h_id128, 128);
+    ncclComm_t comm;
+    NCCL_TRY(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    ctx->nccl_comm = comm; ctx->rank = rank; ctx->nranks = nranks;
+    return MGCR_OK;
+}
+
+void dist_destroy(mgcr_ctx* ctx) {
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+}
+
+extern "C" int mgcr_ctx_rank(mgcr_ctx* ctx, int* rank, int* nranks) {
+    ARG_CHECK(ctx, "ctx is NULL");
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    return MGCR_OK;
+}
+
+int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
+    if (ctx->nranks == 1) return MGCR_OK;
+    ctx->launches++;
+    NCCL_TRY(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat64_, ncclSum_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
+    ARG_CHECK(ctx && d_buf && n >= 0, "mgcr_allreduce_sum: bad argument");
+    return dist_allreduce_sum(ctx, d_buf, n);
+}
+
+int dist_group_begin(mgcr_ctx* ctx) {
+    if (ctx->nranks == 1) return MGCR_OK;
+    NCCL_TRY(g_nccl.GroupStart());
+    return MGCR_OK;
+}
+int dist_group_end(mgcr_ctx* ctx) {
+    if (ctx->nranks == 1) return MGCR_OK;
+    ctx->launches++;
+    NCCL_TRY(g_nccl.GroupEnd());
+    return MGCR_OK;
+}
+int dist_send(mgcr_ctx* ctx, const void* d_send, size_t bytes, int peer, cudaStream_t stream) {
+    NCCL_TRY(g_nccl.Send(d_send, bytes, ncclChar_, peer, (ncclComm_t)ctx->nccl_comm, stream));
+    return MGCR_OK;
+}
+int dist_recv(mgcr_ctx* ctx, void* d_recv, size_t bytes, int peer, cudaStream_t stream) {
+    NCCL_TRY(g_nccl.Recv(d_recv, bytes, ncclChar_, peer, (ncclComm_t)ctx->nccl_comm, stream));
+    return MGCR_OK;
+}
+
+// every rank contributes one int64, all get the list (setup-time metadata: slab offsets, counts)
+int dist_allgather_host_i64(mgcr_ctx* ctx, int64_t mine, std::vector<int64_t>& all) {
+    all.assign((size_t)ctx->nranks, mine);
+    if (ctx->nranks == 1) return MGCR_OK;
+    int64_t* d = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)ctx->nranks + 1, &d));
+    CUDA_TRY(cudaMemcpyAsync(d + ctx->nranks, &mine, 8, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(g_nccl.AllGather(d + ctx->nranks, d, 1, ncclInt64_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d, 8 * (size_t)ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return dev_free(ctx, d);
+}
+
+// contiguous slabs of [0, n) in units of `align`; the first (n/align) % nranks ranks get one unit more
+extern "C" int mgcr_slab_range(int64_t n, int64_t align, int rank, int nranks, int64_t* begin, int64_t* end) {
+    ARG_CHECK(begin && end && nranks >= 1 && rank >= 0 && rank < nranks && align >= 1, "mgcr_slab_range: bad argument");
+    ARG_CHECK(n % align == 0, "mgcr_slab_range: extent %lld is not a multiple of the aggregate size %lld", (long long)n, (long long)align);
+    int64_t units = n / align, q = units / nranks, rem = units % nranks;
+    int64_t b = (int64_t)rank * q + (rank < rem ? rank : rem);
+    int64_t e = b + q + (rank < rem ? 1 : 0);
+    *begin = b * align; *end = e * align;
+    return MGCR_OK;
+}

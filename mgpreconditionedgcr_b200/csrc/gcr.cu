@@ -1,0 +1,332 @@
+// csrc/gcr.cu -- GCR<num_type> (reference: src/GCR.h:158-302) driven from the host with every
+// vector and every scalar (alpha, beta, norms) resident on the device.  Per iteration: 4 fused kernels + the operator
+// apply, one 8-byte read-back for the stopping test that overlaps with the direction update.
+#include <math.h>
+
+#include <algorithm>
+
+#include "kernels_blas.cuh"
+#include "ops.cuh"
+
+int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out);
+int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out);
+int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a);
+
+struct GcrOp : mgcr_op {
+    mgcr_op* A = nullptr;
+    mgcr_gcr_param prm;
+    mgcr_op* right = nullptr;
+    c128* d_rand2 = nullptr;   // cached init_rand(2) start vector (src/GCR.h:63-68)
+    ~GcrOp() override { dev_free(ctx, d_rand2); }
+    int apply(const c128* x, c128* y) override;
+};
+
+template <int NH>
+static void launch_dot_hist(mgcr_ctx* ctx, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
+                            int std_conj, double* out) {
+    k_gcr_dot_hist<NH><<<grid, RED_THREADS, 0, ctx->stream>>>(n, Ar, Aps, stride, hl, std_conj, out, ctx->d_partials, ctx->d_ticket);
+}
+template <int NH>
+static void launch_update_p(mgcr_ctx* ctx, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
+                            int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
+                            int bden_off, double* scal) {
+    k_gcr_update_p<NH><<<grid, RED_THREADS, 0, ctx->stream>>>(n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
+                                                            bden_off, scal, ctx->d_partials, ctx->d_ticket);
+}
+
+static int pick_nh(int count) {
+    if (count <= 0) return 0;
+    if (count <= 1) return 1;
+    if (count <= 2) return 2;
+    if (count <= 4) return 4;
+    if (count <= 8) return 8;
+    return 16;
+}
+
+// stack of pinned read-back slots / events so that nested solves (preconditioners) never share one
+struct SolveSlot { double* h; cudaEvent_t ev; };
+static int acquire_slot(mgcr_ctx* ctx, int depth, SolveSlot* s) {
+    ARG_CHECK(depth < 12, "GCR: solver nesting deeper than 12");
+    static thread_local std::map<std::pair<mgcr_ctx*, int>, cudaEvent_t> events;
+    auto key = std::make_pair(ctx, depth);
+    auto it = events.find(key);
+    if (it == events.end()) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        it = events.emplace(key, e).first;
+    }
+    s->ev = it->second;
+    s->h = ctx->h_pinned + 16 + 8 * depth;
+    return MGCR_OK;
+}
+
+static thread_local int g_depth = 0;
+struct DepthGuard { DepthGuard() { g_depth++; } ~DepthGuard() { g_depth--; } };
+
+int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* right, const c128* rhs, c128* x, double* hist,
+              int hist_cap, int* iters_out) {
+    const int64_t n = A->n_local;
+    ARG_CHECK(prm->truncation == 0 || prm->restart == 0, "Do not support concurrent restarting and truncation. (src/GCR.h:165)");
+    ARG_CHECK(prm->truncation >= 0 && prm->restart >= 0 && prm->max_iter >= 0, "GCR: negative parameter");
+    if (prm->truncation == 0 && prm->restart == 0 && prm->verbose) printf("WARNING: Full GCR solve could incur high memory usage!\n");
+    int storage = prm->max_iter, restart = prm->max_iter;
+    if (prm->truncation != 0) storage = prm->truncation;
+    if (prm->restart != 0) { restart = prm->restart; storage = restart; }
+    if (storage < 1) storage = 1;   // max_iter = 0 (one smoothing step): the reference writes slot 0 of a 0-length array
+    if (restart < 1) restart = 1;
+    const bool aliased = (rhs == x);
+    const int std_conj = prm->std_conj;
+    DepthGuard dg;
+    SolveSlot slot;
+    MGCR_TRY(acquire_slot(ctx, g_depth - 1, &slot));
+
+    c128 *r = nullptr, *Ar = nullptr, *z = nullptr, *ps = nullptr, *Aps = nullptr, *acc_p = nullptr, *acc_Ap = nullptr;
+    double* scal = nullptr;
+    const int64_t stride = n;
+    const int bden_off = S_BNUM + 2 * storage;
+    const int nscal = bden_off + storage;
+    int st = MGCR_OK;
+    auto cleanup = [&]() {
+        dev_free(ctx, r); dev_free(ctx, Ar); dev_free(ctx, z); dev_free(ctx, ps); dev_free(ctx, Aps);
+        dev_free(ctx, acc_p); dev_free(ctx, acc_Ap); dev_free(ctx, scal);
+    };
+#define GTRY(expr) do { st = (expr); if (st != MGCR_OK) { cleanup(); return st; } } while (0)
+#define GCUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { mgcr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); cleanup(); return MGCR_ERR_CUDA; } } while (0)
+    GTRY(dev_alloc_t(ctx, (size_t)n, &r));
+    GTRY(dev_alloc_t(ctx, (size_t)n, &Ar));
+    if (right) GTRY(dev_alloc_t(ctx, (size_t)n, &z));
+    GTRY(dev_alloc_t(ctx, (size_t)n * storage, &ps));
+    GTRY(dev_alloc_t(ctx, (size_t)n * storage, &Aps));
+    if (storage > GCR_CHUNK) { GTRY(dev_alloc_t(ctx, (size_t)n, &acc_p)); GTRY(dev_alloc_t(ctx, (size_t)n, &acc_Ap)); }
+    GTRY(dev_alloc_t(ctx, (size_t)nscal, &scal));
+    GCUDA(cudaMemsetAsync(scal, 0, sizeof(double) * nscal, ctx->stream));
+
+    const int grid = stream_grid(ctx, n, 4, 2);
+    // r = rhs ; p = z = R(r) or r ; Ap = A p                                                   (GCR.h:189-192)
+    if (n) GCUDA(cudaMemcpyAsync(r, rhs, sizeof(c128) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (right) GTRY(right->apply(r, ps)); else if (n) GCUDA(cudaMemcpyAsync(ps, r, sizeof(c128) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    GTRY(A->apply(ps, Aps));
+    KLAUNCH(ctx, "gcr_init", 32. * n, (k_gcr_init<<<grid, RED_THREADS, 0, ctx->stream>>>(n, r, Aps, std_conj, ctx->d_partials, ctx->d_ticket, scal)));
+    GCUDA(cudaGetLastError());
+    GTRY(dist_allreduce_sum(ctx, scal, 4));
+    GCUDA(cudaMemcpyAsync(slot.h, scal + S_BB, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GCUDA(cudaStreamSynchronize(ctx->stream));
+    double bb = slot.h[0];
+    double rr = bb;
+    if (hist && hist_cap > 0) hist[0] = sqrt(rr) / sqrt(bb);
+    if (prm->verbose) printf("Step %d residual norm = %.10e\n", 0, sqrt(rr) / sqrt(bb));
+
+    int iter = 0, g = 0, cur = 0;
+    do {
+        g++; iter++;
+        // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
+        KLAUNCH(ctx, "gcr_update_xr", 96. * n, (k_gcr_update_xr<<<grid, RED_THREADS, 0, ctx->stream>>>(n, ps + (int64_t)cur * stride, Aps + (int64_t)cur * stride, x, r,
+                                                                                          scal, bden_off + cur, ctx->d_partials, ctx->d_ticket)));
+        GCUDA(cudaGetLastError());
+        if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
+            KLAUNCH(ctx, "vec_norm2", 16. * n, (k_norm2<<<grid, RED_THREADS, 0, ctx->stream>>>(n, x, ctx->d_partials, ctx->d_ticket, scal + S_BB)));
+            GCUDA(cudaGetLastError());
+            GTRY(dist_allreduce_sum(ctx, scal + S_BB, 1));
+        }
+        const bool final_iter = (g >= prm->max_iter);   // nothing after the x update is observable on the last pass
+        const c128* zz = r;
+        int lim = 0;
+        if (!final_iter) {
+            if (right) { GTRY(right->apply(r, z)); zz = z; }                                      // flexible form of GCR.h:236-238
+            GTRY(A->apply(zz, Ar));                                                               // GCR.h:242
+            lim = std::min(storage, iter);                                                        // GCR.h:251
+            for (int c0 = 0; c0 < lim; c0 += GCR_CHUNK) {                                         // GCR.h:257-258 numerators
+                HistList hl; hl.count = std::min((int)GCR_CHUNK, lim - c0);
+                for (int k = 0; k < hl.count; k++) hl.slot[k] = c0 + k;
+                double* out = scal + S_BNUM + 2 * c0;
+                ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + hl.count));
+                switch (pick_nh(hl.count)) {
+                    case 1: launch_dot_hist<1>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
+                    case 2: launch_dot_hist<2>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
+                    case 4: launch_dot_hist<4>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
+                    case 8: launch_dot_hist<8>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
+                    default: launch_dot_hist<16>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
+                }
+            }
+            GCUDA(cudaGetLastError());
+        }
+        GTRY(dist_allreduce_sum(ctx, scal + S_RR, 1 + 2 * lim));
+        GCUDA(cudaMemcpyAsync(slot.h, scal + S_BB, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        GCUDA(cudaEventRecord(slot.ev, ctx->stream));
+        if (!final_iter) {
+            // p = z + p_corr, Ap = Ar + Ap_corr into the ring slot, next alpha's inner products          (GCR.h:259-266, 277-287)
+            int next_iter = (iter % restart == 0) ? 0 : iter;
+            int new_slot = next_iter % storage;
+            int nchunks = std::max(1, (lim + GCR_CHUNK - 1) / GCR_CHUNK);
+            for (int c = 0; c < nchunks; c++) {
+                BetaList bl; bl.count = std::min((int)GCR_CHUNK, lim - c * GCR_CHUNK);
+                if (bl.count < 0) bl.count = 0;
+                for (int k = 0; k < bl.count; k++) { bl.slot[k] = c * GCR_CHUNK + k; bl.num_index[k] = c * GCR_CHUNK + k; }
+                int first = (c == 0), last = (c == nchunks - 1);
+                ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * bl.count + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0)));
+                switch (pick_nh(bl.count)) {
+                    case 0: launch_update_p<0>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
+                    case 1: launch_update_p<1>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
+                    case 2: launch_update_p<2>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
+                    case 4: launch_update_p<4>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
+                    case 8: launch_update_p<8>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
+                    default: launch_update_p<16>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
+                }
+            }
+            GCUDA(cudaGetLastError());
+            GTRY(dist_allreduce_sum(ctx, scal + S_ANUM, 3));
+            iter = next_iter;
+            cur = new_slot;
+        }
+        GCUDA(cudaEventSynchronize(slot.ev));
+        if (aliased) bb = slot.h[0];
+        rr = slot.h[1];
+        if (hist && g < hist_cap) hist[g] = sqrt(rr) / sqrt(bb);
+        if (prm->verbose) printf("Step %d residual norm = %.10e\n", g, sqrt(rr) / sqrt(bb));   // GCR.h:271
+    } while ((rr / bb) > prm->tol * prm->tol && g < prm->max_iter);                               // GCR.h:288
+    if (prm->verbose) {
+        if (g == prm->max_iter) printf("GCR did not converge after %d steps! Residual norm = %.10e\n", prm->max_iter, sqrt(rr) / sqrt(bb));
+        else printf("GCR converged after %d steps. Residual norm=%.10e\n", g, sqrt(rr) / sqrt(bb));
+    }
+    if (iters_out) *iters_out = g;
+    cleanup();
+#undef GTRY
+#undef GCUDA
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, const mgcr_c128* rhs,
+                              mgcr_c128* x, double* hist, int hist_cap, int* iters) {
+    ARG_CHECK(ctx && A && prm && rhs && x, "mgcr_gcr_solve: NULL argument");
+    if (left) { mgcr_set_error("mgcr_gcr_solve: left preconditioning (src/GCR.h:201-204,245-247) is not provided"); return MGCR_ERR_UNSUPPORTED; }
+    ARG_CHECK(!right || right->n_local == A->n_local, "x dimension does not match with Operator! (src/GCR.h:161)");
+    return gcr_solve(ctx, A, prm, right, (const c128*)rhs, (c128*)x, hist, hist_cap, iters);
+}
+
+extern "C" int mgcr_gcr_solve_host(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right,
+                                   const mgcr_c128* h_rhs, mgcr_c128* h_x, double* hist, int hist_cap, int* iters) {
+    ARG_CHECK(ctx && A && prm && h_rhs && h_x, "mgcr_gcr_solve_host: NULL argument");
+    const int64_t n = A->n_local;
+    c128 *d_rhs = nullptr, *d_x = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)n, &d_rhs));
+    int st = dev_alloc_t(ctx, (size_t)n, &d_x);
+    if (st == MGCR_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_rhs, h_rhs, sizeof(c128) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, h_x, sizeof(c128) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { mgcr_set_error("solve_host upload: %s", cudaGetErrorString(e)); st = MGCR_ERR_CUDA; }
+    }
+    if (st == MGCR_OK) st = mgcr_gcr_solve(ctx, A, prm, left, right, (const mgcr_c128*)d_rhs, (mgcr_c128*)d_x, hist, hist_cap, iters);
+    if (st == MGCR_OK) {
+        cudaError_t e = cudaMemcpyAsync(h_x, d_x, sizeof(c128) * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { mgcr_set_error("solve_host download: %s", cudaGetErrorString(e)); st = MGCR_ERR_CUDA; }
+    }
+    dev_free(ctx, d_rhs); dev_free(ctx, d_x);
+    return st;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// GCR as an Operator (src/GCR.h:19, 62-68)
+// ----------------------------------------------------------------------------------------------------------
+int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d_out);
+
+int GcrOp::apply(const c128* x, c128* y) {
+    ARG_CHECK(x != y, "operator apply: input and output alias");
+    if (prm.zero_guess) {
+        CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(c128) * n_local, ctx->stream));
+    } else {
+        if (!d_rand2) {
+            MGCR_TRY(dev_alloc_t(ctx, (size_t)n_local, &d_rand2));
+            int64_t skip = 0;
+            if (ctx->nranks > 1) {   // this rank's slice of the global init_rand(2) stream
+                std::vector<int64_t> all;
+                MGCR_TRY(dist_allgather_host_i64(ctx, n_local, all));
+                for (int rnk = 0; rnk < ctx->rank; rnk++) skip += all[rnk];
+            }
+            MGCR_TRY(vec_init_rand_slab(ctx, 2, skip, n_local, d_rand2));
+        }
+        CUDA_TRY(cudaMemcpyAsync(y, d_rand2, sizeof(c128) * n_local, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    mgcr_gcr_param p = prm;
+    p.verbose = prm.verbose;
+    return gcr_solve(ctx, A, &p, right, x, y, nullptr, 0, nullptr);
+}
+
+extern "C" int mgcr_gcr_op_create(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, mgcr_op** out) {
+    ARG_CHECK(ctx && A && prm && out, "mgcr_gcr_op_create: NULL argument");
+    if (left) { mgcr_set_error("mgcr_gcr_op_create: left preconditioning is not provided"); return MGCR_ERR_UNSUPPORTED; }
+    GcrOp* op = new GcrOp();
+    op->kind = OP_GCR; op->ctx = ctx; op->A = A; op->prm = *prm; op->right = right;
+    op->n_local = A->n_local; op->n_global = A->n_global;
+    *out = op;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_gcr_op_retarget(mgcr_op* gcr, mgcr_op* A) {
+    ARG_CHECK(gcr && A && gcr->kind == OP_GCR, "mgcr_gcr_op_retarget: not a GCR operator");
+    GcrOp* op = static_cast<GcrOp*>(gcr);
+    if (op->n_local != A->n_local) { dev_free(op->ctx, op->d_rand2); op->d_rand2 = nullptr; }
+    op->A = A; op->n_local = A->n_local; op->n_global = A->n_global;
+    return MGCR_OK;
+}
+
+// glibc rand() stream of Field::init_rand(seed), elements [skip, skip+n)
+int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d_out) {
+    if (n == 0) return MGCR_OK;
+    c128* h = nullptr;
+    CUDA_TRY(cudaMallocHost(&h, sizeof(c128) * (size_t)n));
+    srand(seed);
+    for (int64_t i = 0; i < 2 * skip; i++) (void)rand();
+    for (int64_t i = 0; i < n; i++) {
+        double im = (rand() % 2000) / 1000. - 1;
+        double re = (rand() % 2000) / 1000. - 1;
+        h[i] = cmake(re, im);
+    }
+    cudaError_t e = cudaMemcpyAsync(d_out, h, sizeof(c128) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(h);
+    CUDA_TRY(e);
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Arnoldi::solve -- near-null vectors by inverse iteration (src/MG.h:90-122; tmp zero-initialised, Q7)
+// ----------------------------------------------------------------------------------------------------------
+int arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* ep, int n_vec, c128* vecs) {
+    const int64_t n = A->n_local;
+    c128* b = vecs;
+    int64_t skip = 0;
+    if (ctx->nranks > 1) {
+        std::vector<int64_t> all;
+        MGCR_TRY(dist_allgather_host_i64(ctx, n, all));
+        for (int rnk = 0; rnk < ctx->rank; rnk++) skip += all[rnk];
+    }
+    MGCR_TRY(vec_init_rand_slab(ctx, 9, skip, n, b));                     // MG.h:96
+    mgcr_gcr_param p = *ep;
+    p.verbose = 0;
+    for (int i = 0; i < 10; i++) {                                        // MG.h:100-104
+        MGCR_TRY(gcr_solve(ctx, A, &p, nullptr, b, b, nullptr, 0, nullptr));
+        MGCR_TRY(vec_normalise(ctx, n, b));
+    }
+    const int grid = stream_grid(ctx, n, 8);
+    for (int c = 1; c < n_vec; c++) {                                     // MG.h:110-121
+        c128* tmp = vecs + (int64_t)c * n;
+        CUDA_TRY(cudaMemsetAsync(tmp, 0, sizeof(c128) * n, ctx->stream));
+        MGCR_TRY(gcr_solve(ctx, A, &p, nullptr, vecs + (int64_t)(c - 1) * n, tmp, nullptr, 0, nullptr));
+        for (int j = 0; j < c; j++) {
+            const c128* ej = vecs + (int64_t)j * n;
+            MGCR_TRY(vec_dot_dev(ctx, n, ej, tmp, ctx->d_scratch + 16));
+            if (n) {
+                KLAUNCH(ctx, "vec_axpy", 48. * n, (k_axpy_devscal<<<grid, RED_THREADS, 0, ctx->stream>>>(n, ctx->d_scratch + 16, -1., ej, tmp, tmp)));
+                CHECK_LAUNCH();
+            }
+        }
+        MGCR_TRY(vec_normalise(ctx, n, tmp));
+    }
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* eigen, int n_vec, mgcr_c128* d_vecs) {
+    ARG_CHECK(ctx && A && eigen && d_vecs && n_vec >= 1, "mgcr_arnoldi: bad argument");
+    return arnoldi(ctx, A, eigen, n_vec, (c128*)d_vecs);
+}

@@ -1,0 +1,480 @@
+// csrc/ops.cu -- operator applies: sliced-ELL SpMV (Sparse::operator(), src/Operator.h:330-346), fused DiracOp
+// (src/Operator.h:569-574), matrix-free hopping stencil, block-CSR coarse operator (src/HierarchicalSparse.h:101-161).
+#include <algorithm>
+
+#include "kernels_blas.cuh"
+#include "ops.cuh"
+
+// ----------------------------------------------------------------------------------------------------------
+// sliced-ELL SpMV: one thread per row, one warp per slice; lane l streams val/col at base + j*32 + l (coalesced),
+// gathers x through L1/L2 and accumulates in CSR order.  DIRAC fuses y = diag.x - k (D x).
+// ----------------------------------------------------------------------------------------------------------
+template <bool DIRAC>
+__global__ void __launch_bounds__(256) k_sell_spmv(int64_t nrow, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
+                                                   const c128* __restrict__ val, const c128* __restrict__ x, const c128* __restrict__ ghost,
+                                                   int64_t n_local, c128 k, const double* __restrict__ diag, c128* __restrict__ y) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t slice = row >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slice * 32 >= nrow) return;
+    const int64_t base = __ldg(slice_ptr + slice);
+    const int width = (int)((__ldg(slice_ptr + slice + 1) - base) >> 5);
+    c128 sum = cmake(0., 0.);
+    const int32_t* cp = col + base + lane;
+    const c128* vp = val + base + lane;
+#pragma unroll 4
+    for (int j = 0; j < width; j++) {
+        const int32_t c = __ldg(cp + (int64_t)j * 32);
+        const c128 v = ld_stream(vp + (int64_t)j * 32);
+        const c128 xv = (c < n_local) ? __ldg(x + c) : __ldg(ghost + (c - n_local));
+        sum = cadd(sum, cmul(v, xv));
+    }
+    if (row < nrow) {
+        if (DIRAC) {
+            c128 xr = __ldg(x + row);
+            if (diag) { double d = __ldg(diag + row); xr = cmake(d * xr.x, d * xr.y); }
+            sum = csub(xr, cmul(k, sum));
+        }
+        st_stream(y + row, sum);
+    }
+}
+
+SellOp::~SellOp() {
+    dev_free(ctx, d_slice_ptr); dev_free(ctx, d_col); dev_free(ctx, d_val);
+    halo_free(ctx, halo);
+}
+
+static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, const double* diag) {
+    mgcr_ctx* ctx = op->ctx;
+    ARG_CHECK(x != y, "operator apply: input and output alias");
+    const c128* ghost = nullptr;
+    if (op->halo) { MGCR_TRY(halo_exchange(ctx, op->halo, x)); ghost = op->halo->d_ghost; }
+    if (op->nrow == 0) return MGCR_OK;
+    int grid = (int)((op->nslices * 32 + 255) / 256);
+    if (dirac)
+        KLAUNCH(ctx, "sell_dirac", op->apply_bytes(), (k_sell_spmv<true><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, y)));
+    else
+        KLAUNCH(ctx, "sell_spmv", op->apply_bytes(), (k_sell_spmv<false><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, y)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+int SellOp::apply(const c128* x, c128* y) { return sell_launch(this, x, y, false, cmake(0., 0.), nullptr); }
+int SellOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag) { return sell_launch(this, x, y, true, k, diag); }
+
+// host CSR (int64) -> device sliced-ELL.  `ncol_local`: columns < ncol_local address x, the rest the ghost buffer.
+int sell_build(mgcr_ctx* ctx, int64_t nrow, int64_t ncol_addressable, const int64_t* row, const int64_t* col, const mgcr_c128* val, SellOp* op) {
+    ARG_CHECK(ncol_addressable < (int64_t)INT32_MAX, "CSR upload: %lld addressable columns exceed the int32 device index (shard the operator)", (long long)ncol_addressable);
+    int64_t nslices = (nrow + 31) / 32;
+    std::vector<int64_t> sp((size_t)nslices + 1, 0);
+    for (int64_t s = 0; s < nslices; s++) {
+        int64_t w = 0;
+        for (int64_t r = s * 32; r < std::min(nrow, s * 32 + 32); r++) {
+            ARG_CHECK(row[r + 1] >= row[r], "CSR upload: row offsets decrease at row %lld", (long long)r);
+            w = std::max(w, row[r + 1] - row[r]);
+        }
+        sp[s + 1] = sp[s] + 32 * w;
+    }
+    int64_t np = sp[nslices];
+    int32_t* hcol = nullptr; c128* hval = nullptr;
+    hcol = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
+    hval = (c128*)malloc(sizeof(c128) * (size_t)std::max<int64_t>(np, 1));
+    if (!hcol || !hval) { free(hcol); free(hval); mgcr_set_error("CSR upload: host staging allocation failed"); return MGCR_ERR_OOM; }
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t s = 0; s < nslices; s++) {
+        int64_t w = (sp[s + 1] - sp[s]) / 32;
+        for (int l = 0; l < 32; l++) {
+            int64_t r = s * 32 + l;
+            int64_t b = r < nrow ? row[r] : 0, e = r < nrow ? row[r + 1] : 0;
+            for (int64_t j = 0; j < w; j++) {
+                int64_t dst = sp[s] + j * 32 + l;
+                if (b + j < e) {
+                    int64_t c = col[b + j];
+                    if (c < 0 || c >= ncol_addressable) { bad = 1; c = 0; }
+                    hcol[dst] = (int32_t)c;
+                    hval[dst] = cmake(val[b + j].re, val[b + j].im);
+                } else {
+                    hcol[dst] = 0;
+                    hval[dst] = cmake(0., 0.);
+                }
+            }
+        }
+    }
+    if (bad) { free(hcol); free(hval); mgcr_set_error("CSR upload: column index out of range (src/Operator.h:332 asserts f.field_size() == dim)"); return MGCR_ERR_ARG; }
+    op->nrow = nrow; op->nnz = row[nrow]; op->nnz_padded = np; op->nslices = nslices;
+    int st = dev_alloc_t(ctx, (size_t)nslices + 1, &op->d_slice_ptr);
+    if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)np, &op->d_col);
+    if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)np, &op->d_val);
+    if (st == MGCR_OK) {
+        cudaError_t e = cudaMemcpyAsync(op->d_slice_ptr, sp.data(), sizeof(int64_t) * (nslices + 1), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && np) e = cudaMemcpyAsync(op->d_col, hcol, sizeof(int32_t) * np, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && np) e = cudaMemcpyAsync(op->d_val, hval, sizeof(c128) * np, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { mgcr_set_error("CSR upload: %s", cudaGetErrorString(e)); st = MGCR_ERR_CUDA; }
+    }
+    free(hcol); free(hval);
+    return st;
+}
+
+extern "C" int mgcr_csr_create(mgcr_ctx* ctx, int64_t nrow, int64_t ncol, const int64_t* row, const int64_t* col, const mgcr_c128* val, mgcr_op** out) {
+    ARG_CHECK(ctx && out && row && nrow >= 0 && ncol >= 0, "mgcr_csr_create: bad argument");
+    ARG_CHECK(ctx->nranks == 1, "mgcr_csr_create: context is distributed, use mgcr_csr_create_dist");
+    ARG_CHECK(row[nrow] == 0 || (col && val), "mgcr_csr_create: NULL col/val");
+    *out = nullptr;
+    SellOp* op = new SellOp();
+    op->kind = OP_SELL; op->ctx = ctx; op->ncol = ncol; op->n_local = ncol; op->n_global = ncol;
+    int st = sell_build(ctx, nrow, ncol, row, col, val, op);
+    if (st != MGCR_OK) { delete op; return st; }
+    *out = op;
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// matrix-free hopping stencil.  A CTA owns a TX x TY tile of the (n1, n0) plane and marches along n2: the plane
+// being processed sits in shared memory (with its one-element halo ring) for the x/y neighbours, the z neighbours
+// live in registers (prev / cur / next), so every element is read from global memory once per CTA (+ ring).
+// Neighbour sum order = ascending column order of the CSR the reference would hold: z-1, y-1, x-1, x+1, y+1, z+1.
+// ----------------------------------------------------------------------------------------------------------
+enum { HOP_TX = 32, HOP_TY = 16 };
+
+struct HopArgs {
+    int64_t n2, n1, n0;      // local planes, rows, columns
+    int64_t zc;              // planes per z-chunk
+    const c128* x; c128* y;
+    const c128* halo_lo; const c128* halo_hi;   // plane below local z=0 / above z=n2-1 (NULL = Dirichlet)
+    int dirac; c128 k; const double* diag;
+};
+
+__global__ void __launch_bounds__(HOP_TX* HOP_TY) k_hopping(HopArgs a) {
+    __shared__ c128 sp[2][HOP_TY + 2][HOP_TX + 2];
+    const int tx = threadIdx.x % HOP_TX, ty = threadIdx.x / HOP_TX;
+    const int64_t x0 = (int64_t)blockIdx.x * HOP_TX, y0 = (int64_t)blockIdx.y * HOP_TY;
+    const int64_t gx = x0 + tx, gy = y0 + ty;
+    const int64_t zs = (int64_t)blockIdx.z * a.zc;
+    const int64_t ze = min(zs + a.zc, a.n2);
+    const int64_t plane = a.n1 * a.n0;
+    const bool inb = gx < a.n0 && gy < a.n1;
+    const c128 zero = cmake(0., 0.);
+    // halo duties of this thread within a plane: left/right column, bottom/top row
+    const bool hx_on = (tx == 0 && gx >= 1 && gy < a.n1) || (tx == HOP_TX - 1 && gx + 1 < a.n0 && gy < a.n1);
+    const int64_t hx_off = gy * a.n0 + (tx == 0 ? gx - 1 : gx + 1);
+    const bool hy_on = (ty == 0 && gy >= 1 && gx < a.n0) || (ty == HOP_TY - 1 && gy + 1 < a.n1 && gx < a.n0);
+    const int64_t hy_off = (ty == 0 ? gy - 1 : gy + 1) * a.n0 + gx;
+    const int64_t c_off = gy * a.n0 + gx;
+
+    auto plane_ptr = [&](int64_t z) -> const c128* {
+        if (z < 0) return a.halo_lo;
+        if (z >= a.n2) return a.halo_hi;
+        return a.x + z * plane;
+    };
+    const c128* pp = plane_ptr(zs - 1);
+    const c128* pc = plane_ptr(zs);
+    c128 prev = (inb && pp) ? ld_stream(pp + c_off) : zero;
+    c128 cur = inb ? ld_stream(pc + c_off) : zero;
+    c128 hx = hx_on ? ld_stream(pc + hx_off) : zero;
+    c128 hy = hy_on ? ld_stream(pc + hy_off) : zero;
+    for (int64_t z = zs; z < ze; z++) {
+        const c128* pn = plane_ptr(z + 1);
+        const c128 next = (inb && pn) ? ld_stream(pn + c_off) : zero;
+        c128 nhx = zero, nhy = zero;
+        if (z + 1 < ze) {   // ring of the next plane, prefetched one step ahead
+            if (hx_on) nhx = ld_stream(pn + hx_off);
+            if (hy_on) nhy = ld_stream(pn + hy_off);
+        }
+        const int b = (int)((z - zs) & 1);
+        sp[b][ty + 1][tx + 1] = cur;
+        if (tx == 0) sp[b][ty + 1][0] = hx;
+        if (tx == HOP_TX - 1) sp[b][ty + 1][HOP_TX + 1] = hx;
+        if (ty == 0) sp[b][0][tx + 1] = hy;
+        if (ty == HOP_TY - 1) sp[b][HOP_TY + 1][tx + 1] = hy;
+        __syncthreads();
+        if (inb) {
+            c128 s = cadd(prev, sp[b][ty][tx + 1]);
+            s = cadd(s, sp[b][ty + 1][tx]);
+            s = cadd(s, sp[b][ty + 1][tx + 2]);
+            s = cadd(s, sp[b][ty + 2][tx + 1]);
+            s = cadd(s, next);
+            if (a.dirac) {
+                c128 xr = cur;
+                if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
+                s = csub(xr, cmul(a.k, s));
+            }
+            st_stream(a.y + z * plane + c_off, s);
+        }
+        prev = cur; cur = next; hx = nhx; hy = nhy;
+    }
+}
+
+HoppingOp::~HoppingOp() {
+    for (int d = 0; d < 3; d++) dev_free(ctx, d_face[d]);
+    dev_free(ctx, d_halo_lo); dev_free(ctx, d_halo_hi);
+}
+
+int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag) {
+    ARG_CHECK(x != y, "operator apply: input and output alias");
+    HopArgs a;
+    a.n2 = n2_local; a.n1 = gdims[1]; a.n0 = gdims[2];
+    a.x = x; a.y = y; a.dirac = dirac; a.k = k; a.diag = diag;
+    a.halo_lo = nullptr; a.halo_hi = nullptr;
+    const int64_t plane = a.n1 * a.n0;
+    if (ctx->nranks > 1) {
+        // one plane to each slab neighbour (NCCL send/recv on the compute stream)
+        int lo = ctx->rank - 1, hi = ctx->rank + 1;
+        MGCR_TRY(dist_group_begin(ctx));
+        if (lo >= 0) {
+            MGCR_TRY(dist_send(ctx, x, sizeof(c128) * plane, lo, ctx->stream));
+            MGCR_TRY(dist_recv(ctx, d_halo_lo, sizeof(c128) * plane, lo, ctx->stream));
+            a.halo_lo = d_halo_lo;
+        }
+        if (hi < ctx->nranks) {
+            MGCR_TRY(dist_send(ctx, x + (n2_local - 1) * plane, sizeof(c128) * plane, hi, ctx->stream));
+            MGCR_TRY(dist_recv(ctx, d_halo_hi, sizeof(c128) * plane, hi, ctx->stream));
+            a.halo_hi = d_halo_hi;
+        }
+        MGCR_TRY(dist_group_end(ctx));
+    }
+    if (n_local == 0) return MGCR_OK;
+    dim3 grid((unsigned)((a.n0 + HOP_TX - 1) / HOP_TX), (unsigned)((a.n1 + HOP_TY - 1) / HOP_TY), 1);
+    int64_t tiles = (int64_t)grid.x * grid.y;
+    int64_t target = (int64_t)ctx->num_sms * 16;
+    int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(a.n2, (target + tiles - 1) / tiles));
+    a.zc = (a.n2 + nchunks - 1) / nchunks;
+    if (a.zc < 8 && a.n2 >= 8) a.zc = 8;
+    grid.z = (unsigned)((a.n2 + a.zc - 1) / a.zc);
+    ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
+    KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.), (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+int HoppingOp::apply(const c128* x, c128* y) { return run(x, y, 0, cmake(0., 0.), nullptr); }
+int HoppingOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag) { return run(x, y, 1, k, diag); }
+
+extern "C" int mgcr_hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims, const double* const* h_face, mgcr_op** out) {
+    ARG_CHECK(ctx && dims && out, "mgcr_hopping_create: NULL argument");
+    ARG_CHECK(ndim >= 1 && ndim <= 3, "mgcr_hopping_create: ndim must be 1..3 (got %d)", ndim);
+    if (h_face) { mgcr_set_error("mgcr_hopping_create: variable bond coefficients are not available yet"); return MGCR_ERR_UNSUPPORTED; }
+    *out = nullptr;
+    HoppingOp* op = new HoppingOp();
+    op->kind = OP_HOPPING; op->ctx = ctx; op->ndim = ndim;
+    for (int d = 0; d < ndim; d++) {
+        ARG_CHECK(dims[d] >= 1, "mgcr_hopping_create: dims[%d] < 1", d);
+        op->gdims[3 - ndim + d] = dims[d];
+    }
+    int64_t zb = 0, ze = op->gdims[0];
+    if (ctx->nranks > 1) {
+        ARG_CHECK(ndim == 3, "mgcr_hopping_create: the distributed stencil is 3-D (slabs along dims[0])");
+        MGCR_TRY(mgcr_slab_range(op->gdims[0], 1, ctx->rank, ctx->nranks, &zb, &ze));
+        ARG_CHECK(ze > zb, "mgcr_hopping_create: rank %d owns no plane", ctx->rank);
+        int64_t plane = op->gdims[1] * op->gdims[2];
+        int st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_lo);
+        if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_hi);
+        if (st != MGCR_OK) { delete op; return st; }
+    }
+    op->z_begin = zb; op->n2_local = ze - zb;
+    op->n_local = op->n2_local * op->gdims[1] * op->gdims[2];
+    op->n_global = op->gdims[0] * op->gdims[1] * op->gdims[2];
+    *out = op;
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// DiracOp = diag - k D
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) k_dirac_combine(int64_t n, c128 k, const double* __restrict__ diag, const c128* __restrict__ x,
+                                                               c128* y /* in: D x, out: diag.x - k D x */) {
+    GRID_STRIDE(i, n) {
+        c128 xr = ld_stream(x + i);
+        if (diag) { double d = __ldg(diag + i); xr = cmake(d * xr.x, d * xr.y); }
+        st_stream(y + i, csub(xr, cmul(k, ld_plain(y + i))));
+    }
+}
+
+DiracOp::~DiracOp() { dev_free(ctx, d_diag); }
+
+int DiracOp::apply(const c128* x, c128* y) {
+    if (D->kind == OP_SELL) return static_cast<SellOp*>(D)->apply_dirac(x, y, k, d_diag);
+    if (D->kind == OP_HOPPING) return static_cast<HoppingOp*>(D)->apply_dirac(x, y, k, d_diag);
+    MGCR_TRY(D->apply(x, y));
+    if (n_local == 0) return MGCR_OK;
+    KLAUNCH(ctx, "dirac_combine", 48. * n_local, (k_dirac_combine<<<stream_grid(ctx, n_local, 8), RED_THREADS, 0, ctx->stream>>>(n_local, k, d_diag, x, y)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* h_diag, mgcr_op** out) {
+    ARG_CHECK(ctx && D && out, "mgcr_dirac_create: NULL argument");
+    *out = nullptr;
+    DiracOp* op = new DiracOp();
+    op->kind = OP_DIRAC; op->ctx = ctx; op->D = D; op->k = cmake(k_re, k_im);
+    op->n_local = D->n_local; op->n_global = D->n_global;
+    if (h_diag) {
+        int st = dev_alloc_t(ctx, (size_t)op->n_local, &op->d_diag);
+        if (st != MGCR_OK) { delete op; return st; }
+        cudaError_t e = cudaMemcpyAsync(op->d_diag, h_diag, sizeof(double) * op->n_local, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { delete op; mgcr_set_error("dirac diag upload: %s", cudaGetErrorString(e)); return MGCR_ERR_CUDA; }
+    }
+    *out = op;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_dirac_set_k(mgcr_op* op, double k_re, double k_im) {
+    ARG_CHECK(op && op->kind == OP_DIRAC, "mgcr_dirac_set_k: not a DiracOp");
+    static_cast<DiracOp*>(op)->k = cmake(k_re, k_im);
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// block-CSR apply: one thread per (block row R, row r inside the block).  Blocks are stored column-major, so for
+// each column c the ne threads of a block row read ne consecutive c128 -- coalesced -- and the matching x element is
+// a warp-broadcast L1 hit.  Accumulation follows the reference: per block o = sum_c m[r][c] x[c] (sequential), then
+// value += o in block order (HierarchicalSparse.h:135-147 with Dense::operator(), Operator.h:159-173).
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_blockcsr_apply(int64_t nb, int ne, const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+                                                        const c128* __restrict__ bval, const c128* __restrict__ x, const c128* __restrict__ ghost,
+                                                        int64_t nb_local_cols, c128* __restrict__ y) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t R = t / ne;
+    const int r = (int)(t - R * ne);
+    if (R >= nb) return;
+    c128 value = cmake(0., 0.);
+    const int lb = __ldg(brow + R), le = __ldg(brow + R + 1);
+    for (int l = lb; l < le; l++) {
+        const int64_t bc = __ldg(bcol + l);
+        const c128* xb = bc < nb_local_cols ? x + bc * ne : ghost + (bc - nb_local_cols) * ne;
+        const c128* m = bval + (int64_t)l * ne * ne + r;
+        c128 o = cmake(0., 0.);
+#pragma unroll 4
+        for (int c = 0; c < ne; c++) o = cadd(o, cmul(ld_stream(m + (int64_t)c * ne), __ldg(xb + c)));
+        value = cadd(value, o);
+    }
+    st_stream(y + t, value);
+}
+
+BlockCsrOp::~BlockCsrOp() {
+    dev_free(ctx, d_brow); dev_free(ctx, d_bcol); dev_free(ctx, d_bval);
+    halo_free(ctx, halo);
+}
+
+int BlockCsrOp::apply(const c128* x, c128* y) {
+    ARG_CHECK(x != y, "operator apply: input and output alias");
+    const c128* ghost = nullptr;
+    if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x)); ghost = halo->d_ghost; }
+    if (nb == 0) return MGCR_OK;
+    int64_t threads = nb * ne;
+    int grid = (int)((threads + 255) / 256);
+    KLAUNCH(ctx, "blockcsr_apply", apply_bytes(), (k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(nb, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+
+// host block-CSR with ROW-major blocks (the reference's Dense layout) -> device compact column-major
+int blockcsr_build(mgcr_ctx* ctx, int64_t nb, int64_t nb_cols_addressable, int ne, const int64_t* brow, const int64_t* bcol,
+                   const mgcr_c128* bval, BlockCsrOp* op) {
+    ARG_CHECK(nb_cols_addressable * ne < (int64_t)INT32_MAX && brow[nb] < (int64_t)INT32_MAX, "block-CSR upload: index exceeds int32");
+    std::vector<int32_t> hrow((size_t)nb + 1, 0), hcol;
+    std::vector<c128> hval;
+    hcol.reserve((size_t)brow[nb]);
+    hval.reserve((size_t)brow[nb] * ne * ne);
+    const size_t bsz = (size_t)ne * ne;
+    for (int64_t R = 0; R < nb; R++) {
+        for (int64_t l = brow[R]; l < brow[R + 1]; l++) {
+            const mgcr_c128* m = bval + (size_t)l * bsz;
+            bool nz = false;
+            for (size_t q = 0; q < bsz; q++) if (m[q].re != 0. || m[q].im != 0.) { nz = true; break; }
+            if (!nz) continue;
+            ARG_CHECK(bcol[l] >= 0 && bcol[l] < nb_cols_addressable, "block-CSR upload: block column %lld out of range", (long long)bcol[l]);
+            hcol.push_back((int32_t)bcol[l]);
+            size_t base = hval.size();
+            hval.resize(base + bsz);
+            for (int r = 0; r < ne; r++) for (int c = 0; c < ne; c++) hval[base + (size_t)c * ne + r] = cmake(m[(size_t)r * ne + c].re, m[(size_t)r * ne + c].im);
+        }
+        hrow[R + 1] = (int32_t)hcol.size();
+    }
+    op->nb = nb; op->ne = ne; op->nnzb = (int64_t)hcol.size(); op->nb_cols = nb_cols_addressable;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)nb + 1, &op->d_brow));
+    MGCR_TRY(dev_alloc_t(ctx, hcol.size(), &op->d_bcol));
+    MGCR_TRY(dev_alloc_t(ctx, hval.size(), &op->d_bval));
+    CUDA_TRY(cudaMemcpyAsync(op->d_brow, hrow.data(), sizeof(int32_t) * hrow.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!hcol.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(op->d_bcol, hcol.data(), sizeof(int32_t) * hcol.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(op->d_bval, hval.data(), sizeof(c128) * hval.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_blockcsr_create(mgcr_ctx* ctx, int64_t nb, int ne, const int64_t* brow, const int64_t* bcol, const mgcr_c128* bval, mgcr_op** out) {
+    ARG_CHECK(ctx && out && brow && nb >= 0 && ne >= 1, "mgcr_blockcsr_create: bad argument");
+    ARG_CHECK(ctx->nranks == 1, "mgcr_blockcsr_create: single-GPU entry point (distributed coarse operators are built by mgcr_mg_create)");
+    *out = nullptr;
+    BlockCsrOp* op = new BlockCsrOp();
+    op->kind = OP_BLOCKCSR; op->ctx = ctx; op->n_local = nb * ne; op->n_global = nb * ne;
+    int st = blockcsr_build(ctx, nb, nb, ne, brow, bcol, bval, op);
+    if (st != MGCR_OK) { delete op; return st; }
+    *out = op;
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// generic entry points
+// ----------------------------------------------------------------------------------------------------------
+extern "C" int mgcr_op_apply(mgcr_ctx* ctx, mgcr_op* op, const mgcr_c128* x, mgcr_c128* y) {
+    ARG_CHECK(ctx && op && x && y, "mgcr_op_apply: NULL argument");
+    return op->apply((const c128*)x, (c128*)y);
+}
+extern "C" int mgcr_op_dim(mgcr_op* op, int64_t* n_local, int64_t* n_global) {
+    ARG_CHECK(op, "mgcr_op_dim: NULL operator");
+    if (n_local) *n_local = op->n_local;
+    if (n_global) *n_global = op->n_global;
+    return MGCR_OK;
+}
+extern "C" int mgcr_op_apply_bytes(mgcr_op* op, double* bytes) {
+    ARG_CHECK(op && bytes, "mgcr_op_apply_bytes: NULL argument");
+    *bytes = op->apply_bytes();
+    return MGCR_OK;
+}
+extern "C" int mgcr_op_destroy(mgcr_op* op) {
+    if (!op) return MGCR_OK;
+    mgcr_ctx* ctx = op->ctx;
+    delete op;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// ghost exchange for list-based halos (distributed CSR / block-CSR)
+// ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) k_pack(int64_t n_items, int elem, const int32_t* __restrict__ idx, const c128* __restrict__ x,
+                                                      c128* __restrict__ buf) {
+    GRID_STRIDE(t, n_items * elem) {
+        int64_t it = t / elem; int e = (int)(t - it * elem);
+        buf[t] = x[(int64_t)idx[it] * elem + e];
+    }
+}
+
+int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x) {
+    if (!h || h->npeers == 0) return MGCR_OK;
+    int64_t n_send = h->send_off[h->npeers];
+    if (h->d_send_idx && n_send > 0) {
+        KLAUNCH(ctx, "halo_pack", 36. * n_send * h->elem, (k_pack<<<stream_grid(ctx, n_send * h->elem, 4), RED_THREADS, 0, ctx->stream>>>(n_send, h->elem, h->d_send_idx, x, h->d_send_buf)));
+        CHECK_LAUNCH();
+    }
+    MGCR_TRY(dist_group_begin(ctx));
+    for (int p = 0; p < h->npeers; p++) {
+        int64_t ns = h->send_off[p + 1] - h->send_off[p], nr = h->recv_off[p + 1] - h->recv_off[p];
+        if (ns > 0) {
+            const c128* src = h->d_send_idx ? h->d_send_buf + h->send_off[p] * h->elem : x + h->send_start[p] * h->elem;
+            MGCR_TRY(dist_send(ctx, src, sizeof(c128) * ns * h->elem, h->peer[p], ctx->stream));
+        }
+        if (nr > 0) MGCR_TRY(dist_recv(ctx, h->d_ghost + h->recv_off[p] * h->elem, sizeof(c128) * nr * h->elem, h->peer[p], ctx->stream));
+    }
+    MGCR_TRY(dist_group_end(ctx));
+    return MGCR_OK;
+}
+
+void halo_free(mgcr_ctx* ctx, HaloPlan* h) {
+    if (!h) return;
+    dev_free(ctx, h->d_send_idx); dev_free(ctx, h->d_send_buf); dev_free(ctx, h->d_ghost);
+    delete h;
+}

@@ -1,0 +1,87 @@
+// csrc/ops.cuh -- operator objects behind the opaque mgcr_op handle (reference: src/Operator.h:16-29).
+#pragma once
+#include "common.cuh"
+
+enum OpKind { OP_SELL = 1, OP_HOPPING = 2, OP_DIRAC = 3, OP_BLOCKCSR = 4, OP_GCR = 5, OP_MG = 6 };
+
+// Ghost-exchange plan of a row-slab-partitioned operator: which local elements each peer needs from us (pack list)
+// and where what we receive lands in the ghost buffer that the kernels address as column n_local + g.
+struct HaloPlan {
+    int npeers = 0;
+    std::vector<int> peer;            // rank of each peer
+    std::vector<int64_t> send_off;    // [npeers+1] offsets into d_send_idx / d_send_buf (elements)
+    std::vector<int64_t> recv_off;    // [npeers+1] offsets into the ghost buffer (elements)
+    int32_t* d_send_idx = nullptr;    // local indices to pack (NULL when the send range is contiguous)
+    std::vector<int64_t> send_start;  // contiguous case: first local element sent to each peer
+    c128* d_send_buf = nullptr;
+    c128* d_ghost = nullptr;
+    int64_t n_ghost = 0;
+    int elem = 1;                     // c128 per exchanged item (ne for block operators)
+};
+
+struct mgcr_op {
+    OpKind kind;
+    mgcr_ctx* ctx = nullptr;
+    int64_t n_local = 0;    // rows / vector length held by this rank
+    int64_t n_global = 0;
+    virtual ~mgcr_op() {}
+    virtual int apply(const c128* x, c128* y) = 0;
+    virtual double apply_bytes() const { return 0.; }
+};
+
+// Sliced-ELL (slice height 32) image of a CSR matrix: slice s holds rows 32s..32s+31 padded to the longest of them,
+// stored column-major inside the slice so that lane l of a warp reads val[base + j*32 + l] -- every access of the
+// matrix is a full 128-bit-per-lane coalesced request; entries keep their CSR order (src/Operator.h:336-343).
+struct SellOp : mgcr_op {
+    int64_t nrow = 0, ncol = 0, nnz = 0, nnz_padded = 0, nslices = 0;
+    int64_t* d_slice_ptr = nullptr;
+    int32_t* d_col = nullptr;
+    c128* d_val = nullptr;
+    HaloPlan* halo = nullptr;
+    ~SellOp() override;
+    int apply(const c128* x, c128* y) override;
+    int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag);
+    double apply_bytes() const override { return (double)nnz_padded * 20. + (double)(nslices + 1) * 8. + 16. * (double)ncol + 16. * (double)nrow; }
+};
+
+// Matrix-free nearest-neighbour hopping operator on an (n2, n1, n0) Dirichlet lattice, n0 fastest.
+struct HoppingOp : mgcr_op {
+    int ndim = 3;
+    int64_t gdims[3] = {1, 1, 1};   // global (n2, n1, n0), missing leading dims are 1
+    int64_t n2_local = 1, z_begin = 0;
+    double* d_face[3] = {nullptr, nullptr, nullptr};   // optional bond coefficients per dim (z, y, x)
+    c128* d_halo_lo = nullptr; c128* d_halo_hi = nullptr;   // neighbour planes (distributed)
+    ~HoppingOp() override;
+    int apply(const c128* x, c128* y) override;
+    int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag);
+    int run(const c128* x, c128* y, int dirac, c128 k, const double* d_diag);
+    double apply_bytes() const override { return 32. * (double)n_local; }
+};
+
+struct DiracOp : mgcr_op {
+    mgcr_op* D = nullptr;
+    c128 k = {0., 0.};
+    double* d_diag = nullptr;
+    ~DiracOp() override;
+    int apply(const c128* x, c128* y) override;
+    double apply_bytes() const override { return D->apply_bytes() + (d_diag ? 8. * (double)n_local : 0.); }
+};
+
+// Block-CSR of dense ne x ne blocks (src/HierarchicalSparse.h:22-48).  Device compute layout: explicit zero blocks
+// dropped, blocks stored COLUMN-major so that the ne threads of a block row read contiguous memory for each column.
+struct BlockCsrOp : mgcr_op {
+    int64_t nb = 0;       // local block rows
+    int64_t nb_cols = 0;  // block columns addressable (local + ghost)
+    int ne = 0;
+    int64_t nnzb = 0;
+    int32_t* d_brow = nullptr;   // [nb+1]
+    int32_t* d_bcol = nullptr;   // [nnzb]
+    c128* d_bval = nullptr;      // [nnzb][ne(col)][ne(row)]
+    HaloPlan* halo = nullptr;
+    ~BlockCsrOp() override;
+    int apply(const c128* x, c128* y) override;
+    double apply_bytes() const override { return (double)nnzb * (16. * ne * ne + 4.) + 32. * (double)nb * ne; }
+};
+
+int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x);
+void halo_free(mgcr_ctx* ctx, HaloPlan* h);

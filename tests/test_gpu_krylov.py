@@ -1,0 +1,369 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/mgcr_oracle.c) on the same seeded inputs and against the golden vectors the unmodified reference produced
+(tests/golden).  Bars: integer/index outputs bit-exact; element-wise complex arithmetic bit-exact (the library is built
+without FMA contraction and accumulates in CSR order); reductions and everything downstream of them within 1e-10
+relative per residual-history entry, iteration count within +-1, solutions within 1e-8 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+HIST_TOL = 1e-10
+X_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mgpreconditionedgcr_b200 import host
+    c = host.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import pyoracle
+    return pyoracle
+
+
+@pytest.fixture(scope="module")
+def host():
+    from mgpreconditionedgcr_b200 import host
+    return host
+
+
+def check_hist(hist, ref, it, it_ref, tol=HIST_TOL):
+    assert abs(it - it_ref) <= 1, (it, it_ref)
+    m = min(len(hist), len(ref))
+    rel = np.abs(hist[:m] - ref[:m]) / ref[:m]
+    assert rel.max() < tol, "residual history deviates: max rel %.3e at step %d" % (rel.max(), int(rel.argmax()))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Field primitives (src/Fields.h)
+# ------------------------------------------------------------------------------------------------------------
+def test_init_rand_bit_exact(ctx, golden):
+    g = golden.c1_apply
+    for seed in (0, 1, 2, 9, 42):
+        assert np.array_equal(ctx.init_rand(seed, 1024).numpy(), g["rand_seed%d" % seed])
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 257, 3072, 100003, 1 << 21])
+def test_blas1_against_oracle(ctx, orc, n):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    fa, fb = ctx.from_numpy(a), ctx.from_numpy(b)
+    s = 0.37 - 1.21j
+    # element-wise ops: same operations in the same order as the reference -> bit-exact
+    assert np.array_equal((fa + fb).numpy(), a + b)
+    assert np.array_equal((fa - fb).numpy(), a - b)
+    t = np.empty_like(a)
+    t.real = s.real * a.real - s.imag * a.imag
+    t.imag = s.real * a.imag + s.imag * a.real
+    assert np.array_equal((fa * s).numpy(), t)
+    fc = fa.copy()
+    fc += fb
+    assert np.array_equal(fc.numpy(), a + b)
+    fc -= fb
+    assert np.array_equal(fc.numpy(), (a + b) - b)
+    assert np.array_equal(fa.copy().set_constant(2 - 3j).numpy(), np.full(n, 2 - 3j))
+    assert np.array_equal(fa.copy().set_zero().numpy(), np.zeros(n))
+    if n == 0:
+        assert fa.dot(fb) == 0 and fa.squarednorm() == 0
+        return
+    # reductions: fixed-shape tree instead of the reference's left-to-right sum -> rounding-level agreement
+    d, dref = fa.dot(fb), orc.dot(a, b)
+    scale = np.sqrt(orc.squarednorm(a) * orc.squarednorm(b))
+    assert abs(d - dref) <= 1e-14 * scale
+    n2, n2ref = fa.squarednorm(), orc.squarednorm(a)
+    assert abs(n2 - n2ref) <= 1e-14 * n2ref
+    fn = fa.copy().normalise()
+    assert relerr(fn.numpy(), a / np.sqrt(n2ref)) < 1e-14
+    # determinism: the reduction tree is fixed, repeated calls agree to the bit
+    assert fa.dot(fb) == d and fa.squarednorm() == n2
+
+
+def test_dot_and_norm_match_reference_golden(ctx, golden, orc):
+    g = golden.c1_apply
+    f1 = ctx.from_numpy(g["f1"])
+    f5 = ctx.init_rand(5, 3072)
+    d = f1.dot(f5)
+    assert abs(d - complex(g["scalars"][0], g["scalars"][1])) < 1e-13 * abs(d)
+    assert abs(f1.squarednorm() - g["scalars"][2]) < 1e-13 * g["scalars"][2]
+    assert abs(f5.norm() - g["scalars"][3]) < 1e-13 * g["scalars"][3]
+
+
+def test_gamma5_bit_exact(ctx, golden, c1):
+    g = golden.c1_apply
+    out = ctx.from_numpy(g["f1"]).gamma5(c1["dims"], 4).numpy()
+    assert np.array_equal(out, g["gamma5_f1"])
+
+
+@pytest.mark.parametrize("tag,dims,sub", [("bm_4444_s2", [4, 4, 4, 4, 4, 3], 2), ("bm_4444_s1", [4, 4, 4, 4, 4, 3], 1),
+                                          ("bm_8484_s4", [8, 4, 8, 4, 4, 3], 4), ("bm_6666_s3", [6, 6, 6, 6, 4, 3], 3)])
+def test_blocking_bit_exact(ctx, golden, tag, dims, sub):
+    bm, bd = ctx.blocking(dims, [sub] * 4)
+    assert np.array_equal(bm.reshape(-1), golden.blocking[tag])
+
+
+def test_blocking_per_dim_and_errors(ctx, orc):
+    bm, bd = ctx.blocking([1, 16, 8, 12], [1, 4, 2, 3])
+    bo, bdo = orc.blocking([1, 16, 8, 12], [1, 4, 2, 3])
+    assert np.array_equal(bm, bo) and np.array_equal(bd, bdo)
+    with pytest.raises(Exception):
+        ctx.blocking([6, 6, 6, 6, 4, 3], [4] * 4)       # the assert at src/Mesh.h:245
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Operator applies (src/Operator.h)
+# ------------------------------------------------------------------------------------------------------------
+def test_spmv_and_dirac_on_sample_matrix_bit_exact(ctx, host, golden, c1):
+    g = golden.c1_apply
+    D = host.Sparse(ctx, c1["n"], c1["n"], c1["row"], c1["col"], c1["val"])
+    A = host.DiracOp(ctx, D, c1["k"])
+    f1 = ctx.from_numpy(g["f1"])
+    assert np.array_equal(D(f1).numpy(), g["spmv_f1"])
+    assert np.array_equal(A(f1).numpy(), g["dirac_f1"])
+    assert D.get_dim() == 3072 and A.get_dim() == 3072
+
+
+def random_csr(rng, n, max_len, empty_every=0):
+    rows, cols, vals = [0], [], []
+    for i in range(n):
+        ln = 0 if (empty_every and i % empty_every == 0) else int(rng.integers(1, max_len + 1))
+        c = np.sort(rng.choice(n, size=min(ln, n), replace=False))
+        cols += list(c)
+        vals += list(rng.standard_normal(len(c)) + 1j * rng.standard_normal(len(c)))
+        rows.append(len(cols))
+    return np.array(rows, np.int64), np.array(cols, np.int64), np.array(vals, np.complex128)
+
+
+@pytest.mark.parametrize("n,max_len,empty_every", [(1, 1, 0), (33, 5, 0), (300, 9, 7), (1000, 40, 0), (4099, 3, 5)])
+def test_spmv_ragged_rows_against_oracle(ctx, host, orc, n, max_len, empty_every):
+    rng = np.random.default_rng(n)
+    row, col, val = random_csr(rng, n, max_len, empty_every)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    D = host.Sparse(ctx, n, n, row, col, val)
+    Do = orc.csr(n, n, row, col, val)
+    assert np.array_equal(D(x), Do(x))
+    k = 0.3 - 0.2j
+    assert np.array_equal(host.DiracOp(ctx, D, k)(x), orc.dirac(Do, k)(x))
+
+
+def test_spmv_rejects_bad_input(ctx, host):
+    with pytest.raises(Exception):
+        host.Sparse(ctx, 2, 2, [0, 1, 2], [0, 5], [1, 1])          # column out of range
+    D = host.Sparse(ctx, 2, 2, [0, 1, 2], [0, 1], [1, 1])
+    f = ctx.from_numpy(np.ones(2))
+    with pytest.raises(Exception):
+        D(f, out=f)                                                   # aliasing input/output
+
+
+@pytest.mark.parametrize("dims", [[7], [1000], [5, 9], [48, 48], [33, 65], [12, 12, 12], [3, 17, 40], [9, 33, 31], [40, 20, 70]])
+def test_hopping_stencil_equals_stored_operator(ctx, host, orc, dims):
+    """the matrix-free path must reproduce the CSR the reference would hold, to the bit"""
+    n = int(np.prod(dims))
+    x = orc.init_rand(3, n)
+    H = host.Hopping(ctx, dims)
+    Ho = orc.hopping(dims)
+    assert np.array_equal(H(x), Ho(x))
+    k = 1.0 / (2 * len(dims) + 0.01)
+    assert np.array_equal(host.DiracOp(ctx, H, k)(x), orc.dirac(Ho, k)(x))
+    row, col, val = host.hopping_csr(dims)
+    ro, co, vo = orc.csr_export(Ho)
+    assert np.array_equal(row, ro) and np.array_equal(col, co) and np.array_equal(val, vo)
+    S = host.Sparse(ctx, n, n, row, col, val)
+    assert np.array_equal(S(x), Ho(x))
+    kc = 0.11 + 0.07j
+    assert np.array_equal(host.DiracOp(ctx, H, kc)(x), orc.dirac(Ho, kc)(x))
+
+
+def test_dirac_with_diagonal(ctx, host, orc):
+    dims = [10, 12, 14]
+    n = int(np.prod(dims))
+    rng = np.random.default_rng(5)
+    diag = 1.0 + rng.random(n)
+    x = orc.init_rand(4, n)
+    k = 0.13
+    ref = diag * x - (k * orc.hopping(dims)(x))
+    for D in (host.Hopping(ctx, dims), host.Sparse(ctx, n, n, *host.hopping_csr(dims))):
+        out = host.DiracOp(ctx, D, k, diag=diag)(x)
+        assert relerr(out, ref) < 1e-15
+
+
+def test_block_csr_apply_against_reference(ctx, host, golden):
+    h = golden.hierarchy
+    for tag, ne in (("mg_s2_e2", 4), ("mg_s1_e1", 2), ("mg_s2_e3", 6)):
+        brow, bcol = h[tag + "_coarse_row"].astype(np.int64), h[tag + "_coarse_col"].astype(np.int64)
+        nb = len(brow) - 1
+        bval = h[tag + "_coarse_val"]
+        Ac = host.HierarchicalSparse(ctx, nb, ne, brow, bcol, bval)
+        out = Ac(h[tag + "_restrict_f42"])
+        assert relerr(out, h[tag + "_coarse_apply"]) < 1e-14
+
+
+def test_block_csr_apply_random(ctx, host, orc):
+    rng = np.random.default_rng(11)
+    for nb, ne in ((1, 1), (7, 3), (40, 8), (13, 20)):
+        brow, bcol = [0], []
+        for r in range(nb):
+            c = np.sort(rng.choice(nb, size=min(nb, int(rng.integers(1, 6))), replace=False))
+            bcol += list(c)
+            brow.append(len(bcol))
+        bval = rng.standard_normal((len(bcol), ne, ne)) + 1j * rng.standard_normal((len(bcol), ne, ne))
+        bval[::3] = 0    # explicit zero blocks, as the reference stores them
+        x = rng.standard_normal(nb * ne) + 1j * rng.standard_normal(nb * ne)
+        out = host.HierarchicalSparse(ctx, nb, ne, brow, bcol, bval)(x)
+        ref = orc.blockcsr(nb, ne, brow, bcol, bval.reshape(-1))(x)
+        assert np.array_equal(out, ref)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GCR (src/GCR.h:158-302)
+# ------------------------------------------------------------------------------------------------------------
+MODES = {"r5": (0, 5, 4000, 1e-13), "r2": (0, 2, 4000, 1e-13), "t5": (5, 0, 4000, 1e-13),
+         "r10": (0, 10, 4000, 1e-10), "full100": (0, 0, 100, 1e-10), "smooth0": (0, 10, 0, 1e-8)}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_gcr_history_against_reference_golden(ctx, host, golden, c1, mode):
+    trunc, restart, max_iter, tol = MODES[mode]
+    g = golden.gcr
+    A = host.DiracOp(ctx, host.Sparse(ctx, c1["n"], c1["n"], c1["row"], c1["col"], c1["val"]), c1["k"])
+    rhs = ctx.init_rand(0, c1["n"])
+    x = ctx.field(c1["n"]).set_zero()
+    it, hist = host.GCR(ctx, A, host.GCR_Param(trunc, restart, max_iter, tol, False, None, None)).solve(rhs, x)
+    ref = g[mode + "_hist"]
+    # the tail of a 1e-13 solve sits on rounding noise of the residual recurrence: compare down to 1e-10 tightly
+    keep = ref > 1e-10
+    m = min(len(hist), int(keep.sum()))
+    rel = np.abs(hist[:m] - ref[:m]) / ref[:m]
+    assert rel.max() < 1e-9, (rel.max(), int(rel.argmax()))
+    assert abs(it - (len(ref) - 1)) <= 1
+    assert relerr(x.numpy(), g[mode + "_x"]) < X_TOL
+
+
+def test_gcr_operator_call_starts_from_rand2(ctx, host, golden, c1):
+    g = golden.gcr
+    A = host.DiracOp(ctx, host.Sparse(ctx, c1["n"], c1["n"], c1["row"], c1["col"], c1["val"]), c1["k"])
+    x = host.GCR(ctx, A, host.GCR_Param(0, 5, 4000, 1e-13, False, None, None))(ctx.init_rand(0, c1["n"]))
+    assert relerr(x.numpy(), g["call_r5_x"]) < X_TOL
+
+
+def test_gcr_aliased_solve(ctx, host, golden, c1):
+    """gcr.solve(b, b) of the inverse iteration (src/MG.h:102): the stopping test sees the live norm of b"""
+    g = golden.gcr
+    A = host.DiracOp(ctx, host.Sparse(ctx, c1["n"], c1["n"], c1["row"], c1["col"], c1["val"]), c1["k"])
+    b = ctx.init_rand(9, c1["n"])
+    it, _ = host.GCR(ctx, A, host.GCR_Param(0, 10, 10, 1e-8, False, None, None)).solve(b, b)
+    assert it == int(g["alias_iters"][0])
+    assert relerr(b.numpy(), g["alias_b9"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag,dims", [("lap2d_48", [48, 48]), ("lap3d_12", [12, 12, 12])])
+@pytest.mark.parametrize("form", ["csr", "stencil"])
+def test_gcr_synthetic_against_reference_golden(ctx, host, golden, tag, dims, form):
+    g = golden.gcr
+    n = int(np.prod(dims))
+    D = host.Hopping(ctx, dims) if form == "stencil" else host.Sparse(ctx, n, n, *host.hopping_csr(dims))
+    A = host.DiracOp(ctx, D, 1.0 / (2 * len(dims) + 0.01))
+    rhs = ctx.init_rand(0, n)
+    x = ctx.field(n).set_zero()
+    it, hist = host.GCR(ctx, A, host.GCR_Param(0, 10, 100000, 1e-10, False, None, None)).solve(rhs, x)
+    ref = g[tag + "_hist"]
+    check_hist(hist, ref, it, len(ref) - 1, tol=1e-9)
+    assert relerr(x.numpy(), g[tag + "_x"]) < X_TOL
+
+
+@pytest.mark.parametrize("trunc,restart,max_iter", [(0, 4, 60), (3, 0, 60), (0, 0, 25), (0, 20, 70), (18, 0, 50)])
+def test_gcr_random_operator_against_oracle(ctx, host, orc, trunc, restart, max_iter):
+    rng = np.random.default_rng(7)
+    n = 300
+    row, col, val = random_csr(rng, n, 8)
+    rhs = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x0 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    k = 0.02 + 0.01j
+    A = host.DiracOp(ctx, host.Sparse(ctx, n, n, row, col, val), k)
+    Ao = orc.dirac(orc.csr(n, n, row, col, val), k)
+    for std in (0, 1):
+        x = ctx.from_numpy(x0)
+        it, hist = host.GCR(ctx, A, host.GCR_Param(trunc, restart, max_iter, 1e-12, False, None, None, std_conj=std)).solve(ctx.from_numpy(rhs), x)
+        xo, ho, ito = orc.gcr_solve(Ao, orc.gcr_param(trunc, restart, max_iter, 1e-12, std_conj=std), rhs, x0=x0)
+        keep = int((ho > 1e-9).sum())
+        check_hist(hist[:keep], ho[:keep], it, ito, tol=1e-8)
+        assert relerr(x.numpy(), xo) < X_TOL
+
+
+def test_gcr_flexible_right_preconditioner(ctx, host, orc):
+    """right preconditioner = an inner GCR (solver-as-operator), flexible form z = R(r)"""
+    dims = [10, 10, 10]
+    n = 1000
+    A = host.DiracOp(ctx, host.Hopping(ctx, dims), 1 / 6.01)
+    Ao = orc.dirac(orc.hopping(dims), 1 / 6.01)
+    inner = host.GCR(ctx, A, host.GCR_Param(0, 4, 3, 1e-8, False, None, None, zero_guess=True))
+    inner_o = orc.gcr_op(Ao, orc.gcr_param(0, 4, 3, 1e-8), zero_guess=True)
+    rhs = orc.init_rand(0, n)
+    x = ctx.field(n).set_zero()
+    it, hist = host.GCR(ctx, A, host.GCR_Param(0, 10, 200, 1e-10, False, None, inner)).solve(ctx.from_numpy(rhs), x)
+    xo, ho, ito = orc.gcr_solve(Ao, orc.gcr_param(0, 10, 200, 1e-10), rhs, precond=inner_o)
+    check_hist(hist, ho, it, ito, tol=1e-8)
+    assert relerr(x.numpy(), xo) < X_TOL
+
+
+def test_gcr_rejects_trunc_and_restart(ctx, host):
+    A = host.DiracOp(ctx, host.Hopping(ctx, [8, 8]), 0.2)
+    f = ctx.init_rand(0, 64)
+    with pytest.raises(Exception):
+        host.GCR(ctx, A, host.GCR_Param(3, 3, 10, 1e-8, False, None, None)).solve(f, ctx.field(64).set_zero())
+
+
+def test_solve_through_host_buffers(ctx, host, orc):
+    dims = [24, 24]
+    n = 576
+    A = host.DiracOp(ctx, host.Sparse(ctx, n, n, *host.hopping_csr(dims)), 1 / 4.01)
+    rhs = orc.init_rand(0, n)
+    x, it, hist = host.GCR(ctx, A, host.GCR_Param(0, 10, 5000, 1e-10, False, None, None)).solve_host(rhs, np.zeros(n, dtype=np.complex128))
+    xo, ho, ito = orc.gcr_solve(orc.dirac(orc.hopping(dims), 1 / 4.01), orc.gcr_param(0, 10, 5000, 1e-10), rhs)
+    check_hist(hist, ho, it, ito, tol=1e-8)
+    assert relerr(x, xo) < X_TOL
+
+
+# ------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json config 2: 4096 x 4096 five-point operator)
+# ------------------------------------------------------------------------------------------------------------
+def test_full_size_properties_config2(ctx, host):
+    dims = [4096, 4096]
+    n = 4096 * 4096
+    H = host.Hopping(ctx, dims)
+    k = 1 / 4.01
+    A = host.DiracOp(ctx, H, k)
+    rng = np.random.default_rng(0)
+    a = ctx.from_numpy(rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    b = ctx.from_numpy(rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    # linearity: A(a + 2b) = A a + 2 A b
+    lhs = A(a + b * 2.0)
+    rhs = A(a) + A(b) * 2.0
+    d = lhs - rhs
+    assert d.norm() <= 1e-14 * lhs.norm()
+    # symmetry of the real operator: <a, A b> = conj(<b, A a>)
+    assert abs(a.dot(A(b)) - np.conj(b.dot(A(a)))) <= 1e-12 * a.norm() * b.norm()
+    # constant vector: interior rows give 1 - 4k, the row sums of H are the neighbour counts
+    ones = ctx.field(n).set_constant(1.0)
+    y = H(ones).numpy().reshape(4096, 4096)
+    assert y[1:-1, 1:-1].min() == 4 and y[0, 0] == 2 and y[0, 5] == 3 and y[-1, -1] == 2
+    # stored-operator path agrees with the matrix-free path at full size
+    row, col, val = host.hopping_csr(dims)
+    S = host.DiracOp(ctx, host.Sparse(ctx, n, n, row, col, val), k)
+    assert np.array_equal(S(a).numpy(), A(a).numpy())
+    # 30 GCR iterations: residual history is monotone and both operator forms give the same history
+    p = host.GCR_Param(0, 10, 30, 1e-10, False, None, None)
+    x1, x2 = ctx.field(n).set_zero(), ctx.field(n).set_zero()
+    it1, h1 = host.GCR(ctx, A, p).solve(a, x1)
+    it2, h2 = host.GCR(ctx, S, p).solve(a, x2)
+    assert it1 == it2 == 30 and np.all(np.diff(h1) < 0)
+    assert np.array_equal(h1, h2)
+    r = a - A(x1)
+    assert abs(r.norm() / a.norm() - h1[-1]) < 1e-10 * h1[-1] + 1e-14
