@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- time-to-solution of the GCR / MG-GCR solve path on synthetic operators of BASELINE.json's shapes.
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--operator csr|stencil] [--impl reference]
+
+A "step" is one full solve (x0 = 0, relative residual 1e-10) of the named workload with the operator, the right-hand
+side and every Krylov vector resident in HBM.  `value` = seconds per solve (device time, CUDA events on the
+library's stream, max over ranks); `e2e` = the same solve through the C ABI's host-buffer entry point
+(mgcr_gcr_solve_host: pinned host rhs/x0 -> device -> solve -> host).  `roofline` is measured live: every kernel
+launch of the timed steps is bracketed by pooled CUDA events inside the library (no synchronisation in the loop) and
+the dominant kernel class is reported as algorithmic bytes / device time against MEASURED_PEAKS.json.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/ref_oracle = the unmodified reference
+headers compiled by oracle/Makefile; the C restatement if that binary is absent) on a bounded sample of the same
+workload on the host cores, extrapolated by rows x iterations to the same time-to-solution metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> description of the synthetic operator A = I - k H (H = unit hopping, Dirichlet), k = 1/(2 nd + m2)
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "gcr2d_4096": dict(dims=[4096, 4096], m2=0.01, restart=10, tol=1e-10, max_iter=100000, mg=None,
+                       desc="2-D 5-point 4096x4096, I - H/(4+0.01), unpreconditioned restart-10 GCR to 1e-10",
+                       cpu_sample=[1024, 1024], cpu_iters=10),
+    "gcr3d_256": dict(dims=[256, 256, 256], m2=0.01, restart=10, tol=1e-10, max_iter=100000, mg=None,
+                      desc="3-D 7-point 256^3, I - H/(6+0.01), unpreconditioned restart-10 GCR to 1e-10",
+                      cpu_sample=[96, 96, 96], cpu_iters=10),
+    "gcr3d_512": dict(dims=[512, 512, 512], m2=0.01, restart=10, tol=1e-10, max_iter=100000, mg=None,
+                      desc="3-D 7-point 512^3, I - H/(6+0.01), unpreconditioned restart-10 GCR to 1e-10",
+                      cpu_sample=[96, 96, 96], cpu_iters=10),
+}
+# iteration counts measured on B200 (parity-checked against the CPU oracle at reduced size); used by the reference
+# arm, which cannot afford the full CPU solve, to extrapolate time-to-solution.  Updated from BENCH logs.
+KNOWN_ITERS = {}
+KNOWN_ITERS_FILE = os.path.join(ROOT, "profiles", "bench_iterations.json")
+if os.path.exists(KNOWN_ITERS_FILE):
+    KNOWN_ITERS.update(json.load(open(KNOWN_ITERS_FILE)))
+
+METRIC = "MG-GCR solve time to 1e-10 & SpMV HBM GB/s at 1/2/4/8 B200 vs CPU ref"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_cpu_sample(wl):
+    """times the reference's CPU GCR on a bounded sample of the workload; returns dict with seconds per row-iteration"""
+    dims = wl["cpu_sample"]
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_oracle")
+    V = 1
+    for d in dims:
+        V *= d
+    if os.path.exists(ref):
+        cwd = os.path.join(ROOT, "oracle", "_ref", "work", "run", "a")
+        os.makedirs(cwd, exist_ok=True)
+        os.makedirs(os.path.join(ROOT, "oracle", "_ref", "work", "data", "out_data"), exist_ok=True)
+        cmd = [ref, "bench", str(len(dims))] + [str(d) for d in dims] + [str(wl["m2"]), str(wl["restart"]), str(wl["cpu_iters"])]
+        out = subprocess.run(cmd, cwd=cwd, check=True, capture_output=True, text=True).stdout
+        js = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+        return dict(kind="reference", cores=1, V=V, iters=js["iters"], sec_per_iter=js["seconds_per_iter"], spmv_seconds=js["spmv_seconds"],
+                    sample="unmodified reference GCR (1 thread, as in src/GCR.h) on %s, restart %d, %d iterations" % ("x".join(map(str, dims)), wl["restart"], js["iters"]))
+    # restatement fallback (port)
+    import numpy as np
+    from oracle import pyoracle as orc
+    H = orc.hopping(dims)
+    A = orc.dirac(H, 1.0 / (2 * len(dims) + wl["m2"]))
+    rhs = orc.init_rand(0, H.n)
+    t0 = time.perf_counter()
+    _, _, it = orc.gcr_solve(A, orc.gcr_param(0, wl["restart"], wl["cpu_iters"], 1e-10), rhs)
+    dt = time.perf_counter() - t0
+    return dict(kind="port", cores=1, V=V, iters=it, sec_per_iter=dt / max(it, 1), spmv_seconds=None,
+                sample="C restatement of the reference GCR (1 thread) on %s, restart %d, %d iterations" % ("x".join(map(str, dims)), wl["restart"], it))
+
+
+def extrapolate(sample, wl, iterations):
+    V = 1
+    for d in wl["dims"]:
+        V *= d
+    return sample["sec_per_iter"] * (V / sample["V"]) * iterations
+
+
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    its = KNOWN_ITERS.get(args.workload)
+    times = []
+    sample = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        sample = reference_cpu_sample(wl)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    its_used = its if its else sample["iters"]
+    value = extrapolate(sample, wl, its_used)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "operator": "csr (Sparse<long>, the reference's only format)"},
+        "cpu_baseline": {"value": value, "unit": "s", "cores": sample["cores"], "kind": sample["kind"],
+                         "sample": sample["sample"] + "; time-to-solution extrapolated as sec/iteration x (rows/sample rows) x %s iterations%s"
+                         % (its_used, "" if its else " (full-size iteration count unknown: per-sample count used)"),
+                         "sec_per_iter_sample": sample["sec_per_iter"]},
+        "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--operator", default="csr", choices=["csr", "stencil"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-iter", type=int, default=None, help="cap GCR iterations (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "gcr2d_4096" if world == 1 else "gcr3d_512"
+    wl = dict(WORKLOADS[args.workload])
+    if args.max_iter:
+        wl["max_iter"] = args.max_iter
+    if args.impl == "reference":
+        return run_reference(args, wl, rank)
+
+    import numpy as np
+    import torch
+    from mgpreconditionedgcr_b200 import host
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    ctx = host.Context(local_rank)
+    if world > 1:
+        ids = [host.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.init_dist(rank, world, ids[0])
+    if world > 1 and args.operator == "csr":
+        args.operator = "stencil"   # TODO(dist csr)
+    dims = wl["dims"]
+    nd = len(dims)
+    V = int(np.prod(dims))
+    k = 1.0 / (2 * nd + wl["m2"])
+    # operator
+    if args.operator == "stencil":
+        D = host.Hopping(ctx, dims)
+    else:
+        row, col, val = host.hopping_csr(dims)
+        D = host.Sparse(ctx, V, V, row, col, val)
+        del row, col, val
+    A = host.DiracOp(ctx, D, k)
+    n_local = A.get_dim()
+    # right-hand side: Field::init_rand(0) stream of the reference (this rank's slab of it)
+    if world == 1:
+        rhs = ctx.init_rand(0, V)
+    else:
+        b, e = host.slab_range(dims[0], 1, rank, world)
+        plane = V // dims[0]
+        rhs = ctx.init_rand(0, n_local, skip=b * plane)
+    x = ctx.field(n_local)
+    param = host.GCR_Param(0, wl["restart"], wl["max_iter"], wl["tol"], False, None, None)
+    gcr = host.GCR(ctx, A, param)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    def step():
+        x.set_zero()
+        return gcr.solve(rhs, x, hist_cap=2)
+
+    def sync_all():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    it = 0
+    for _ in range(args.warmup):
+        it, _ = step()
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ctx.set_profile(True)
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        it, _ = step()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    prof = ctx.profile()
+    ctx.set_profile(False)
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sec_per_solve = ms / args.steps / 1e3
+    # true residual of the last solve
+    r = rhs - A(x)
+    final_rel = r.norm() / rhs.norm()
+
+    # end to end through host buffers (single GPU: the C ABI's host entry point)
+    e2e = None
+    if world == 1:
+        h_rhs = torch.empty(V, dtype=torch.complex128, pin_memory=True)
+        h_x = torch.zeros(V, dtype=torch.complex128, pin_memory=True)
+        h_rhs.numpy()[:] = rhs.numpy()
+        import ctypes as C
+        from mgpreconditionedgcr_b200 import capi
+        hist = np.zeros(2)
+        itc = C.c_int()
+        times = []
+        for i in range(2):
+            h_x.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            capi.check(ctx.lib.mgcr_gcr_solve_host(ctx.h, A.h, C.byref(param), None, None, C.c_void_p(h_rhs.data_ptr()), C.c_void_p(h_x.data_ptr()),
+                                                   capi.ptr(hist), 2, C.byref(itc)))
+            times.append(time.perf_counter() - t0)
+        e2e = {"value": min(times), "unit": "s", "h2d_bytes_per_step": 2 * 16 * V, "d2h_bytes_per_step": 16 * V,
+               "how": "mgcr_gcr_solve_host: pinned host rhs + x0 -> HBM, solve, x -> host; wall clock around the (synchronous) call, best of 2"}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    total_ms = sum(v["ms"] for v in prof.values())
+    dom = max(prof, key=lambda kname: prof[kname]["ms"])
+    classes = {kname: {"ms_per_launch": v["ms"] / max(v["calls"], 1), "launches": v["calls"], "share": v["ms"] / total_ms,
+                       "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None} for kname, v in prof.items()}
+    d = prof[dom]
+    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf)).get(args.workload, {}).get(dom)
+    opname = [n for n in prof if n.startswith(("sell", "hopping"))]
+    spmv = None
+    if opname:
+        o = prof[opname[0]]
+        spmv = {"kernel": opname[0], "GBps": o["bytes"] / (o["ms"] * 1e-3) / 1e9, "frac": o["bytes"] / (o["ms"] * 1e-3) / 1e9 / peak,
+                "bytes_per_apply": o["bytes"] / max(o["calls"], 1)}
+    line = {
+        "metric": METRIC, "value": sec_per_solve, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "c128 (f64)",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "operator": args.operator, "rows": V,
+                   "l2": "inputs larger than L2 (every vector is %.0f MB, L2 is 126 MB)" % (16 * V / 1e6)},
+        "iterations": it, "final_true_rel_residual": final_rel,
+        "gpu_launches": launches, "clocks": clk, "e2e": e2e,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "how": "algorithmic bytes of every launch of the class / its summed CUDA-event time over the timed steps"},
+        "spmv": spmv, "kernels": classes,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        s = reference_cpu_sample(wl)
+        line["cpu_baseline"] = {"value": extrapolate(s, wl, it), "unit": "s", "cores": s["cores"], "kind": s["kind"],
+                                "sample": s["sample"] + "; extrapolated as sec/iteration x (rows/sample rows) x %d iterations (the count this solve took)" % it,
+                                "sec_per_iter_sample": s["sec_per_iter"]}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

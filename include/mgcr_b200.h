@@ -97,6 +97,8 @@ int mgcr_vec_gamma5(mgcr_ctx* ctx, int ndim, const int64_t* h_dims, int axis, co
 /* Field::init_rand(seed) (Fields.h:125-135): the glibc srand/rand stream, drawn on the host (imaginary part first,
  * as g++ evaluates it) and uploaded -- the GPU never re-implements rand(). */
 int mgcr_vec_init_rand(mgcr_ctx* ctx, int seed, int64_t n, mgcr_c128* d_out);
+/* elements [skip, skip+n) of the same stream: the local slab of a distributed Field::init_rand(seed) */
+int mgcr_vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, mgcr_c128* d_out);
 
 /* Mesh<num_type>::blocking(sub, mask) (src/Mesh.h:236-298), generalised to a per-dimension block size.
  * Exactly 4 dims must be masked.  Writes block_map[b*bs + o] = site (int64, HOST array of prod(masked dims)

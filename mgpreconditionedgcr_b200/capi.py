@@ -71,6 +71,7 @@ SIGNATURES = {
     "mgcr_vec_normalise": [_vp, _i64, _vp],
     "mgcr_vec_gamma5": [_vp, _int, _pi64, _int, _vp, _vp],
     "mgcr_vec_init_rand": [_vp, _int, _i64, _vp],
+    "mgcr_vec_init_rand_slab": [_vp, _int, _i64, _i64, _vp],
     "mgcr_blocking_build": [_vp, _int, _pi64, _pi64, C.POINTER(C.c_uint8), _pi64, _pi64, _pi64],
     "mgcr_csr_create": [_vp, _i64, _i64, _vp, _vp, _vp, _pvp],
     "mgcr_csr_create_dist": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _pvp],

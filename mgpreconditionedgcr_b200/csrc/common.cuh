@@ -163,7 +163,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // blockDim.x must be RED_THREADS.  Returns true in every thread of the last block (after results are final).
 template <int NV>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
-                                            double* __restrict__ result) {
+                                            double* __restrict__ result, int nwrite = NV) {
     constexpr int NW = RED_THREADS / 32;
     __shared__ double sm[NW][NV];
     __shared__ bool is_last;
@@ -208,7 +208,7 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict_
         double s = 0.;
 #pragma unroll
         for (int w = 0; w < NW; w++) s += sm[w][threadIdx.x];
-        result[threadIdx.x] = s;
+        if ((int)threadIdx.x < nwrite) result[threadIdx.x] = s;
     }
     return true;
 }

@@ -132,7 +132,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, 
             v[2 * k] += t.x; v[2 * k + 1] += t.y;
         }
     }
-    grid_reduce<2 * NH>(v, partials, ticket, out);
+    grid_reduce<2 * NH>(v, partials, ticket, out, 2 * hl.count);
 }
 
 // p_new = z + sum_i(-beta_i ps[i]) ; Ap_new = Ar + sum_i(-beta_i Aps[i]) written into ring slot `cur`, with the next

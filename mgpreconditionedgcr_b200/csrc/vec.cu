@@ -135,22 +135,14 @@ extern "C" int mgcr_vec_gamma5(mgcr_ctx* ctx, int ndim, const int64_t* dims, int
 }
 
 // glibc rand() stream on the host, imaginary part drawn first (src/Fields.h:125-135 as compiled by g++)
+int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d_out);
 extern "C" int mgcr_vec_init_rand(mgcr_ctx* ctx, int seed, int64_t n, mgcr_c128* d_out) {
     ARG_CHECK(ctx && (n == 0 || d_out), "mgcr_vec_init_rand: NULL buffer");
-    if (n == 0) return MGCR_OK;
-    c128* h = nullptr;
-    CUDA_TRY(cudaMallocHost(&h, sizeof(c128) * (size_t)n));
-    srand(seed);
-    for (int64_t i = 0; i < n; i++) {
-        double im = (rand() % 2000) / 1000. - 1;
-        double re = (rand() % 2000) / 1000. - 1;
-        h[i] = cmake(re, im);
-    }
-    cudaError_t e = cudaMemcpyAsync(d_out, h, sizeof(c128) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFreeHost(h);
-    CUDA_TRY(e);
-    return MGCR_OK;
+    return vec_init_rand_slab(ctx, seed, 0, n, (c128*)d_out);
+}
+extern "C" int mgcr_vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, mgcr_c128* d_out) {
+    ARG_CHECK(ctx && skip >= 0 && (n == 0 || d_out), "mgcr_vec_init_rand_slab: bad argument");
+    return vec_init_rand_slab(ctx, seed, skip, n, (c128*)d_out);
 }
 
 // ----------------------------------------------------------------------------------------------------------

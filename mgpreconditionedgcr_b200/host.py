@@ -80,9 +80,9 @@ class Context:
         check(self.lib.mgcr_vec_upload(self.h, f.ptr, capi.ptr(a), a.size))
         return f
 
-    def init_rand(self, seed, n):
+    def init_rand(self, seed, n, skip=0):
         f = Field(self, n)
-        check(self.lib.mgcr_vec_init_rand(self.h, seed, n, f.ptr))
+        check(self.lib.mgcr_vec_init_rand_slab(self.h, seed, skip, n, f.ptr))
         return f
 
     def blocking(self, dims, sub4, mask=None):
