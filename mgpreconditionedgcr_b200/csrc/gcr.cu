@@ -82,7 +82,8 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
 
     c128 *r = nullptr, *Ar = nullptr, *z = nullptr, *ps = nullptr, *Aps = nullptr, *acc_p = nullptr, *acc_Ap = nullptr;
     double* scal = nullptr;
-    const int64_t stride = n;
+    static const int64_t ring_pad = getenv("MGCR_RING_PAD") ? atoll(getenv("MGCR_RING_PAD")) : 0;   // experiment knob
+    const int64_t stride = n + ring_pad;
     const int bden_off = S_BNUM + 2 * storage;
     const int nscal = bden_off + storage;
     int st = MGCR_OK;
@@ -95,13 +96,14 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     GTRY(dev_alloc_t(ctx, (size_t)n, &r));
     GTRY(dev_alloc_t(ctx, (size_t)n, &Ar));
     if (right) GTRY(dev_alloc_t(ctx, (size_t)n, &z));
-    GTRY(dev_alloc_t(ctx, (size_t)n * storage, &ps));
-    GTRY(dev_alloc_t(ctx, (size_t)n * storage, &Aps));
+    GTRY(dev_alloc_t(ctx, (size_t)stride * storage, &ps));
+    GTRY(dev_alloc_t(ctx, (size_t)stride * storage, &Aps));
     if (storage > GCR_CHUNK) { GTRY(dev_alloc_t(ctx, (size_t)n, &acc_p)); GTRY(dev_alloc_t(ctx, (size_t)n, &acc_Ap)); }
     GTRY(dev_alloc_t(ctx, (size_t)nscal, &scal));
     GCUDA(cudaMemsetAsync(scal, 0, sizeof(double) * nscal, ctx->stream));
 
-    const int grid = stream_grid(ctx, n, 4, 2);
+    static const int grid_per_sm = getenv("MGCR_GRID_PER_SM") ? atoi(getenv("MGCR_GRID_PER_SM")) : 4;   // experiment knob
+    const int grid = stream_grid(ctx, n, grid_per_sm, 2);
     // r = rhs ; p = z = R(r) or r ; Ap = A p                                                   (GCR.h:189-192)
     if (n) GCUDA(cudaMemcpyAsync(r, rhs, sizeof(c128) * n, cudaMemcpyDeviceToDevice, ctx->stream));
     if (right) GTRY(right->apply(r, ps)); else if (n) GCUDA(cudaMemcpyAsync(ps, r, sizeof(c128) * n, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -1,15 +1,633 @@
-// placeholder, replaced below
+// csrc/mg.cu -- adaptive aggregation multigrid (reference: src/MG.h), device resident.
+//   setup  (MG::initialise, MG.h:131-285): blocking -> near-null vectors -> chirality doubling -> block projection ->
+//          per-aggregate Gram-Schmidt -> Galerkin coarse blocks, generalised per SURVEY.md Appendix B Q12 to per-dim
+//          aggregate sizes, any dof per site and n_level coarse grids.
+//   apply  (MG.h:347-383, 405-430): restrict, prolong and the cycle of report Algorithm 2.
+// The prolongator is stored compactly ([aggregate][vector][dof in aggregate]): every fine dof lies in exactly one
+// aggregate, so the reference's n_blocks*ne full-lattice Fields (MG.h:158-187) collapse to ne numbers per dof.
+// The Galerkin product is one pass over the operator's rows: G[B',b] += conj(P_B'[i,:])^T (sum_j M_ij P_b[j,:]) for
+// i in B', instead of the reference's n_blocks*9*ne^2 full-lattice matvecs (MG.h:206-278).
+#include <math.h>
+
+#include <algorithm>
+
+#include "kernels_blas.cuh"
 #include "mg.cuh"
-#define STUB(name, ...) extern "C" int name(__VA_ARGS__) { mgcr_set_error(#name ": not built yet"); return MGCR_ERR_UNSUPPORTED; }
-STUB(mgcr_mg_create, mgcr_ctx*, mgcr_op*, int, const mgcr_level_cfg*, const mgcr_gcr_param*, const mgcr_gcr_param*, const mgcr_gcr_param*, int, const mgcr_c128*, mgcr_mg**)
-STUB(mgcr_mg_destroy, mgcr_mg*)
-STUB(mgcr_mg_level_info, mgcr_mg*, int, int64_t*, int64_t*, int*, int64_t*)
-STUB(mgcr_mg_export_block_map, mgcr_mg*, int, int64_t*)
-STUB(mgcr_mg_export_prolongator, mgcr_mg*, int, mgcr_c128*)
-STUB(mgcr_mg_export_coarse, mgcr_mg*, int, int64_t*, int64_t*, mgcr_c128*)
-STUB(mgcr_mg_coarse_op, mgcr_mg*, int, mgcr_op**)
-STUB(mgcr_mg_restrict, mgcr_ctx*, mgcr_mg*, int, const mgcr_c128*, mgcr_c128*)
-STUB(mgcr_mg_prolong, mgcr_ctx*, mgcr_mg*, int, const mgcr_c128*, mgcr_c128*)
-STUB(mgcr_mg_cycle, mgcr_ctx*, mgcr_mg*, int, const mgcr_c128*, mgcr_c128*)
-STUB(mgcr_mg_op_create, mgcr_ctx*, mgcr_mg*, mgcr_op**)
-STUB(mgcr_csr_create_dist, mgcr_ctx*, int64_t, int64_t, int64_t, const int64_t*, const int64_t*, const mgcr_c128*, mgcr_op**)
+
+// ----------------------------------------------------------------------------------------------------------
+// small setup kernels
+// ----------------------------------------------------------------------------------------------------------
+// v+ = 0.5 (v + g5 v), v- = 0.5 (v - g5 v)                                                      (MG.h:316-329)
+static __global__ void __launch_bounds__(RED_THREADS) k_chiral(int64_t n, const c128* __restrict__ v, const c128* __restrict__ g5,
+                                                               c128* __restrict__ vp, c128* __restrict__ vm) {
+    GRID_STRIDE(i, n) {
+        c128 a = v[i], b = g5[i];
+        c128 s = cadd(a, b), d = csub(a, b);
+        vp[i] = cmake(0.5 * s.x, 0.5 * s.y);
+        vm[i] = cmake(0.5 * d.x, 0.5 * d.y);
+    }
+}
+
+// P[b][e][o*dof+d] = vec[e][block_map[b][o]*dof + d]                                             (MG.h:385-403)
+static __global__ void __launch_bounds__(RED_THREADS) k_project(int64_t total, LevelGeom g, int64_t n, const int64_t* __restrict__ block_map,
+                                                                const c128* __restrict__ vecs, c128* __restrict__ P) {
+    GRID_STRIDE(t, total) {
+        int64_t q = t % g.bl;
+        int64_t be = t / g.bl;
+        int e = (int)(be % g.ne);
+        int64_t b = be / g.ne;
+        int64_t site = block_map[b * g.bs + q / g.dof];
+        P[t] = vecs[(int64_t)e * n + site * g.dof + q % g.dof];
+    }
+}
+
+// block-level sum of a complex value over the CTA (all threads get the result)
+template <int THREADS>
+__device__ __forceinline__ c128 cta_sum(c128 v, double* sm /* 2*THREADS/32 + 2 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double a = warp_sum(v.x), b = warp_sum(v.y);
+    __syncthreads();
+    if (lane == 0) { sm[2 * warp] = a; sm[2 * warp + 1] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0., sb = 0.;
+        for (int w = 0; w < THREADS / 32; w++) { sa += sm[2 * w]; sb += sm[2 * w + 1]; }
+        sm[2 * (THREADS / 32)] = sa; sm[2 * (THREADS / 32) + 1] = sb;
+    }
+    __syncthreads();
+    return cmake(sm[2 * (THREADS / 32)], sm[2 * (THREADS / 32) + 1]);
+}
+
+// per-aggregate modified Gram-Schmidt + normalisation, in place                                   (MG.h:189-198)
+static __global__ void __launch_bounds__(128) k_block_mgs(LevelGeom g, c128* P) {
+    __shared__ double sm[2 * 4 + 2];
+    const int64_t b = blockIdx.x;
+    c128* Pb = P + b * g.ne * g.bl;
+    for (int v = 0; v < g.ne; v++) {
+        c128* pv = Pb + (int64_t)v * g.bl;
+        for (int j = 0; j < v; j++) {
+            const c128* pj = Pb + (int64_t)j * g.bl;
+            c128 acc = cmake(0., 0.);
+            for (int64_t q = threadIdx.x; q < g.bl; q += 128) { c128 t = cmulc(pj[q], pv[q]); acc.x += t.x; acc.y += t.y; }
+            c128 h = cta_sum<128>(acc, sm);
+            for (int64_t q = threadIdx.x; q < g.bl; q += 128) pv[q] = csub(pv[q], cmul(h, pj[q]));
+            __syncthreads();
+        }
+        c128 acc = cmake(0., 0.);
+        for (int64_t q = threadIdx.x; q < g.bl; q += 128) { c128 t = pv[q]; acc.x += t.x * t.x + t.y * t.y; }
+        c128 nn = cta_sum<128>(acc, sm);
+        const double s = 1. / sqrt(nn.x);
+        for (int64_t q = threadIdx.x; q < g.bl; q += 128) { c128 t = pv[q]; pv[q] = cmake(t.x * s, t.y * s); }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// row visitors: enumerate (column, value) of one fine row of a matrix-like operator
+// ----------------------------------------------------------------------------------------------------------
+struct SellRows {
+    const int64_t* slice_ptr; const int32_t* col; const c128* val;
+    int dirac; c128 k; const double* diag;
+    template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
+        const int64_t slice = i >> 5; const int lane = (int)(i & 31);
+        const int64_t base = slice_ptr[slice];
+        const int w = (int)((slice_ptr[slice + 1] - base) >> 5);
+        for (int t = 0; t < w; t++) {
+            c128 v = val[base + (int64_t)t * 32 + lane];
+            if (v.x == 0. && v.y == 0.) continue;
+            if (dirac) { v = cmul(k, v); v = cmake(-v.x, -v.y); }     // 1 - k D: src/Operator.h:111-112
+            f((int64_t)col[base + (int64_t)t * 32 + lane], v);
+        }
+        if (dirac) f(i, cmake(diag ? diag[i] : 1., 0.));
+    }
+};
+
+struct HopRows {
+    int64_t n2, n1, n0;   // local planes, rows, columns (single GPU: global)
+    int dirac; c128 k; const double* diag;
+    template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
+        const int64_t x = i % n0, y = (i / n0) % n1, z = i / (n0 * n1);
+        c128 v = cmake(1., 0.);
+        if (dirac) { v = cmul(k, v); v = cmake(-v.x, -v.y); }
+        if (z > 0) f(i - n0 * n1, v);
+        if (y > 0) f(i - n0, v);
+        if (x > 0) f(i - 1, v);
+        if (x < n0 - 1) f(i + 1, v);
+        if (y < n1 - 1) f(i + n0, v);
+        if (z < n2 - 1) f(i + n0 * n1, v);
+        if (dirac) f(i, cmake(diag ? diag[i] : 1., 0.));
+    }
+};
+
+struct BlockRows {
+    const int32_t* brow; const int32_t* bcol; const c128* bval; int ne;
+    template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
+        const int64_t R = i / ne; const int r = (int)(i - R * ne);
+        for (int l = brow[R]; l < brow[R + 1]; l++) {
+            const c128* m = bval + (int64_t)l * ne * ne + r;
+            const int64_t c0 = (int64_t)bcol[l] * ne;
+            for (int c = 0; c < ne; c++) f(c0 + c, m[(int64_t)c * ne]);
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// Galerkin coarse blocks.  One CTA per coarse block row B.  Reference slots of a row (MG.h:217-276 seen from the row):
+//   0        (B, B)
+//   2d+1     (B, B-e_d)   the "+d" triplet of column block B-e_d          present iff bd[d] >= 2
+//   2d+2     (B, B+e_d)   the "-d" triplet of column block B+e_d          present iff bd[d] >= 3
+// (with 2 blocks in a direction both neighbours coincide and the reference keeps the "+" triplet only; neighbours wrap
+// periodically as in MG.h:229-231.)  Blocks are written column-major in ascending column order.
+// ----------------------------------------------------------------------------------------------------------
+struct RowSlots { int K; int slot[9]; int64_t col[9]; };
+
+__host__ __device__ inline void row_slots(const LevelGeom& g, int64_t B, RowSlots* rs) {
+    int64_t bi[4], rem = B;
+    for (int c = 3; c >= 0; c--) { bi[c] = rem % g.bd[c]; rem /= g.bd[c]; }
+    int K = 0;
+    rs->slot[K] = 0; rs->col[K] = B; K++;
+    for (int d = 0; d < 4; d++) {
+        int64_t stride = 1;
+        for (int c = 3; c > d; c--) stride *= g.bd[c];
+        if (g.bd[d] >= 2) {
+            int64_t m = (bi[d] - 1 + g.bd[d]) % g.bd[d];
+            rs->slot[K] = 2 * d + 1; rs->col[K] = B + (m - bi[d]) * stride; K++;
+        }
+        if (g.bd[d] >= 3) {
+            int64_t p = (bi[d] + 1) % g.bd[d];
+            rs->slot[K] = 2 * d + 2; rs->col[K] = B + (p - bi[d]) * stride; K++;
+        }
+    }
+    // ascending column order, ties (none structurally) by slot: insertion sort
+    for (int a = 1; a < K; a++) {
+        int s = rs->slot[a]; int64_t c = rs->col[a]; int q = a;
+        while (q > 0 && (rs->col[q - 1] > c || (rs->col[q - 1] == c && rs->slot[q - 1] > s))) { rs->slot[q] = rs->slot[q - 1]; rs->col[q] = rs->col[q - 1]; q--; }
+        rs->slot[q] = s; rs->col[q] = c;
+    }
+    rs->K = K;
+}
+
+template <class Rows>
+__global__ void __launch_bounds__(256) k_galerkin(Rows M, LevelGeom g, int K, const int64_t* __restrict__ block_map,
+                                                  const int32_t* __restrict__ site_block, const int32_t* __restrict__ site_off,
+                                                  const c128* __restrict__ P, int32_t* __restrict__ bcol_out, int8_t* __restrict__ bslot_out,
+                                                  c128* __restrict__ bval_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* G = (c128*)smem_raw;                       // [K][ne*ne] row-major accumulators
+    c128* T = G + (int64_t)K * g.ne * g.ne;          // [K][ne]
+    __shared__ RowSlots rs;
+    const int64_t B = blockIdx.x;
+    const int ne = g.ne;
+    if (threadIdx.x == 0) {
+        row_slots(g, B, &rs);
+        for (int a = 0; a < rs.K; a++) { bcol_out[B * K + a] = (int32_t)rs.col[a]; bslot_out[B * K + a] = (int8_t)rs.slot[a]; }
+    }
+    for (int t = threadIdx.x; t < K * ne * ne; t += blockDim.x) G[t] = cmake(0., 0.);
+    __syncthreads();
+    for (int64_t q = 0; q < g.bl; q++) {
+        const int64_t i = block_map[B * g.bs + q / g.dof] * g.dof + q % g.dof;
+        // T[a][c] = sum over the entries (j, v) of row i whose column lies in the block of position a of v * P[j][c]
+        for (int c = threadIdx.x; c < ne; c += blockDim.x) {
+            c128 tacc[9];
+#pragma unroll
+            for (int a = 0; a < 9; a++) tacc[a] = cmake(0., 0.);
+            M.for_each(i, [&](int64_t j, c128 v) {
+                const int64_t js = j / g.dof;
+                const int64_t b = site_block[js];
+                int pos = -1;
+#pragma unroll
+                for (int a = 0; a < 9; a++) if (pos < 0 && a < K && rs.col[a] == b) pos = a;
+                if (pos < 0) return;   // not a face neighbour: the reference assembles 9 blocks per row only
+                const int64_t off = (int64_t)site_off[js] * g.dof + (j - js * g.dof);
+                const c128 pv = P[(b * ne + c) * g.bl + off];
+#pragma unroll
+                for (int a = 0; a < 9; a++) if (a == pos) tacc[a] = cadd(tacc[a], cmul(v, pv));
+            });
+#pragma unroll
+            for (int a = 0; a < 9; a++) if (a < K) T[a * ne + c] = tacc[a];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < ne * ne; t += blockDim.x) {
+            const int r = t / ne, c = t - r * ne;
+            const c128 pr = P[(B * ne + r) * g.bl + q];
+            for (int a = 0; a < K; a++) {
+                const c128 tv = T[a * ne + c];
+                if (tv.x != 0. || tv.y != 0.) G[(int64_t)a * ne * ne + t] = cadd(G[(int64_t)a * ne * ne + t], cmulc(pr, tv));
+            }
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < K * ne * ne; t += blockDim.x) {
+        const int a = t / (ne * ne), rc = t - a * ne * ne;
+        const int r = rc / ne, c = rc - r * ne;
+        bval_out[((int64_t)(B * K + a) * ne + c) * ne + r] = G[t];
+    }
+}
+
+// replicate src/MG.h:263: the (B, B+e_d) block [slot 2d+2, column block b = B+e_d] takes the value of the block the
+// reference computed with prolongator[nb_idx], i.e. the "+d" triplet of the same column block: (b+e_d, b) [slot 2d+1]
+static __global__ void k_neg_bug(LevelGeom g, int K, const int8_t* __restrict__ bslot, c128* bval) {
+    const int64_t B = blockIdx.x;
+    const int64_t bsz = (int64_t)g.ne * g.ne;
+    for (int a = 0; a < K; a++) {
+        int s = bslot[B * K + a];
+        if (s == 0 || (s & 1)) continue;
+        int d = (s - 2) / 2;
+        int64_t bi[4], rem = B;
+        for (int c = 3; c >= 0; c--) { bi[c] = rem % g.bd[c]; rem /= g.bd[c]; }
+        int64_t stride = 1;
+        for (int c = 3; c > d; c--) stride *= g.bd[c];
+        int64_t src_row = B + (((bi[d] + 2) % g.bd[d]) - bi[d]) * stride;   // b + e_d = B + 2 e_d
+        int sa = -1;
+        for (int q = 0; q < K; q++) if (bslot[src_row * K + q] == s - 1) sa = q;
+        if (sa < 0) continue;
+        const c128* src = bval + (src_row * K + sa) * bsz;
+        c128* dst = bval + (B * K + a) * bsz;
+        for (int64_t t = threadIdx.x; t < bsz; t += blockDim.x) dst[t] = src[t];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// restrict / prolong
+// ----------------------------------------------------------------------------------------------------------
+// xc[b*ne+e] = sum_q conj(P[b][e][q]) x[map(b,q)]   (MG.h:366-383).  One CTA per aggregate: the aggregate's slice of x
+// is gathered into shared memory once, warp w reduces near-null vectors e = w, w+nw, ... with lanes striding over q.
+static __global__ void __launch_bounds__(256) k_restrict(LevelGeom g, const int64_t* __restrict__ block_map, const c128* __restrict__ P,
+                                                         const c128* __restrict__ xf, c128* __restrict__ xc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* xs = (c128*)smem_raw;
+    const int64_t b = blockIdx.x;
+    for (int64_t q = threadIdx.x; q < g.bl; q += blockDim.x) {
+        const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
+        xs[q] = __ldg(xf + site * g.dof + q % g.dof);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int e = warp; e < g.ne; e += nw) {
+        const c128* pv = P + (b * g.ne + e) * g.bl;
+        double sr = 0., si = 0.;
+        for (int64_t q = lane; q < g.bl; q += 32) {
+            c128 t = cmulc(ld_stream(pv + q), xs[q]);
+            sr += t.x; si += t.y;
+        }
+        sr = warp_sum(sr); si = warp_sum(si);
+        if (lane == 0) xc[b * g.ne + e] = cmake(sr, si);
+    }
+}
+
+// x[map(b,q)] = sum_e xc[b*ne+e] P[b][e][q]   (MG.h:347-364): one thread per fine dof, e in the reference's order
+static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, int64_t total, const int64_t* __restrict__ block_map,
+                                                        const c128* __restrict__ P, const c128* __restrict__ xc, c128* __restrict__ xf) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int64_t b = t / g.bl, q = t - b * g.bl;
+    const c128* pv = P + b * g.ne * g.bl + q;
+    const c128* a = xc + b * g.ne;
+    c128 acc = cmake(0., 0.);
+#pragma unroll 4
+    for (int e = 0; e < g.ne; e++) acc = cadd(acc, cmul(__ldg(a + e), ld_stream(pv + (int64_t)e * g.bl)));
+    const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
+    xf[site * g.dof + q % g.dof] = acc;
+}
+
+static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
+    const LevelGeom& g = L.g;
+    if (g.nb == 0) return MGCR_OK;
+    int threads = 32 * (int)std::min<int64_t>(8, std::max<int64_t>(1, g.ne));
+    size_t smem = sizeof(c128) * (size_t)g.bl;
+    KLAUNCH(ctx, "mg_restrict", 16. * L.n * (1 + g.ne) + 16. * L.nc, (k_restrict<<<(unsigned)g.nb, threads, smem, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+
+static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf) {
+    const LevelGeom& g = L.g;
+    if (L.n == 0) return MGCR_OK;
+    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne) + 16. * L.nc, (k_prolong<<<(unsigned)((L.n + 255) / 256), 256, 0, ctx->stream>>>(g, L.n, L.d_block_map, L.d_P, xc, xf)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// MG as an operator + the cycle
+// ----------------------------------------------------------------------------------------------------------
+static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x);
+
+struct MgOp : mgcr_op {
+    mgcr_mg* mg = nullptr;
+    int level = 0;
+    int apply(const c128* x, c128* y) override { return mg_cycle(mg, level, x, y); }
+};
+
+// Report Algorithm 2 (SemesterProject.pdf p.4) in the structure of src/MG.h:405-430 with the defects of SURVEY.md facts
+// 6-7 removed:  x = S b ; r = b - A x ; xc = Ac^-1 (P^H r) ; x += P xc ; r = b - A x ; x += S r.  S = one call of the
+// smoother GCR (its solve ADDS to x, GCR.h:232).  The coarse solve is GCR on the block-CSR operator, right-
+// preconditioned by this same cycle one level down when that level exists (K-cycle), plain on the coarsest level.
+static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x) {
+    mgcr_ctx* ctx = mg->ctx;
+    MgLevel& L = mg->lv[l];
+    const int64_t n = L.n, nc = L.nc;
+    ARG_CHECK(b != x, "MG cycle: input and output alias");
+    CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(c128) * n, ctx->stream));
+    MGCR_TRY(gcr_solve(ctx, L.A, &mg->smooth, nullptr, b, x, nullptr, 0, nullptr));
+    MGCR_TRY(L.A->apply(x, L.d_t));
+    MGCR_TRY(vec_axpy(ctx, n, cmake(-1., 0.), L.d_t, b, L.d_r));          // r = b - A x
+    MGCR_TRY(mg_restrict(ctx, L, L.d_r, L.d_rc));
+    CUDA_TRY(cudaMemsetAsync(L.d_xc, 0, sizeof(c128) * nc, ctx->stream));
+    MGCR_TRY(gcr_solve(ctx, L.Ac, &mg->coarse, L.deeper, L.d_rc, L.d_xc, nullptr, 0, nullptr));
+    MGCR_TRY(mg_prolong(ctx, L, L.d_xc, L.d_t));
+    MGCR_TRY(vec_axpy(ctx, n, cmake(1., 0.), L.d_t, x, x));               // x += P xc
+    MGCR_TRY(L.A->apply(x, L.d_t));
+    MGCR_TRY(vec_axpy(ctx, n, cmake(-1., 0.), L.d_t, b, L.d_r));
+    MGCR_TRY(gcr_solve(ctx, L.A, &mg->smooth, nullptr, L.d_r, x, nullptr, 0, nullptr));
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// setup
+// ----------------------------------------------------------------------------------------------------------
+template <class Rows>
+static int galerkin_launch(mgcr_ctx* ctx, MgLevel& L, const Rows& rows, int32_t* bcol, c128* bval) {
+    const LevelGeom& g = L.g;
+    size_t smem = sizeof(c128) * ((size_t)L.K * g.ne * g.ne + (size_t)L.K * g.ne);
+    ARG_CHECK(smem <= 200 * 1024, "MG setup: %d near-null vectors per aggregate need %zu bytes of shared memory for the coarse blocks", g.ne, smem);
+    CUDA_TRY(cudaFuncSetAttribute(k_galerkin<Rows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KLAUNCH(ctx, "mg_galerkin", 0., (k_galerkin<Rows><<<(unsigned)g.nb, 256, smem, ctx->stream>>>(rows, g, L.K, L.d_block_map, L.d_site_block, L.d_site_off,
+                                                                                                L.d_P, bcol, L.d_bslot, bval)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+
+static int galerkin(mgcr_ctx* ctx, MgLevel& L, int32_t* bcol, c128* bval) {
+    mgcr_op* A = L.A;
+    int dirac = 0; c128 k = cmake(0., 0.); const double* diag = nullptr;
+    if (A->kind == OP_DIRAC) {
+        DiracOp* d = static_cast<DiracOp*>(A);
+        dirac = 1; k = d->k; diag = d->d_diag; A = d->D;
+    }
+    if (A->kind == OP_SELL) {
+        SellOp* s = static_cast<SellOp*>(A);
+        SellRows r{s->d_slice_ptr, s->d_col, s->d_val, dirac, k, diag};
+        return galerkin_launch(ctx, L, r, bcol, bval);
+    }
+    if (A->kind == OP_HOPPING) {
+        HoppingOp* h = static_cast<HoppingOp*>(A);
+        HopRows r{h->n2_local, h->gdims[1], h->gdims[2], dirac, k, diag};
+        return galerkin_launch(ctx, L, r, bcol, bval);
+    }
+    if (A->kind == OP_BLOCKCSR && !dirac) {
+        BlockCsrOp* bo = static_cast<BlockCsrOp*>(A);
+        BlockRows r{bo->d_brow, bo->d_bcol, bo->d_bval, bo->ne};
+        return galerkin_launch(ctx, L, r, bcol, bval);
+    }
+    mgcr_set_error("MG setup: the operator of this level has no accessible matrix entries (kind %d)", (int)A->kind);
+    return MGCR_ERR_UNSUPPORTED;
+}
+
+static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
+    mgcr_ctx* ctx = mg->ctx;
+    MgLevel& L = mg->lv[l];
+    const mgcr_level_cfg& c = L.cfg;
+    LevelGeom& g = L.g;
+    ARG_CHECK(c.n_spin >= 1 && c.n_col >= 1 && c.n_eigen >= 1, "MG level %d: n_spin, n_col, n_eigen must be positive", l);
+    g.dof = c.n_spin * c.n_col;
+    L.nsite = 1; g.bs = 1; g.nb = 1;
+    for (int i = 0; i < 4; i++) {
+        ARG_CHECK(c.site_dims[i] >= 1 && c.sub[i] >= 1 && c.site_dims[i] % c.sub[i] == 0,
+                  "MG level %d: dimension %lld is not divisible by the aggregate size %lld (src/Mesh.h:245)", l, (long long)c.site_dims[i], (long long)c.sub[i]);
+        g.sd[i] = c.site_dims[i]; g.sub[i] = c.sub[i]; g.bd[i] = c.site_dims[i] / c.sub[i];
+        L.nsite *= g.sd[i]; g.bs *= g.sub[i]; g.nb *= g.bd[i];
+    }
+    L.n = L.nsite * g.dof;
+    ARG_CHECK(L.n == L.A->n_local, "MG level %d: mesh has %lld dofs, the operator %lld (src/GCR.h:160)", l, (long long)L.n, (long long)L.A->n_local);
+    ARG_CHECK(L.nsite < (int64_t)INT32_MAX, "MG level %d: too many sites for one device shard", l);
+    const bool doubled = (c.n_spin == 4);
+    g.ne = doubled ? 2 * c.n_eigen : c.n_eigen;
+    g.bl = g.bs * g.dof;
+    L.nc = g.nb * g.ne;
+    const int64_t n = L.n;
+    const int nv = c.n_eigen, ne = g.ne;
+    // aggregation (Mesh::blocking)
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nsite, &L.d_block_map));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nsite, &L.d_site_block));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nsite, &L.d_site_off));
+    int64_t bd[4];
+    MGCR_TRY(blocking_device(ctx, g.sd, g.sub, bd, L.d_block_map, L.d_site_block, L.d_site_off));
+    // near-null vectors (Arnoldi::solve) and chirality doubling
+    c128* ev = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)n * ne, &ev));
+    c128* base = doubled ? nullptr : ev;
+    c128* raw = nullptr;
+    if (doubled) { MGCR_TRY(dev_alloc_t(ctx, (size_t)n * nv, &raw)); base = raw; }
+    if (d_nearnull) CUDA_TRY(cudaMemcpyAsync(base, d_nearnull, sizeof(c128) * n * nv, cudaMemcpyDeviceToDevice, ctx->stream));
+    else MGCR_TRY(arnoldi(ctx, L.A, &mg->eigen, nv, base));
+    if (doubled) {
+        c128* g5 = nullptr;
+        MGCR_TRY(dev_alloc_t(ctx, (size_t)n, &g5));
+        for (int i = 0; i < nv; i++) {
+            const c128* v = raw + (int64_t)i * n;
+            MGCR_TRY(vec_gamma5(ctx, n, c.n_col, c.n_spin, v, g5));
+            KLAUNCH(ctx, "mg_chiral", 64. * n, (k_chiral<<<stream_grid(ctx, n, 8), RED_THREADS, 0, ctx->stream>>>(n, v, g5, ev + (int64_t)i * n, ev + (int64_t)(i + nv) * n)));
+            CHECK_LAUNCH();
+        }
+        MGCR_TRY(dev_free(ctx, g5));
+        MGCR_TRY(dev_free(ctx, raw));
+    }
+    // block projection into compact storage + per-aggregate Gram-Schmidt
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)n * ne, &L.d_P));
+    KLAUNCH(ctx, "mg_project", 32. * n * ne, (k_project<<<stream_grid(ctx, n * ne, 8), RED_THREADS, 0, ctx->stream>>>(n * ne, g, n, L.d_block_map, ev, L.d_P)));
+    CHECK_LAUNCH();
+    MGCR_TRY(dev_free(ctx, ev));
+    KLAUNCH(ctx, "mg_block_mgs", 0., (k_block_mgs<<<(unsigned)g.nb, 128, 0, ctx->stream>>>(g, L.d_P)));
+    CHECK_LAUNCH();
+    // Galerkin coarse operator, written straight into the block-CSR compute layout
+    RowSlots rs0;
+    row_slots(g, 0, &rs0);
+    L.K = rs0.K;
+    BlockCsrOp* Ac = new BlockCsrOp();
+    Ac->kind = OP_BLOCKCSR; Ac->ctx = ctx; Ac->nb = g.nb; Ac->nb_cols = g.nb; Ac->ne = ne; Ac->nnzb = g.nb * L.K;
+    Ac->n_local = L.nc; Ac->n_global = L.nc;
+    L.Ac = Ac;
+    ARG_CHECK(Ac->nnzb < (int64_t)INT32_MAX, "MG level %d: coarse operator too large for one device shard", l);
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)g.nb + 1, &Ac->d_brow));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)Ac->nnzb, &Ac->d_bcol));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)Ac->nnzb * ne * ne, &Ac->d_bval));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)Ac->nnzb, &L.d_bslot));
+    {
+        std::vector<int32_t> hrow((size_t)g.nb + 1);
+        for (int64_t r = 0; r <= g.nb; r++) hrow[r] = (int32_t)(r * L.K);
+        CUDA_TRY(cudaMemcpyAsync(Ac->d_brow, hrow.data(), sizeof(int32_t) * hrow.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    MGCR_TRY(galerkin(ctx, L, Ac->d_bcol, Ac->d_bval));
+    if (mg->flags & MGCR_MG_NEG_NEIGHBOUR_BUG) {
+        KLAUNCH(ctx, "mg_neg_bug", 0., (k_neg_bug<<<(unsigned)g.nb, 128, 0, ctx->stream>>>(g, L.K, L.d_bslot, Ac->d_bval)));
+        CHECK_LAUNCH();
+    }
+    // cycle work vectors
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)n, &L.d_r));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)n, &L.d_t));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nc, &L.d_rc));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nc, &L.d_xc));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MGCR_OK;
+}
+
+static void level_free(mgcr_ctx* ctx, MgLevel& L) {
+    dev_free(ctx, L.d_block_map); dev_free(ctx, L.d_site_block); dev_free(ctx, L.d_site_off); dev_free(ctx, L.d_P);
+    dev_free(ctx, L.d_bslot); dev_free(ctx, L.d_r); dev_free(ctx, L.d_t); dev_free(ctx, L.d_rc); dev_free(ctx, L.d_xc);
+    delete L.deeper; L.deeper = nullptr;
+    delete L.Ac; L.Ac = nullptr;
+}
+
+extern "C" int mgcr_mg_destroy(mgcr_mg* mg) {
+    if (!mg) return MGCR_OK;
+    for (auto& L : mg->lv) level_free(mg->ctx, L);
+    cudaStreamSynchronize(mg->ctx->stream);
+    delete mg;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr_level_cfg* cfg, const mgcr_gcr_param* eigen,
+                              const mgcr_gcr_param* coarse, const mgcr_gcr_param* smooth, int flags, const mgcr_c128* d_nearnull0, mgcr_mg** out) {
+    ARG_CHECK(ctx && A && cfg && eigen && coarse && smooth && out && n_level >= 1, "mgcr_mg_create: bad argument");
+    ARG_CHECK(ctx->nranks == 1, "mgcr_mg_create: the distributed hierarchy is not available yet");
+    *out = nullptr;
+    mgcr_mg* mg = new mgcr_mg();
+    mg->ctx = ctx; mg->n_level = n_level; mg->flags = flags;
+    mg->eigen = *eigen; mg->coarse = *coarse; mg->smooth = *smooth;
+    const int sc = (flags & MGCR_MG_STD_CONJ) ? 1 : 0;
+    mg->eigen.std_conj = sc; mg->coarse.std_conj = sc; mg->smooth.std_conj = sc;
+    mg->eigen.verbose = 0; mg->coarse.verbose = 0; mg->smooth.verbose = 0;
+    mg->lv.resize((size_t)n_level);
+    mgcr_op* cur = A;
+    for (int l = 0; l < n_level; l++) {
+        mg->lv[l].cfg = cfg[l];
+        mg->lv[l].A = cur;
+        int st = level_setup(mg, l, l == 0 ? (const c128*)d_nearnull0 : nullptr);
+        if (st != MGCR_OK) { mgcr_mg_destroy(mg); return st; }
+        cur = mg->lv[l].Ac;
+    }
+    for (int l = 0; l + 1 < n_level; l++) {
+        MgOp* op = new MgOp();
+        op->kind = OP_MG; op->ctx = ctx; op->mg = mg; op->level = l + 1;
+        op->n_local = mg->lv[l + 1].n; op->n_global = op->n_local;
+        mg->lv[l].deeper = op;
+    }
+    *out = mg;
+    return MGCR_OK;
+}
+
+#define LEVEL_CHECK(mg, level) ARG_CHECK((mg) && (level) >= 0 && (level) < (mg)->n_level, "MG: level %d out of range", (level))
+
+extern "C" int mgcr_mg_level_info(mgcr_mg* mg, int level, int64_t* n_fine, int64_t* n_blocks, int* ne, int64_t* block_len) {
+    LEVEL_CHECK(mg, level);
+    const MgLevel& L = mg->lv[level];
+    if (n_fine) *n_fine = L.n;
+    if (n_blocks) *n_blocks = L.g.nb;
+    if (ne) *ne = L.g.ne;
+    if (block_len) *block_len = L.g.bl;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_mg_export_block_map(mgcr_mg* mg, int level, int64_t* h) {
+    LEVEL_CHECK(mg, level);
+    ARG_CHECK(h, "NULL output");
+    const MgLevel& L = mg->lv[level];
+    CUDA_TRY(cudaMemcpyAsync(h, L.d_block_map, sizeof(int64_t) * L.nsite, cudaMemcpyDeviceToHost, mg->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(mg->ctx->stream));
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_mg_export_prolongator(mgcr_mg* mg, int level, mgcr_c128* h) {
+    LEVEL_CHECK(mg, level);
+    ARG_CHECK(h, "NULL output");
+    const MgLevel& L = mg->lv[level];
+    CUDA_TRY(cudaMemcpyAsync(h, L.d_P, sizeof(c128) * L.n * L.g.ne, cudaMemcpyDeviceToHost, mg->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(mg->ctx->stream));
+    return MGCR_OK;
+}
+
+// The reference's pattern (HierarchicalSparse.h:58-98 fed by MG.h:217-276): always 9 blocks per row, explicit zero
+// blocks where a neighbour coincides with the block itself or with the other neighbour, sorted by (row, col) with
+// ties in triplet order; blocks row-major.
+extern "C" int mgcr_mg_export_coarse(mgcr_mg* mg, int level, int64_t* h_brow, int64_t* h_bcol, mgcr_c128* h_bval) {
+    LEVEL_CHECK(mg, level);
+    ARG_CHECK(h_brow && h_bcol && h_bval, "NULL output");
+    const MgLevel& L = mg->lv[level];
+    const LevelGeom& g = L.g;
+    const int ne = g.ne, K = L.K;
+    const size_t bsz = (size_t)ne * ne;
+    std::vector<c128> val((size_t)g.nb * K * bsz);
+    std::vector<int8_t> slot((size_t)g.nb * K);
+    CUDA_TRY(cudaMemcpyAsync(val.data(), L.Ac->d_bval, sizeof(c128) * val.size(), cudaMemcpyDeviceToHost, mg->ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(slot.data(), L.d_bslot, slot.size(), cudaMemcpyDeviceToHost, mg->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(mg->ctx->stream));
+    for (int64_t R = 0; R < g.nb; R++) {
+        h_brow[R] = 9 * R;
+        int64_t bi[4], rem = R;
+        for (int c = 3; c >= 0; c--) { bi[c] = rem % g.bd[c]; rem /= g.bd[c]; }
+        struct Ent { int64_t col; int s; bool zero; } ent[9];
+        ent[0] = {R, 0, false};
+        for (int d = 0; d < 4; d++) {
+            int64_t stride = 1;
+            for (int c = 3; c > d; c--) stride *= g.bd[c];
+            int64_t m = (bi[d] - 1 + g.bd[d]) % g.bd[d], p = (bi[d] + 1) % g.bd[d];
+            ent[2 * d + 1] = {R + (m - bi[d]) * stride, 2 * d + 1, g.bd[d] < 2};
+            ent[2 * d + 2] = {R + (p - bi[d]) * stride, 2 * d + 2, g.bd[d] < 3};
+        }
+        std::stable_sort(ent, ent + 9, [](const Ent& a, const Ent& b) { return a.col < b.col || (a.col == b.col && a.s < b.s); });
+        for (int a = 0; a < 9; a++) {
+            h_bcol[9 * R + a] = ent[a].col;
+            mgcr_c128* dst = h_bval + (size_t)(9 * R + a) * bsz;
+            int src = -1;
+            if (!ent[a].zero) for (int q = 0; q < K; q++) if (slot[R * K + q] == ent[a].s) src = q;
+            for (int r = 0; r < ne; r++) for (int c = 0; c < ne; c++) {
+                c128 v = src < 0 ? cmake(0., 0.) : val[(size_t)(R * K + src) * bsz + (size_t)c * ne + r];
+                dst[(size_t)r * ne + c].re = v.x; dst[(size_t)r * ne + c].im = v.y;
+            }
+        }
+    }
+    h_brow[g.nb] = 9 * g.nb;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_mg_coarse_op(mgcr_mg* mg, int level, mgcr_op** out) {
+    LEVEL_CHECK(mg, level);
+    ARG_CHECK(out, "NULL output");
+    *out = mg->lv[level].Ac;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_mg_restrict(mgcr_ctx* ctx, mgcr_mg* mg, int level, const mgcr_c128* fine, mgcr_c128* coarse) {
+    LEVEL_CHECK(mg, level);
+    ARG_CHECK(ctx && fine && coarse, "NULL argument");
+    return mg_restrict(ctx, mg->lv[level], (const c128*)fine, (c128*)coarse);
+}
+
+extern "C" int mgcr_mg_prolong(mgcr_ctx* ctx, mgcr_mg* mg, int level, const mgcr_c128* coarse, mgcr_c128* fine) {
+    LEVEL_CHECK(mg, level);
+    ARG_CHECK(ctx && fine && coarse, "NULL argument");
+    return mg_prolong(ctx, mg->lv[level], (const c128*)coarse, (c128*)fine);
+}
+
+extern "C" int mgcr_mg_cycle(mgcr_ctx* ctx, mgcr_mg* mg, int level, const mgcr_c128* b, mgcr_c128* x) {
+    LEVEL_CHECK(mg, level);
+    ARG_CHECK(ctx && b && x, "NULL argument");
+    return mg_cycle(mg, level, (const c128*)b, (c128*)x);
+}
+
+extern "C" int mgcr_mg_op_create(mgcr_ctx* ctx, mgcr_mg* mg, mgcr_op** out) {
+    ARG_CHECK(ctx && mg && out, "mgcr_mg_op_create: NULL argument");
+    MgOp* op = new MgOp();
+    op->kind = OP_MG; op->ctx = ctx; op->mg = mg; op->level = 0;
+    op->n_local = mg->lv[0].n; op->n_global = op->n_local;
+    *out = op;
+    return MGCR_OK;
+}
+
+// the distributed CSR entry point lives here until the slab-partitioned hierarchy lands
+extern "C" int mgcr_csr_create_dist(mgcr_ctx*, int64_t, int64_t, int64_t, const int64_t*, const int64_t*, const mgcr_c128*, mgcr_op**) {
+    mgcr_set_error("mgcr_csr_create_dist: not available yet");
+    return MGCR_ERR_UNSUPPORTED;
+}

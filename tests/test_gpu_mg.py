@@ -1,0 +1,259 @@
+"""GPU parity tests of the multigrid hierarchy (run with -m gpu): aggregation and sparsity pattern bit-exact against
+the unmodified reference's MG::initialise (tests/golden/hierarchy.npz), prolongator / coarse blocks / restrict / expand /
+coarse apply to rounding, the Algorithm-2 cycle and the MG-preconditioned GCR against the oracle's restatement (which is
+itself pinned against the reference's public pieces, tests/golden/mgsolve.npz)."""
+import numpy as np
+import pytest
+
+from conftest import check_hist, perturbed, reference_envelope, relerr
+
+pytestmark = pytest.mark.gpu
+
+HIER = {"mg_s2_e2": (2, 2, False), "mg_s1_e1": (1, 1, True), "mg_s2_e3": (2, 3, False)}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mgpreconditionedgcr_b200 import host
+    c = host.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import pyoracle
+    return pyoracle
+
+
+@pytest.fixture(scope="module")
+def host():
+    from mgpreconditionedgcr_b200 import host
+    return host
+
+
+def c1_ops(ctx, host, orc, c1):
+    A = host.DiracOp(ctx, host.Sparse(ctx, c1["n"], c1["n"], c1["row"], c1["col"], c1["val"]), c1["k"])
+    Ao = orc.dirac(orc.csr(c1["n"], c1["n"], c1["row"], c1["col"], c1["val"]), c1["k"])
+    return A, Ao
+
+
+def c1_params(host):
+    return (host.GCR_Param(0, 10, 10, 1e-8, False, None, None), host.GCR_Param(0, 10, 50, 1e-2, False, None, None),
+            host.GCR_Param(0, 10, 0, 1e-8, False, None, None))
+
+
+def c1_mg(ctx, host, A, golden, tag, neg_bug=None, nearnull=True, std_conj=False):
+    sub, nv, bug = HIER[tag]
+    lv = [dict(site_dims=[4, 4, 4, 4], sub=[sub] * 4, n_spin=4, n_col=3, n_eigen=nv)]
+    nn = golden.hierarchy[tag + "_nearnull"] if nearnull else None
+    e, c, s = c1_params(host)
+    return host.MG(ctx, A, lv, e, c, s, neg_bug=bug if neg_bug is None else neg_bug, std_conj=std_conj, nearnull=nn)
+
+
+def test_arnoldi_near_null_vectors(ctx, host, orc, golden, c1):
+    A, _ = c1_ops(ctx, host, orc, c1)
+    v = host.arnoldi(ctx, A, host.GCR_Param(0, 10, 10, 1e-8, False, None, None), 2).numpy()
+    ref = golden.hierarchy["mg_s2_e2_nearnull"]
+    assert relerr(v, ref) < 1e-9
+
+
+@pytest.mark.parametrize("tag", list(HIER))
+def test_hierarchy_against_reference(ctx, host, orc, golden, c1, tag):
+    h = golden.hierarchy
+    A, _ = c1_ops(ctx, host, orc, c1)
+    mg = c1_mg(ctx, host, A, golden, tag)
+    i = mg.info()
+    nb, ne = i["n_blocks"], i["ne"]
+    # aggregation and sparsity pattern: bit exact
+    assert np.array_equal(mg.block_map().reshape(-1), h[tag + "_block_map"])
+    brow, bcol, bval = mg.coarse()
+    assert np.array_equal(brow, h[tag + "_coarse_row"]) and brow[-1] == 9 * nb
+    assert np.array_equal(bcol, h[tag + "_coarse_col"])
+    # prolongator: the reference's Gram-Schmidt with tree-reduced instead of sequential inner products
+    P = mg.prolongator()
+    assert relerr(P.reshape(-1), h[tag + "_prolongator"]) < 1e-13
+    # coarse blocks, per-row multisets keyed by column (the reference's sort is unstable on duplicates, Q10)
+    ref_val = h[tag + "_coarse_val"].reshape(9 * nb, ne, ne)
+    scale = np.abs(ref_val).max()
+    for r in range(nb):
+        sl = slice(brow[r], brow[r + 1])
+        for c in np.unique(bcol[sl]):
+            m = bval[sl][bcol[sl] == c].sum(axis=0)
+            q = ref_val[sl][bcol[sl] == c].sum(axis=0)
+            assert np.abs(m - q).max() < 1e-12 * scale
+    f = ctx.init_rand(42, c1["n"])
+    rc = mg.restrict(f)
+    assert relerr(rc.numpy(), h[tag + "_restrict_f42"]) < 1e-13
+    assert relerr(mg.expand(ctx.from_numpy(h[tag + "_restrict_f42"])).numpy(), h[tag + "_expand_restrict_f42"]) < 1e-13
+    assert relerr(mg.coarse_op()(rc).numpy(), h[tag + "_coarse_apply"]) < 1e-12
+
+
+def test_expand_is_bit_exact_given_the_same_prolongator(ctx, host, orc, golden, c1):
+    """prolong does the reference's operations in the reference's order: feed it the oracle's inputs and compare bits"""
+    A, Ao = c1_ops(ctx, host, orc, c1)
+    mg = c1_mg(ctx, host, A, golden, "mg_s2_e3")
+    xc = orc.init_rand(5, mg.info()["n_blocks"] * mg.info()["ne"])
+    P = mg.prolongator()
+    bm = mg.block_map()
+    out = mg.expand(ctx.from_numpy(xc)).numpy()
+    ref = np.zeros(c1["n"], dtype=np.complex128).reshape(-1, 12)
+    ne = mg.info()["ne"]
+    for b in range(P.shape[0]):
+        acc = np.zeros(P.shape[2], dtype=np.complex128)
+        for e in range(ne):
+            a = xc[b * ne + e]
+            pv = P[b, e]
+            t = np.empty_like(pv)
+            t.real = a.real * pv.real - a.imag * pv.imag
+            t.imag = a.real * pv.imag + a.imag * pv.real
+            acc = acc + t
+        ref[bm[b]] = acc.reshape(-1, 12)
+    assert np.array_equal(out, ref.reshape(-1))
+
+
+def test_galerkin_identity_and_neg_neighbour_switch(ctx, host, orc, golden, c1):
+    """R M P R v = m_c R v holds for the correct operator and fails for the reference's negative-neighbour variant
+    (src/MG.h:263) once a direction has >= 3 aggregates."""
+    A, _ = c1_ops(ctx, host, orc, c1)
+    v = ctx.init_rand(3, c1["n"])
+    err = {}
+    for bug in (False, True):
+        mg = c1_mg(ctx, host, A, golden, "mg_s1_e1", neg_bug=bug)
+        rv = mg.restrict(v)
+        lhs = mg.coarse_op()(rv).numpy()
+        rhs = mg.restrict(A(mg.expand(rv))).numpy()
+        err[bug] = relerr(lhs, rhs)
+        assert relerr(mg.restrict(mg.expand(rv)).numpy(), rv.numpy()) < 1e-13      # R P = 1 (src/main.cpp:899-909)
+    assert err[False] < 1e-13
+    assert err[True] > 1e-2
+
+
+def test_cycle_and_mg_gcr_against_reference_assembly(ctx, host, orc, golden, c1):
+    g = golden.mgsolve
+    A, Ao = c1_ops(ctx, host, orc, c1)
+    mg = c1_mg(ctx, host, A, golden, "mg_s2_e3", nearnull=False)
+    z = mg.cycle(ctx.init_rand(7, c1["n"]))
+    assert relerr(z.numpy(), g["mgsolve_stdconj_e3_cycle_f7"]) < 1e-8
+    e, c, s = (orc.gcr_param(0, 10, 10, 1e-8), orc.gcr_param(0, 10, 50, 1e-2), orc.gcr_param(0, 10, 0, 1e-8))
+    lv = [dict(site_dims=[4, 4, 4, 4], sub=[2] * 4, n_spin=4, n_col=3, n_eigen=3)]
+    rhs = orc.init_rand(0, c1["n"])
+    for tag, std in (("mgsolve_stdconj_e3", 1), ("mgsolve_refconj_e3", 0)):
+        mgs = mg   # inner solvers keep the reference convention (they are the reference's own GCR::solve in the golden run)
+        x = ctx.field(c1["n"]).set_zero()
+        p = host.GCR_Param(0, 2, 200, 1e-13, False, None, mgs, std_conj=bool(std))
+        it, hist = host.GCR(ctx, A, p).solve(ctx.from_numpy(rhs), x)
+        ref = g[tag + "_hist"]
+        # The inner coarse solves stop on a 1e-2 tolerance: the preconditioner is a discontinuous function of its
+        # input and the outer history is only reproducible inside the reference algorithm's own perturbation envelope
+        # (the restatement, rhs perturbed by 1e-16) -- the bar the oracle itself is held to against the reference.
+        mo = orc.MG(Ao, lv, e, c, s)
+        env, spread = reference_envelope(perturbed(orc, Ao, orc.gcr_param(0, 2, 200, 1e-13, std_conj=std), rhs, precond=mo.as_op()),
+                                         ref, len(ref) - 1)
+        check_hist(hist, ref, it, len(ref) - 1, env, max(spread, 4), tol=1e-8)
+        assert np.max(np.abs(hist[:8] - ref[:8]) / ref[:8]) < 1e-7
+        if std:
+            assert hist[-1] <= 1e-13 and relerr(x.numpy(), g[tag + "_x"]) < 1e-8
+
+
+def scalar_levels(dims, subs, n_eigen):
+    """level configs of a 3-D scalar lattice: site_dims = [1, nz, ny, nx], coarse dof = ne of the level above"""
+    lv, cur, ncol = [], list(dims), 1
+    for sub, ne in zip(subs, n_eigen):
+        lv.append(dict(site_dims=[1] + cur, sub=[1] + [sub] * 3, n_spin=1, n_col=ncol, n_eigen=ne))
+        cur = [d // sub for d in cur]
+        ncol = ne
+    return lv
+
+
+@pytest.mark.parametrize("form", ["stencil", "csr"])
+def test_two_level_scalar_3d_against_oracle(ctx, host, orc, form):
+    dims = [8, 8, 8]
+    n = 512
+    k = 1.0 / 6.01
+    D = host.Hopping(ctx, dims) if form == "stencil" else host.Sparse(ctx, n, n, *host.hopping_csr(dims))
+    A = host.DiracOp(ctx, D, k)
+    Ao = orc.dirac(orc.hopping(dims), k)
+    lv = scalar_levels(dims, [4], [3])
+    # same near-null vectors on both sides: the oracle's inverse iteration
+    vecs = orc.arnoldi(Ao, orc.gcr_param(0, 10, 10, 1e-8), 3)
+    mo = orc.MG(Ao, lv, orc.gcr_param(0, 10, 10, 1e-8), orc.gcr_param(0, 10, 50, 1e-2), orc.gcr_param(0, 4, 3, 1e-8), nearnull=vecs)
+    mg = host.MG(ctx, A, lv, host.GCR_Param(0, 10, 10, 1e-8), host.GCR_Param(0, 10, 50, 1e-2), host.GCR_Param(0, 4, 3, 1e-8), nearnull=vecs)
+    assert mg.info()["n_blocks"] == 8 and mg.info()["ne"] == 3
+    assert np.array_equal(mg.block_map(), mo.block_map())
+    assert relerr(mg.prolongator(), mo.prolongator()) < 1e-13
+    bo, co, vo = mo.coarse()
+    bg, cg, vg = mg.coarse()
+    assert np.array_equal(bo, bg) and np.array_equal(co, cg)
+    assert np.abs(vg - vo).max() < 1e-13 * np.abs(vo).max()
+    v = orc.init_rand(3, n)
+    rv = mg.restrict(ctx.from_numpy(v))
+    assert relerr(rv.numpy(), mo.restrict(v)) < 1e-13
+    assert relerr(mg.coarse_op()(rv).numpy(), mg.restrict(A(mg.expand(rv))).numpy()) < 1e-13
+    b7 = orc.init_rand(7, n)
+    assert relerr(mg.cycle(ctx.from_numpy(b7)).numpy(), mo.cycle(b7)) < 1e-9
+    rhs = orc.init_rand(0, n)
+    x = ctx.field(n).set_zero()
+    it, hist = host.GCR(ctx, A, host.GCR_Param(0, 10, 1000, 1e-10, False, None, mg)).solve(ctx.from_numpy(rhs), x)
+    xo, ho, ito = orc.gcr_solve(Ao, orc.gcr_param(0, 10, 1000, 1e-10), rhs, precond=mo.as_op())
+    assert abs(it - ito) <= 1 and hist[-1] <= 1e-10
+    m = min(len(hist), len(ho))
+    assert np.max(np.abs(np.log10(hist[:m]) - np.log10(ho[:m]))) < 0.3
+    assert np.max(np.abs(hist[:4] - ho[:4]) / ho[:4]) < 1e-7
+    assert relerr(A(x).numpy(), rhs) < 1.5e-10
+    # and the preconditioner pays: fewer outer iterations than plain GCR
+    x0 = ctx.field(n).set_zero()
+    it0, _ = host.GCR(ctx, A, host.GCR_Param(0, 10, 1000, 1e-10, False, None, None)).solve(ctx.from_numpy(rhs), x0)
+    assert it < it0
+
+
+def test_three_level_scalar_3d(ctx, host, orc):
+    dims = [16, 16, 16]
+    n = 4096
+    k = 1.0 / 6.01
+    A = host.DiracOp(ctx, host.Hopping(ctx, dims), k)
+    Ao = orc.dirac(orc.hopping(dims), k)
+    lv = scalar_levels(dims, [4, 2], [4, 4])
+    mg = host.MG(ctx, A, lv, host.GCR_Param(0, 10, 10, 1e-8), host.GCR_Param(0, 10, 20, 1e-2), host.GCR_Param(0, 4, 3, 1e-8))
+    assert mg.info(0)["n_blocks"] == 64 and mg.info(1)["n_blocks"] == 8 and mg.info(1)["n_fine"] == 256
+    # Galerkin identity on both levels
+    v = ctx.init_rand(3, n)
+    rv = mg.restrict(v, 0)
+    assert relerr(mg.coarse_op(0)(rv).numpy(), mg.restrict(A(mg.expand(rv, 0)), 0).numpy()) < 1e-13
+    rrv = mg.restrict(rv, 1)
+    A1 = mg.coarse_op(0)
+    assert relerr(mg.coarse_op(1)(rrv).numpy(), mg.restrict(A1(mg.expand(rrv, 1)), 1).numpy()) < 1e-13
+    rhs = orc.init_rand(0, n)
+    x = ctx.field(n).set_zero()
+    it, hist = host.GCR(ctx, A, host.GCR_Param(0, 10, 200, 1e-10, False, None, mg)).solve(ctx.from_numpy(rhs), x)
+    assert hist[-1] <= 1e-10 and relerr(A(x).numpy(), rhs) < 1.5e-10
+    # the oracle's three-level K-cycle on the same problem converges in a comparable number of iterations
+    mo = orc.MG(Ao, lv, orc.gcr_param(0, 10, 10, 1e-8), orc.gcr_param(0, 10, 20, 1e-2), orc.gcr_param(0, 4, 3, 1e-8))
+    _, ho, ito = orc.gcr_solve(Ao, orc.gcr_param(0, 10, 200, 1e-10), rhs, precond=mo.as_op())
+    assert abs(it - ito) <= 2
+
+
+def test_mg_rejects_bad_configuration(ctx, host):
+    A = host.DiracOp(ctx, host.Hopping(ctx, [8, 8, 8]), 0.16)
+    e, c, s = c1_params(host)
+    with pytest.raises(Exception):   # aggregate size does not divide the lattice (src/Mesh.h:245)
+        host.MG(ctx, A, [dict(site_dims=[1, 8, 8, 8], sub=[1, 3, 4, 4], n_eigen=2)], e, c, s)
+    with pytest.raises(Exception):   # mesh does not match the operator (src/GCR.h:160)
+        host.MG(ctx, A, [dict(site_dims=[1, 8, 8, 4], sub=[1, 4, 4, 4], n_eigen=2)], e, c, s)
+
+
+def test_config3_shape_64cubed_three_levels(ctx, host):
+    """BASELINE.json config 3 at 1/64 of its volume: 64^3, aggregates 4^3 -> 16^3 -> 4^3, MG-GCR to 1e-10"""
+    dims = [64, 64, 64]
+    n = 64 ** 3
+    A = host.DiracOp(ctx, host.Hopping(ctx, dims), 1.0 / 6.01)
+    lv = scalar_levels(dims, [4, 4], [8, 8])
+    mg = host.MG(ctx, A, lv, host.GCR_Param(0, 10, 10, 1e-8), host.GCR_Param(0, 10, 20, 1e-2), host.GCR_Param(0, 4, 3, 1e-8))
+    rhs = ctx.init_rand(0, n)
+    x = ctx.field(n).set_zero()
+    it, hist = host.GCR(ctx, A, host.GCR_Param(0, 10, 300, 1e-10, False, None, mg)).solve(rhs, x)
+    r = rhs - A(x)
+    assert hist[-1] <= 1e-10 and r.norm() / rhs.norm() < 1.5e-10
+    x0 = ctx.field(n).set_zero()
+    it0, _ = host.GCR(ctx, A, host.GCR_Param(0, 10, 3000, 1e-10, False, None, None)).solve(rhs, x0)
+    assert it * 4 < it0
