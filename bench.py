@@ -38,6 +38,32 @@ WORKLOADS = {
                       desc="3-D 7-point 512^3, I - H/(6+0.01), unpreconditioned restart-10 GCR to 1e-10",
                       cpu_sample=[96, 96, 96], cpu_iters=10),
 }
+MG_DEFAULT = dict(eigen=(0, 10, 10, 1e-8), coarse=(0, 10, 20, 1e-2), smooth=(0, 4, 3, 1e-8))
+WORKLOADS.update({
+    # BASELINE.json configs[2]: 3-level hierarchy 256^3 -> 64^3 -> 16^3
+    "mg3d_256": dict(dims=[256, 256, 256], m2=0.01, restart=10, tol=1e-10, max_iter=1000,
+                     mg=dict(subs=[4, 4], n_eigen=[4, 4], **MG_DEFAULT),
+                     desc="3-D 7-point 256^3, I - H/(6+0.01), 3-level MG (4^3 aggregates, 4 near-null vectors) preconditioned restart-10 GCR to 1e-10",
+                     cpu_sample=[64, 64, 64], cpu_iters=0),
+    # BASELINE.json configs[3]: 4-level hierarchy 512^3 -> 128^3 -> 32^3 -> 8^3
+    "mg3d_512": dict(dims=[512, 512, 512], m2=0.01, restart=10, tol=1e-10, max_iter=1000,
+                     mg=dict(subs=[4, 4, 4], n_eigen=[4, 4, 4], **MG_DEFAULT),
+                     desc="3-D 7-point 512^3, I - H/(6+0.01), 4-level MG (4^3 aggregates, 4 near-null vectors) preconditioned restart-10 GCR to 1e-10",
+                     cpu_sample=[64, 64, 64], cpu_iters=0),
+})
+
+
+def scalar_levels(dims, subs, n_eigen):
+    """MG level configs of a 3-D scalar lattice: site_dims = [1, nz, ny, nx]; the dof of a coarse level is the number of
+    near-null vectors of the level above (coarse index = block * ne + e, reference src/MG.h:359,378)"""
+    lv, cur, ncol = [], list(dims), 1
+    for sub, ne in zip(subs, n_eigen):
+        lv.append(dict(site_dims=[1] + cur, sub=[1] + [sub] * 3, n_spin=1, n_col=ncol, n_eigen=ne))
+        cur = [d // sub for d in cur]
+        ncol = ne
+    return lv
+
+
 # iteration counts measured on B200 (parity-checked against the CPU oracle at reduced size); used by the reference
 # arm, which cannot afford the full CPU solve, to extrapolate time-to-solution.  Updated from BENCH logs.
 KNOWN_ITERS = {}
@@ -111,6 +137,24 @@ def reference_cpu_sample(wl):
     V = 1
     for d in dims:
         V *= d
+    if wl.get("mg"):
+        # The reference's MG is two-level, 6-D only and returns an uninitialised buffer: it cannot
+        # run this workload.  The CPU arm is the C restatement of the same algorithm (oracle/mgcr_oracle.c), 1 thread.
+        import numpy as np  # noqa: F401
+        from oracle import pyoracle as orc
+        m = wl["mg"]
+        H = orc.hopping(dims)
+        A = orc.dirac(H, 1.0 / (2 * len(dims) + wl["m2"]))
+        lv = scalar_levels(dims, m["subs"], m["n_eigen"])
+        t0 = time.perf_counter()
+        mg = orc.MG(A, lv, orc.gcr_param(*m["eigen"]), orc.gcr_param(*m["coarse"]), orc.gcr_param(*m["smooth"]))
+        t1 = time.perf_counter()
+        rhs = orc.init_rand(0, H.n)
+        _, h, it = orc.gcr_solve(A, orc.gcr_param(0, wl["restart"], wl["max_iter"], wl["tol"]), rhs, precond=mg.as_op())
+        t2 = time.perf_counter()
+        return dict(kind="port", cores=1, V=V, iters=it, sec_per_iter=(t2 - t1) / max(it, 1), spmv_seconds=None, setup_seconds=t1 - t0,
+                    sample="C restatement (oracle/mgcr_oracle.c, 1 thread; the reference's own MG cannot run 3-D multi-level problems) of the "
+                           "same %d-level MG-GCR on %s: %d outer iterations to %.1e" % (len(lv) + 1, "x".join(map(str, dims)), it, h[-1]))
     if os.path.exists(ref):
         cwd = os.path.join(ROOT, "oracle", "_ref", "work", "run", "a")
         os.makedirs(cwd, exist_ok=True)
@@ -203,6 +247,8 @@ def main():
         ids = [host.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.init_dist(rank, world, ids[0])
+    if wl.get("mg") and args.operator == "csr" and args.workload == "mg3d_512":
+        args.operator = "stencil"   # the stored 512^3 operator (22.5 GB) plus the hierarchy is built matrix-free by default
     if world > 1 and args.operator == "csr":
         args.operator = "stencil"   # TODO(dist csr)
     dims = wl["dims"]
@@ -226,7 +272,16 @@ def main():
         plane = V // dims[0]
         rhs = ctx.init_rand(0, n_local, skip=b * plane)
     x = ctx.field(n_local)
-    param = host.GCR_Param(0, wl["restart"], wl["max_iter"], wl["tol"], False, None, None)
+    mg = None
+    setup_seconds = None
+    if wl.get("mg"):
+        m = wl["mg"]
+        t0 = time.perf_counter()
+        mg = host.MG(ctx, A, scalar_levels(dims, m["subs"], m["n_eigen"]), host.GCR_Param(*m["eigen"]), host.GCR_Param(*m["coarse"]),
+                     host.GCR_Param(*m["smooth"]))
+        ctx.sync()
+        setup_seconds = time.perf_counter() - t0
+    param = host.GCR_Param(0, wl["restart"], wl["max_iter"], wl["tol"], False, None, mg)
     gcr = host.GCR(ctx, A, param)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
 
@@ -247,7 +302,6 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ctx.set_profile(True)
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -258,6 +312,12 @@ def main():
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - l0
+    # one more step of the same solve with every launch bracketed by pooled CUDA events on the library's stream (no
+    # synchronisation inside the loop): per-kernel-class device time and algorithmic bytes for the roofline.  Kept out
+    # of the timed steps because two extra event records per launch slow the launch-bound coarse-level solves down.
+    ctx.set_profile(True)
+    step()
+    sync_all()
     prof = ctx.profile()
     ctx.set_profile(False)
     clk = clocks.stop() if rank == 0 else None
@@ -285,7 +345,7 @@ def main():
             h_x.zero_()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            capi.check(ctx.lib.mgcr_gcr_solve_host(ctx.h, A.h, C.byref(param), None, None, C.c_void_p(h_rhs.data_ptr()), C.c_void_p(h_x.data_ptr()),
+            capi.check(ctx.lib.mgcr_gcr_solve_host(ctx.h, A.h, C.byref(param), None, mg.h if mg else None, C.c_void_p(h_rhs.data_ptr()), C.c_void_p(h_x.data_ptr()),
                                                    capi.ptr(hist), 2, C.byref(itc)))
             times.append(time.perf_counter() - t0)
         e2e = {"value": min(times), "unit": "s", "h2d_bytes_per_step": 2 * 16 * V, "d2h_bytes_per_step": 16 * V,
@@ -316,11 +376,11 @@ def main():
         "data": "synthetic",
         "config": {"workload": args.workload, "desc": wl["desc"], "operator": args.operator, "rows": V,
                    "l2": "inputs larger than L2 (every vector is %.0f MB, L2 is 126 MB)" % (16 * V / 1e6)},
-        "iterations": it, "final_true_rel_residual": final_rel,
+        "iterations": it, "final_true_rel_residual": final_rel, "mg_setup_seconds": setup_seconds,
         "gpu_launches": launches, "clocks": clk, "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "how": "algorithmic bytes of every launch of the class / its summed CUDA-event time over the timed steps"},
+                     "how": "algorithmic bytes of every launch of the class / its summed CUDA-event time (events on the library stream) over one more identical step after the timed ones"},
         "spmv": spmv, "kernels": classes,
     }
     if not args.no_cpu_baseline and world == 1:
