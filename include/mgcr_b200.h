@@ -133,6 +133,11 @@ int mgcr_dirac_set_k(mgcr_op* dirac, double k_re, double k_im);                 
  * already sorted block-CSR: nb block rows of dense ne x ne row-major blocks (Dense, Operator.h:32-54). */
 int mgcr_blockcsr_create(mgcr_ctx* ctx, int64_t nb, int ne, const int64_t* h_brow, const int64_t* h_bcol,
                          const mgcr_c128* h_bval, mgcr_op** out);
+/* Any other subclass of Operator<num_type> (Operator.h:16-29 is an open interface): the library calls fn(user, d_x,
+ * d_y) with DEVICE pointers of n elements whenever it needs y = A x; fn enqueues its work on the context's stream (or
+ * synchronises itself) and returns MGCR_OK.  Lets caller-defined operators be solved / used as preconditioners. */
+typedef int (*mgcr_apply_fn)(void* user, const mgcr_c128* d_x, mgcr_c128* d_y);
+int mgcr_callback_op_create(mgcr_ctx* ctx, int64_t n, mgcr_apply_fn fn, void* user, mgcr_op** out);
 /* Operator::operator()(const Field&) (Operator.h:18): y = A x.  x and y must not alias. */
 int mgcr_op_apply(mgcr_ctx* ctx, mgcr_op* op, const mgcr_c128* d_x, mgcr_c128* d_y);
 int mgcr_op_dim(mgcr_op* op, int64_t* n_local, int64_t* n_global);                   /* Operator.h:20 get_dim  */

@@ -79,6 +79,7 @@ SIGNATURES = {
     "mgcr_dirac_create": [_vp, _vp, _dbl, _dbl, _vp, _pvp],
     "mgcr_dirac_set_k": [_vp, _dbl, _dbl],
     "mgcr_blockcsr_create": [_vp, _i64, _int, _vp, _vp, _vp, _pvp],
+    "mgcr_callback_op_create": [_vp, _i64, _vp, _vp, _pvp],
     "mgcr_op_apply": [_vp, _vp, _vp, _vp],
     "mgcr_op_dim": [_vp, _pi64, _pi64],
     "mgcr_op_apply_bytes": [_vp, _pdbl],

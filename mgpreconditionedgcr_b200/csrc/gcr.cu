@@ -12,6 +12,9 @@ int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* 
 int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out);
 int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a);
 
+int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const c128* rhs, c128* x, double* hist, int hist_cap,
+                    int* iters_out, int storage, int restart, int* handled);
+
 struct GcrOp : mgcr_op {
     mgcr_op* A = nullptr;
     mgcr_gcr_param prm;
@@ -21,26 +24,51 @@ struct GcrOp : mgcr_op {
     int apply(const c128* x, c128* y) override;
 };
 
-template <int NH>
+// ---- launch tables: exact history length NH (1..16), U elements per thread (dot) / MINB resident CTAs per SM (update)
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+template <int NH, int U>
 static void launch_dot_hist(mgcr_ctx* ctx, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
                             int std_conj, double* out) {
-    k_gcr_dot_hist<NH><<<grid, RED_THREADS, 0, ctx->stream>>>(n, Ar, Aps, stride, hl, std_conj, out, ctx->d_partials, ctx->d_ticket);
+    k_gcr_dot_hist<NH, U><<<grid, RED_THREADS, 0, ctx->stream>>>(n, Ar, Aps, stride, hl, std_conj, out, ctx->d_partials, ctx->d_ticket);
 }
 template <int NH>
+static void dot_hist_u(mgcr_ctx* ctx, int u, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
+                       int std_conj, double* out) {
+    if constexpr (NH <= 4) { if (u >= 4) return launch_dot_hist<NH, 4>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); }
+    if constexpr (NH <= 8) { if (u >= 2) return launch_dot_hist<NH, 2>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); }
+    launch_dot_hist<NH, 1>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out);
+}
+static void dot_hist(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
+                     int std_conj, double* out) {
+    static const int u_env = env_int("MGCR_DOT_U", 0);   // experiment knob
+    const int u = u_env ? u_env : (nh <= 1 ? 4 : nh <= 3 ? 2 : 1);
+    switch (nh) {
+#define C(NH) case NH: dot_hist_u<NH>(ctx, u, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
+        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
+#undef C
+    }
+}
+
+template <int NH, int MINB>
 static void launch_update_p(mgcr_ctx* ctx, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                             int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
                             int bden_off, double* scal) {
-    k_gcr_update_p<NH><<<grid, RED_THREADS, 0, ctx->stream>>>(n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
-                                                            bden_off, scal, ctx->d_partials, ctx->d_ticket);
+    k_gcr_update_p<NH, MINB><<<grid, RED_THREADS, 0, ctx->stream>>>(n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
+                                                                  bden_off, scal, ctx->d_partials, ctx->d_ticket);
 }
-
-static int pick_nh(int count) {
-    if (count <= 0) return 0;
-    if (count <= 1) return 1;
-    if (count <= 2) return 2;
-    if (count <= 4) return 4;
-    if (count <= 8) return 8;
-    return 16;
+static void update_p(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
+                     int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj, int bden_off,
+                     double* scal) {
+    static const int minb_env = env_int("MGCR_UPD_MINB", 0);   // experiment knob
+    const int minb = minb_env ? minb_env : 4;
+#define ARGS ctx, grid, n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal
+#define C(NH) case NH: if (minb >= 4) launch_update_p<NH, 4>(ARGS); else if (minb == 3) launch_update_p<NH, 3>(ARGS); else launch_update_p<NH, 2>(ARGS); break;
+    switch (nh) {
+        C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
+    }
+#undef C
+#undef ARGS
 }
 
 // stack of pinned read-back slots / events so that nested solves (preconditioners) never share one
@@ -76,6 +104,11 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     if (restart < 1) restart = 1;
     const bool aliased = (rhs == x);
     const int std_conj = prm->std_conj;
+    if (!right) {   // small operators: the whole solve as one persistent cooperative kernel (gcr_small.cu)
+        int handled = 0;
+        MGCR_TRY(gcr_solve_small(ctx, A, prm, rhs, x, hist, hist_cap, iters_out, storage, restart, &handled));
+        if (handled) return MGCR_OK;
+    }
     DepthGuard dg;
     SolveSlot slot;
     MGCR_TRY(acquire_slot(ctx, g_depth - 1, &slot));
@@ -138,17 +171,11 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
             GTRY(A->apply(zz, Ar));                                                               // GCR.h:242
             lim = std::min(storage, iter);                                                        // GCR.h:251
             for (int c0 = 0; c0 < lim; c0 += GCR_CHUNK) {                                         // GCR.h:257-258 numerators
-                HistList hl; hl.count = std::min((int)GCR_CHUNK, lim - c0);
-                for (int k = 0; k < hl.count; k++) hl.slot[k] = c0 + k;
-                double* out = scal + S_BNUM + 2 * c0;
-                ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + hl.count));
-                switch (pick_nh(hl.count)) {
-                    case 1: launch_dot_hist<1>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
-                    case 2: launch_dot_hist<2>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
-                    case 4: launch_dot_hist<4>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
-                    case 8: launch_dot_hist<8>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
-                    default: launch_dot_hist<16>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
-                }
+                HistList hl;
+                const int cnt = std::min((int)GCR_CHUNK, lim - c0);
+                for (int k = 0; k < GCR_CHUNK; k++) hl.slot[k] = k < cnt ? c0 + k : 0;
+                ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + cnt));
+                dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, scal + S_BNUM + 2 * c0);
             }
             GCUDA(cudaGetLastError());
         }
@@ -161,19 +188,12 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
             int new_slot = next_iter % storage;
             int nchunks = std::max(1, (lim + GCR_CHUNK - 1) / GCR_CHUNK);
             for (int c = 0; c < nchunks; c++) {
-                BetaList bl; bl.count = std::min((int)GCR_CHUNK, lim - c * GCR_CHUNK);
-                if (bl.count < 0) bl.count = 0;
-                for (int k = 0; k < bl.count; k++) { bl.slot[k] = c * GCR_CHUNK + k; bl.num_index[k] = c * GCR_CHUNK + k; }
+                BetaList bl;
+                const int cnt = std::max(0, std::min((int)GCR_CHUNK, lim - c * GCR_CHUNK));
+                for (int k = 0; k < GCR_CHUNK; k++) { bl.slot[k] = k < cnt ? c * GCR_CHUNK + k : 0; bl.num_index[k] = bl.slot[k]; }
                 int first = (c == 0), last = (c == nchunks - 1);
-                ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * bl.count + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0)));
-                switch (pick_nh(bl.count)) {
-                    case 0: launch_update_p<0>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
-                    case 1: launch_update_p<1>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
-                    case 2: launch_update_p<2>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
-                    case 4: launch_update_p<4>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
-                    case 8: launch_update_p<8>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
-                    default: launch_update_p<16>(ctx, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal); break;
-                }
+                ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * cnt + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0)));
+                update_p(ctx, cnt, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal);
             }
             GCUDA(cudaGetLastError());
             GTRY(dist_allreduce_sum(ctx, scal + S_ANUM, 3));

@@ -111,28 +111,46 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n,
     grid_reduce<1>(v, partials, ticket, scal + S_RR);
 }
 
-// batched <Ar, Aps[slot]> for up to GCR_CHUNK history vectors in one pass over Ar      (GCR.h:257-258)
-struct HistList { int count; int slot[GCR_CHUNK]; };
+// batched <Ar, Aps[slot]> for NH (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
+// U elements per thread and trip keep enough 128-bit loads in flight when NH is small.
+struct HistList { int slot[GCR_CHUNK]; };
 
-template <int NH>
+template <int NH, int U>
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                               int64_t stride, HistList hl, int std_conj, double* out /* 2*NH */,
                                                               double* partials, unsigned int* ticket) {
     double v[2 * NH];
 #pragma unroll
     for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
-    GRID_STRIDE(i, n) {
-        c128 a = ld_stream(Ar + i);
-        c128 h[NH];
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i0 + (U - 1) * T < n; i0 += T * U) {     // full trips: U*(1+NH) independent 128-bit loads in flight
+        c128 a[U], h[U][NH];
 #pragma unroll
-        for (int k = 0; k < NH; k++) h[k] = (k < hl.count) ? ld_stream(Aps + (int64_t)hl.slot[k] * stride + i) : cmake(0., 0.);
+        for (int u = 0; u < U; u++) {
+            a[u] = ld_stream(Ar + i0 + u * T);
+#pragma unroll
+            for (int k = 0; k < NH; k++) h[u][k] = ld_stream(Aps + (int64_t)hl.slot[k] * stride + i0 + u * T);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int k = 0; k < NH; k++) {
+                c128 t = std_conj ? cmulc(h[u][k], a[u]) : cmulc(a[u], h[u][k]);
+                v[2 * k] += t.x; v[2 * k + 1] += t.y;
+            }
+        }
+    }
+    for (; i0 < n; i0 += T) {                        // tail
+        const c128 a = ld_stream(Ar + i0);
 #pragma unroll
         for (int k = 0; k < NH; k++) {
-            c128 t = std_conj ? cmulc(h[k], a) : cmulc(a, h[k]);
+            const c128 h = ld_stream(Aps + (int64_t)hl.slot[k] * stride + i0);
+            c128 t = std_conj ? cmulc(h, a) : cmulc(a, h);
             v[2 * k] += t.x; v[2 * k + 1] += t.y;
         }
     }
-    grid_reduce<2 * NH>(v, partials, ticket, out, 2 * hl.count);
+    grid_reduce<2 * NH>(v, partials, ticket, out);
 }
 
 // p_new = z + sum_i(-beta_i ps[i]) ; Ap_new = Ar + sum_i(-beta_i Aps[i]) written into ring slot `cur`, with the next
@@ -140,16 +158,18 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, 
 // History slots are visited in the reference's order i = 0..lim-1.  More than GCR_CHUNK history vectors are
 // processed in several passes: all but the last accumulate pc / Apc in two scratch vectors (the ring slot `cur` may
 // itself still be unread history), the last one adds z / Ar, writes the slot and reduces.
-struct BetaList { int count; int slot[GCR_CHUNK]; int num_index[GCR_CHUNK]; };
+// NH is the exact number of history vectors of this pass; MINB (resident CTAs per SM) bounds the registers so that
+// long histories do not collapse the occupancy.
+struct BetaList { int slot[GCR_CHUNK]; int num_index[GCR_CHUNK]; };
 
-template <int NH>
-static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_p(int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps,
-                                                              c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
-                                                              c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, double* scal,
-                                                              double* partials, unsigned int* ticket) {
+template <int NH, int MINB>
+static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps,
+                                                                    c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
+                                                                    c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, double* scal,
+                                                                    double* partials, unsigned int* ticket) {
     constexpr int NHS = NH > 0 ? NH : 1;
     __shared__ c128 beta[NHS];
-    if ((int)threadIdx.x < NH && (int)threadIdx.x < bl.count) {
+    if ((int)threadIdx.x < NH) {
         int q = bl.num_index[threadIdx.x];
         beta[threadIdx.x] = cdivr(cmake(scal[S_BNUM + 2 * q], scal[S_BNUM + 2 * q + 1]), scal[bden_off + bl.slot[threadIdx.x]]);
     }
@@ -157,22 +177,37 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_p(int64_t n, 
     c128* pout = last ? ps + (int64_t)cur * stride : acc_p;
     c128* Apout = last ? Aps + (int64_t)cur * stride : acc_Ap;
     double v[3] = {0., 0., 0.};
+    constexpr int CH = 4;                    // history vectors loaded per batch: 2*CH 128-bit loads in flight per thread
+    constexpr int NFULL = (NH / CH) * CH;
     GRID_STRIDE(i, n) {
-        c128 hp[NHS], hA[NHS];
-#pragma unroll
-        for (int k = 0; k < NH; k++) {
-            if (k < bl.count) {
-                hp[k] = ld_plain(ps + (int64_t)bl.slot[k] * stride + i);
-                hA[k] = ld_plain(Aps + (int64_t)bl.slot[k] * stride + i);
-            }
-        }
         c128 pc = first ? cmake(0., 0.) : ld_plain(acc_p + i);
         c128 Apc = first ? cmake(0., 0.) : ld_plain(acc_Ap + i);
+#pragma unroll 1
+        for (int k0 = 0; k0 < NFULL; k0 += CH) {
+            c128 hp[CH], hA[CH];
 #pragma unroll
-        for (int k = 0; k < NH; k++) {
-            if (k < bl.count) {
-                pc = csub(pc, cmul(beta[k], hp[k]));
-                Apc = csub(Apc, cmul(beta[k], hA[k]));
+            for (int k = 0; k < CH; k++) {
+                hp[k] = ld_plain(ps + (int64_t)bl.slot[k0 + k] * stride + i);
+                hA[k] = ld_plain(Aps + (int64_t)bl.slot[k0 + k] * stride + i);
+            }
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                pc = csub(pc, cmul(beta[k0 + k], hp[k]));
+                Apc = csub(Apc, cmul(beta[k0 + k], hA[k]));
+            }
+        }
+        if (NH > NFULL) {
+            constexpr int TL = NH - NFULL > 0 ? NH - NFULL : 1;
+            c128 hp[TL], hA[TL];
+#pragma unroll
+            for (int k = 0; k < NH - NFULL; k++) {
+                hp[k] = ld_plain(ps + (int64_t)bl.slot[NFULL + k] * stride + i);
+                hA[k] = ld_plain(Aps + (int64_t)bl.slot[NFULL + k] * stride + i);
+            }
+#pragma unroll
+            for (int k = 0; k < NH - NFULL; k++) {
+                pc = csub(pc, cmul(beta[NFULL + k], hp[k]));
+                Apc = csub(Apc, cmul(beta[NFULL + k], hA[k]));
             }
         }
         if (last) {

@@ -13,6 +13,7 @@
 
 #include "kernels_blas.cuh"
 #include "mg.cuh"
+#include "rows.cuh"
 
 // ----------------------------------------------------------------------------------------------------------
 // small setup kernels
@@ -81,55 +82,6 @@ static __global__ void __launch_bounds__(128) k_block_mgs(LevelGeom g, c128* P) 
         __syncthreads();
     }
 }
-
-// ----------------------------------------------------------------------------------------------------------
-// row visitors: enumerate (column, value) of one fine row of a matrix-like operator
-// ----------------------------------------------------------------------------------------------------------
-struct SellRows {
-    const int64_t* slice_ptr; const int32_t* col; const c128* val;
-    int dirac; c128 k; const double* diag;
-    template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
-        const int64_t slice = i >> 5; const int lane = (int)(i & 31);
-        const int64_t base = slice_ptr[slice];
-        const int w = (int)((slice_ptr[slice + 1] - base) >> 5);
-        for (int t = 0; t < w; t++) {
-            c128 v = val[base + (int64_t)t * 32 + lane];
-            if (v.x == 0. && v.y == 0.) continue;
-            if (dirac) { v = cmul(k, v); v = cmake(-v.x, -v.y); }     // 1 - k D: src/Operator.h:111-112
-            f((int64_t)col[base + (int64_t)t * 32 + lane], v);
-        }
-        if (dirac) f(i, cmake(diag ? diag[i] : 1., 0.));
-    }
-};
-
-struct HopRows {
-    int64_t n2, n1, n0;   // local planes, rows, columns (single GPU: global)
-    int dirac; c128 k; const double* diag;
-    template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
-        const int64_t x = i % n0, y = (i / n0) % n1, z = i / (n0 * n1);
-        c128 v = cmake(1., 0.);
-        if (dirac) { v = cmul(k, v); v = cmake(-v.x, -v.y); }
-        if (z > 0) f(i - n0 * n1, v);
-        if (y > 0) f(i - n0, v);
-        if (x > 0) f(i - 1, v);
-        if (x < n0 - 1) f(i + 1, v);
-        if (y < n1 - 1) f(i + n0, v);
-        if (z < n2 - 1) f(i + n0 * n1, v);
-        if (dirac) f(i, cmake(diag ? diag[i] : 1., 0.));
-    }
-};
-
-struct BlockRows {
-    const int32_t* brow; const int32_t* bcol; const c128* bval; int ne;
-    template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
-        const int64_t R = i / ne; const int r = (int)(i - R * ne);
-        for (int l = brow[R]; l < brow[R + 1]; l++) {
-            const c128* m = bval + (int64_t)l * ne * ne + r;
-            const int64_t c0 = (int64_t)bcol[l] * ne;
-            for (int c = 0; c < ne; c++) f(c0 + c, m[(int64_t)c * ne]);
-        }
-    }
-};
 
 // ----------------------------------------------------------------------------------------------------------
 // Galerkin coarse blocks.  One CTA per coarse block row B.  Reference slots of a row (MG.h:217-276 seen from the row):
@@ -359,28 +311,9 @@ static int galerkin_launch(mgcr_ctx* ctx, MgLevel& L, const Rows& rows, int32_t*
 }
 
 static int galerkin(mgcr_ctx* ctx, MgLevel& L, int32_t* bcol, c128* bval) {
-    mgcr_op* A = L.A;
-    int dirac = 0; c128 k = cmake(0., 0.); const double* diag = nullptr;
-    if (A->kind == OP_DIRAC) {
-        DiracOp* d = static_cast<DiracOp*>(A);
-        dirac = 1; k = d->k; diag = d->d_diag; A = d->D;
-    }
-    if (A->kind == OP_SELL) {
-        SellOp* s = static_cast<SellOp*>(A);
-        SellRows r{s->d_slice_ptr, s->d_col, s->d_val, dirac, k, diag};
-        return galerkin_launch(ctx, L, r, bcol, bval);
-    }
-    if (A->kind == OP_HOPPING) {
-        HoppingOp* h = static_cast<HoppingOp*>(A);
-        HopRows r{h->n2_local, h->gdims[1], h->gdims[2], dirac, k, diag};
-        return galerkin_launch(ctx, L, r, bcol, bval);
-    }
-    if (A->kind == OP_BLOCKCSR && !dirac) {
-        BlockCsrOp* bo = static_cast<BlockCsrOp*>(A);
-        BlockRows r{bo->d_brow, bo->d_bcol, bo->d_bval, bo->ne};
-        return galerkin_launch(ctx, L, r, bcol, bval);
-    }
-    mgcr_set_error("MG setup: the operator of this level has no accessible matrix entries (kind %d)", (int)A->kind);
+    int st = MGCR_OK;
+    if (with_rows(L.A, [&](auto rows) { return galerkin_launch(ctx, L, rows, bcol, bval); }, &st)) return st;
+    mgcr_set_error("MG setup: the operator of this level has no accessible matrix entries (kind %d)", (int)L.A->kind);
     return MGCR_ERR_UNSUPPORTED;
 }
 

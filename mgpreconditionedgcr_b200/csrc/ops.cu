@@ -417,6 +417,26 @@ extern "C" int mgcr_blockcsr_create(mgcr_ctx* ctx, int64_t nb, int ne, const int
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// caller-implemented operators
+// ----------------------------------------------------------------------------------------------------------
+int CallbackOp::apply(const c128* x, c128* y) {
+    ARG_CHECK(x != y, "operator apply: input and output alias");
+    ctx->launches++;
+    int st = fn(user, (const mgcr_c128*)x, (mgcr_c128*)y);
+    if (st != MGCR_OK) mgcr_set_error("callback operator returned status %d", st);
+    return st;
+}
+
+extern "C" int mgcr_callback_op_create(mgcr_ctx* ctx, int64_t n, mgcr_apply_fn fn, void* user, mgcr_op** out) {
+    ARG_CHECK(ctx && fn && out && n >= 0, "mgcr_callback_op_create: bad argument");
+    CallbackOp* op = new CallbackOp();
+    op->kind = OP_CALLBACK; op->ctx = ctx; op->fn = fn; op->user = user;
+    op->n_local = n; op->n_global = n;
+    *out = op;
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // generic entry points
 // ----------------------------------------------------------------------------------------------------------
 extern "C" int mgcr_op_apply(mgcr_ctx* ctx, mgcr_op* op, const mgcr_c128* x, mgcr_c128* y) {

@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-enum OpKind { OP_SELL = 1, OP_HOPPING = 2, OP_DIRAC = 3, OP_BLOCKCSR = 4, OP_GCR = 5, OP_MG = 6 };
+enum OpKind { OP_SELL = 1, OP_HOPPING = 2, OP_DIRAC = 3, OP_BLOCKCSR = 4, OP_GCR = 5, OP_MG = 6, OP_CALLBACK = 7 };
 
 // Ghost-exchange plan of a row-slab-partitioned operator: which local elements each peer needs from us (pack list)
 // and where what we receive lands in the ghost buffer that the kernels address as column n_local + g.
@@ -81,6 +81,14 @@ struct BlockCsrOp : mgcr_op {
     ~BlockCsrOp() override;
     int apply(const c128* x, c128* y) override;
     double apply_bytes() const override { return (double)nnzb * (16. * ne * ne + 4.) + 32. * (double)nb * ne; }
+};
+
+// An Operator<num_type> subclass implemented by the caller (src/Operator.h:16-29 is an open interface): apply() calls back
+// into host code with DEVICE pointers; the callee enqueues its work on the context's stream (or synchronises itself).
+struct CallbackOp : mgcr_op {
+    mgcr_apply_fn fn = nullptr;
+    void* user = nullptr;
+    int apply(const c128* x, c128* y) override;
 };
 
 int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x);
