@@ -6,6 +6,8 @@
 #ifndef MGCR_DROPIN_SOLVERPARAM_H
 #define MGCR_DROPIN_SOLVERPARAM_H
 
+#include <cstring>
+
 #include "Operator.h"
 
 template <typename num_type>
@@ -37,6 +39,7 @@ public:
 
     mgcr_gcr_param c_param() const {   // the C ABI's view of this record
         mgcr_gcr_param p;
+        std::memset(&p, 0, sizeof p);   // padding too: callers compare these records bytewise
         p.truncation = truncation; p.restart = restart; p.max_iter = max_iter; p.tol = tol;
         p.verbose = verbose ? 1 : 0; p.std_conj = std_conj ? 1 : 0; p.zero_guess = zero_guess ? 1 : 0;
         return p;
