@@ -27,27 +27,48 @@ struct GcrOp : mgcr_op {
 // ---- launch tables: exact history length NH (1..16), U elements per thread (dot) / MINB resident CTAs per SM (update)
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
-template <int NH, int U>
-static void launch_dot_hist(mgcr_ctx* ctx, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
+template <int NK, int KS>
+static void launch_dot_hist(mgcr_ctx* ctx, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int nh,
                             int std_conj, double* out) {
-    k_gcr_dot_hist<NH, U><<<grid, RED_THREADS, 0, ctx->stream>>>(n, Ar, Aps, stride, hl, std_conj, out, ctx->d_partials, ctx->d_ticket);
+    k_gcr_dot_hist<NK, KS><<<grid, RED_THREADS, 0, ctx->stream>>>(n, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket);
 }
 template <int NH>
-static void dot_hist_u(mgcr_ctx* ctx, int u, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
-                       int std_conj, double* out) {
-    if constexpr (NH <= 4) { if (u >= 4) return launch_dot_hist<NH, 4>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); }
-    if constexpr (NH <= 8) { if (u >= 2) return launch_dot_hist<NH, 2>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out); }
-    launch_dot_hist<NH, 1>(ctx, grid, n, Ar, Aps, stride, hl, std_conj, out);
-}
-static void dot_hist(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
-                     int std_conj, double* out) {
-    static const int u_env = env_int("MGCR_DOT_U", 0);   // experiment knob
-    const int u = u_env ? u_env : (nh <= 1 ? 4 : nh <= 3 ? 2 : 1);
-    switch (nh) {
-#define C(NH) case NH: dot_hist_u<NH>(ctx, u, grid, n, Ar, Aps, stride, hl, std_conj, out); break;
-        C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
-#undef C
+static int launch_dot_hist_tma(mgcr_ctx* ctx, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int std_conj,
+                               double* out) {
+    static thread_local bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_gcr_dot_hist_tma<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
     }
+    // tile = 256*ept elements of each of the 1+NH vectors; ring of `stages` tiles in ~150 KB (measured: scripts/kbench_dot5.cu)
+    const int ept = NH <= 3 ? 4 : NH <= 7 ? 2 : 1;
+    const size_t stage_bytes = (size_t)(1 + NH) * RED_THREADS * ept * sizeof(c128);
+    const int stages = (int)std::max<size_t>(2, std::min<size_t>(4, (150 * 1024) / stage_bytes));
+    const int64_t tiles = (n + (int64_t)RED_THREADS * ept - 1) / ((int64_t)RED_THREADS * ept);
+    const int grid = (int)std::min<int64_t>(ctx->num_sms, tiles);
+    k_gcr_dot_hist_tma<NH><<<grid, RED_THREADS, stages * stage_bytes, ctx->stream>>>(n, Ar, Aps, stride, hl, std_conj, ept, stages, out,
+                                                                                    ctx->d_partials, ctx->d_ticket);
+    return MGCR_OK;
+}
+
+// history length -> kernel.  Short histories (and short vectors): register-staged kernel, KS thread groups per CTA with
+// <= NK vectors each; nh >= 3 on long vectors: TMA-staged ring (measured on B200, profiles/r01_kbench_dot.txt).
+static int dot_hist(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
+                    int std_conj, double* out) {
+    static const int use_tma = env_int("MGCR_DOT_TMA", 1);   // experiment knob
+    if (use_tma && nh >= 3 && n >= ((int64_t)1 << 20)) {
+        switch (nh) {
+#define C(NH) case NH: return launch_dot_hist_tma<NH>(ctx, n, Ar, Aps, stride, hl, std_conj, out);
+            C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
+#undef C
+        }
+    }
+#define GO(NK, KS) launch_dot_hist<NK, KS>(ctx, grid, n, Ar, Aps, stride, hl, nh, std_conj, out)
+    if (nh <= 3) GO(3, 1);
+    else if (nh <= 8) GO(4, 2);
+    else GO(4, 4);
+#undef GO
+    return MGCR_OK;
 }
 
 template <int NH, int MINB>
@@ -175,7 +196,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
                 const int cnt = std::min((int)GCR_CHUNK, lim - c0);
                 for (int k = 0; k < GCR_CHUNK; k++) hl.slot[k] = k < cnt ? c0 + k : 0;
                 ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + cnt));
-                dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, scal + S_BNUM + 2 * c0);
+                GTRY(dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, scal + S_BNUM + 2 * c0));
             }
             GCUDA(cudaGetLastError());
         }

@@ -82,11 +82,12 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, cons
     double v[4] = {0., 0., 0., 0.};
     GRID_STRIDE(i, n) {
         c128 rv = ld_stream(r + i), av = ld_stream(Ap + i);
-        c128 t = std_conj ? cmulc(av, rv) : cmulc(rv, av);
+        c128 t = cmulc(rv, av);
         v[0] += t.x; v[1] += t.y;
         v[2] += av.x * av.x + av.y * av.y;
         v[3] += rv.x * rv.x + rv.y * rv.y;
     }
+    if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
     grid_reduce<4>(v, partials, ticket, out4);
 }
 
@@ -111,32 +112,29 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n,
     grid_reduce<1>(v, partials, ticket, scal + S_RR);
 }
 
-// batched <Ar, Aps[slot]> for NH (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
-// U elements per thread and trip keep enough 128-bit loads in flight when NH is small.
+// batched <Ar, Aps[slot]> for nh (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
+// The CTA is split into KS thread groups; group g owns the history vectors g, g+KS, ... (at most NK of them) for the
+// element range of the whole CTA, so a thread carries 2*NK accumulators and U*(1+NK) independent 128-bit loads instead
+// of 2*nh and 1+nh (long histories otherwise end up with few loads in flight; Ar is read KS times, the repeats hit L2).
 struct HistList { int slot[GCR_CHUNK]; };
 
-template <int NH, int U>
-static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
-                                                              int64_t stride, HistList hl, int std_conj, double* out /* 2*NH */,
-                                                              double* partials, unsigned int* ticket) {
-    double v[2 * NH];
-#pragma unroll
-    for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
-    const int64_t T = (int64_t)gridDim.x * blockDim.x;
-    int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    for (; i0 + (U - 1) * T < n; i0 += T * U) {     // full trips: U*(1+NH) independent 128-bit loads in flight
-        c128 a[U], h[U][NH];
+// one thread group's pass: CNT history vectors (compile time: no predicated loads), U elements per trip
+template <int CNT, int U, int NK>
+__device__ __forceinline__ void dot_hist_group(int64_t n, int64_t i0, int64_t T, const c128* __restrict__ Ar, const c128* const (&hp)[NK],
+                                               double (&v)[2 * NK]) {
+    for (; i0 + (U - 1) * T < n; i0 += T * U) {
+        c128 a[U], h[U][CNT];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             a[u] = ld_stream(Ar + i0 + u * T);
 #pragma unroll
-            for (int k = 0; k < NH; k++) h[u][k] = ld_stream(Aps + (int64_t)hl.slot[k] * stride + i0 + u * T);
+            for (int k = 0; k < CNT; k++) h[u][k] = ld_stream(hp[k] + i0 + u * T);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
 #pragma unroll
-            for (int k = 0; k < NH; k++) {
-                c128 t = std_conj ? cmulc(h[u][k], a[u]) : cmulc(a[u], h[u][k]);
+            for (int k = 0; k < CNT; k++) {
+                c128 t = cmulc(a[u], h[u][k]);
                 v[2 * k] += t.x; v[2 * k + 1] += t.y;
             }
         }
@@ -144,11 +142,166 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, 
     for (; i0 < n; i0 += T) {                        // tail
         const c128 a = ld_stream(Ar + i0);
 #pragma unroll
-        for (int k = 0; k < NH; k++) {
-            const c128 h = ld_stream(Aps + (int64_t)hl.slot[k] * stride + i0);
-            c128 t = std_conj ? cmulc(h, a) : cmulc(a, h);
+        for (int k = 0; k < CNT; k++) {
+            c128 t = cmulc(a, ld_stream(hp[k] + i0));
             v[2 * k] += t.x; v[2 * k + 1] += t.y;
         }
+    }
+}
+
+template <int NK, int KS>
+static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
+                                                              int64_t stride, HistList hl, int nh, int std_conj, double* out /* 2*nh */,
+                                                              double* partials, unsigned int* ticket) {
+    constexpr int GT = RED_THREADS / KS;     // threads per group
+    constexpr int GW = GT / 32;              // warps per group
+    const int g = threadIdx.x / GT, tl = threadIdx.x % GT;
+    const int cnt = (nh - g + KS - 1) / KS;  // history vectors of this group: g, g+KS, ...  (warp-uniform)
+    const c128* hp[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) hp[k] = Aps + (int64_t)hl.slot[k < cnt ? g + k * KS : 0] * stride;
+    double v[2 * NK];
+#pragma unroll
+    for (int k = 0; k < 2 * NK; k++) v[k] = 0.;
+    const int64_t T = (int64_t)gridDim.x * GT;
+    const int64_t i0 = blockIdx.x * (int64_t)GT + tl;
+    switch (cnt) {
+        case 1: dot_hist_group<1, 4, NK>(n, i0, T, Ar, hp, v); break;
+        case 2: if constexpr (NK >= 2) dot_hist_group<2, 2, NK>(n, i0, T, Ar, hp, v); break;
+        case 3: if constexpr (NK >= 3) dot_hist_group<3, 2, NK>(n, i0, T, Ar, hp, v); break;
+        case 4: if constexpr (NK >= 4) dot_hist_group<4, 1, NK>(n, i0, T, Ar, hp, v); break;
+        default: break;
+    }
+    // <h, a> = conj(<a, h>) term by term and exactly (the products commute, the difference changes sign): the textbook
+    // convention only flips the sign of the imaginary sums
+    if (std_conj) {
+#pragma unroll
+        for (int k = 0; k < NK; k++) v[2 * k + 1] = -v[2 * k + 1];
+    }
+    // CTA partials: value q = 2*kk + c of history vector kk = g + k*KS lives in the warps of group g
+    __shared__ double sm[RED_THREADS / 32][2 * NK];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 2 * NK; k++) {
+        double s = warp_sum(v[k]);
+        if (lane == 0) sm[warp][k] = s;
+    }
+    __syncthreads();
+    const int nv = 2 * nh;
+    if ((int)threadIdx.x < nv) {
+        const int kk = threadIdx.x >> 1, c = threadIdx.x & 1;
+        const int gg = kk % KS, k = kk / KS;
+        double s = 0.;
+#pragma unroll
+        for (int w = 0; w < GW; w++) s += sm[gg * GW + w][2 * k + c];
+        partials[(size_t)blockIdx.x * MAX_RED_VALUES + threadIdx.x] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last CTA: warp w sums value q = w, w + 8, ... over all CTAs in a fixed order (lanes stride over CTAs, then the tree)
+    for (int q = warp; q < nv; q += RED_THREADS / 32) {
+        double acc = 0.;
+        for (unsigned int bidx = lane; bidx < gridDim.x; bidx += 32) acc += __ldcg(&partials[(size_t)bidx * MAX_RED_VALUES + q]);
+        acc = warp_sum(acc);
+        if (lane == 0) out[q] = acc;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// The same inner products with the operands staged through shared memory by TMA (1-D bulk copies completing on an
+// mbarrier): a ring of S stages, each holding a tile of TE elements of Ar and of the NH history vectors.  One elected
+// thread keeps S tiles in flight per SM whatever the compiler does with the consumer loop, every thread needs only its
+// 2*NH accumulators, and the work is balanced for every NH.  One CTA per SM (the ring takes most of the shared memory).
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+enum { DOT_TMA_MAX_STAGES = 16 };
+
+template <int NH>
+static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
+                                                                     int64_t stride, HistList hl, int std_conj, int ept, int stages,
+                                                                     double* out /* 2*NH */, double* partials, unsigned int* ticket) {
+    extern __shared__ __align__(128) unsigned char dot_smem[];
+    __shared__ __align__(8) uint64_t full[DOT_TMA_MAX_STAGES];
+    const int te = RED_THREADS * ept;                         // elements per tile
+    const size_t stage_elems = (size_t)(1 + NH) * te;
+    c128* ring = (c128*)dot_smem;
+    const int64_t tiles = (n + te - 1) / te;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tile, int s) {                   // thread 0 only
+        const int64_t e0 = tile * te;
+        const uint32_t cnt = (uint32_t)min((int64_t)te, n - e0);
+        c128* dst = ring + (size_t)s * stage_elems;
+        mbar_expect_tx(&full[s], cnt * 16u * (1 + NH));
+        tma_load_1d(dst, Ar + e0, cnt * 16u, &full[s]);
+#pragma unroll
+        for (int k = 0; k < NH; k++) tma_load_1d(dst + (size_t)(1 + k) * te, Aps + (int64_t)hl.slot[k] * stride + e0, cnt * 16u, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < stages; s++) {
+            const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+            if (tile < tiles) issue(tile, s);
+        }
+    double v[2 * NH];
+#pragma unroll
+    for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
+    int s = 0; uint32_t parity = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&full[s], parity);
+        const c128* st = ring + (size_t)s * stage_elems;
+        const int64_t left = n - tile * te;
+        for (int q = 0; q < ept; q++) {
+            const int e = q * RED_THREADS + threadIdx.x;
+            if (e < left) {
+                const c128 a = st[e];
+#pragma unroll
+                for (int k = 0; k < NH; k++) {
+                    c128 t = cmulc(a, st[(size_t)(1 + k) * te + e]);
+                    v[2 * k] += t.x; v[2 * k + 1] += t.y;
+                }
+            }
+        }
+        __syncthreads();                                      // every thread is done with stage s
+        const int64_t next = tile + (int64_t)stages * gridDim.x;
+        if (threadIdx.x == 0 && next < tiles) issue(next, s);
+        if (++s == stages) { s = 0; parity ^= 1; }
+    }
+    if (std_conj) {
+#pragma unroll
+        for (int k = 0; k < NH; k++) v[2 * k + 1] = -v[2 * k + 1];
     }
     grid_reduce<2 * NH>(v, partials, ticket, out);
 }
@@ -215,13 +368,14 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64
             pc = cadd(zv, pc);
             Apc = cadd(av, Apc);
             c128 rv = (r == z) ? zv : ld_stream(r + i);
-            c128 t = std_conj ? cmulc(Apc, rv) : cmulc(rv, Apc);
+            c128 t = cmulc(rv, Apc);
             v[0] += t.x; v[1] += t.y;
             v[2] += Apc.x * Apc.x + Apc.y * Apc.y;
         }
         st_stream(pout + i, pc);
         st_stream(Apout + i, Apc);
     }
+    if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
     if (last) grid_reduce<3>(v, partials, ticket, scal + S_ANUM);   // -> S_ANUM(2), S_ADEN
 }
 
