@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-iter", type=int, default=None, help="cap GCR iterations (profiling runs)")
+    ap.add_argument("--mg", default=None, help='JSON overriding the workload\'s MG parameters, e.g. \'{"coarse": [0,10,4,0.1], "n_eigen": [8,8]}\'')
+    ap.add_argument("--restart", type=int, default=None, help="override the outer GCR restart length")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -230,6 +232,10 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.max_iter:
         wl["max_iter"] = args.max_iter
+    if args.restart:
+        wl["restart"] = args.restart
+    if args.mg and wl.get("mg"):
+        wl["mg"] = dict(wl["mg"], **json.loads(args.mg))
     if args.impl == "reference":
         return run_reference(args, wl, rank)
 
@@ -354,6 +360,7 @@ def main():
     if rank != 0:
         return
     peak, peak_src = peaks()
+    host = {kname: prof.pop(kname) for kname in list(prof) if kname.startswith("host_")}
     total_ms = sum(v["ms"] for v in prof.values())
     dom = max(prof, key=lambda kname: prof[kname]["ms"])
     classes = {kname: {"ms_per_launch": v["ms"] / max(v["calls"], 1), "launches": v["calls"], "share": v["ms"] / total_ms,
@@ -382,6 +389,7 @@ def main():
                      "traffic": traffic, "peak_source": peak_src,
                      "how": "algorithmic bytes of every launch of the class / its summed CUDA-event time (events on the library stream) over one more identical step after the timed ones"},
         "spmv": spmv, "kernels": classes,
+        "host_side": {kname: {"ms": v["ms"], "calls": v["calls"]} for kname, v in host.items()},
     }
     if not args.no_cpu_baseline and world == 1:
         s = reference_cpu_sample(wl)

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <map>
 #include <string>
 #include <vector>
@@ -85,6 +86,14 @@ struct mgcr_ctx {
     double* d_scratch = nullptr;            // small device scalar scratch for the BLAS-1 entry points
     double* h_pinned = nullptr;             // pinned host mirror (256 doubles)
     int64_t launches = 0;
+    // host-side time spent inside the allocator and waiting on the device (diagnostics: reported as the profile classes
+    // "host_alloc" / "host_sync" when profiling is on)
+    double host_alloc_ms = 0, host_sync_ms = 0;
+    int64_t host_alloc_calls = 0, host_sync_calls = 0;
+    // device-memory cache behind dev_alloc / dev_free (context.cu)
+    std::multimap<size_t, void*> mem_free;     // capacity -> idle buffer
+    std::map<void*, size_t> mem_live;          // buffer handed out -> capacity
+    size_t mem_free_bytes = 0;
     // distributed
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
@@ -127,8 +136,18 @@ struct ProfScope {
 
 #define CHECK_LAUNCH() CUDA_TRY(cudaGetLastError())
 
-// stream-ordered device memory (cudaMallocAsync pool with an unlimited release threshold: inner solves of the
-// multigrid cycle allocate and free their Krylov workspaces on every call without touching the driver)
+struct HostTimer {
+    double* acc; int64_t* calls;
+    std::chrono::steady_clock::time_point t0;
+    HostTimer(double* a, int64_t* c) : acc(a), calls(c), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); (*calls)++; }
+};
+
+// Device memory for everything the library owns.  Inner solves of the multigrid cycle take and return their Krylov
+// workspaces on every call (hundreds of times per outer iteration), so buffers are recycled through a per-context
+// cache of exact-size classes: after the first cycle no call reaches the driver.  (The first version used
+// cudaMallocAsync; its pool cost 0.5 us per call in some runs and 74 us in others, profiles/r01_allocator_cost.txt.)
+// All work of a context is enqueued on one stream by one host thread, so reuse in host order is stream-ordered.
 int dev_alloc(mgcr_ctx* ctx, size_t bytes, void** out);
 int dev_free(mgcr_ctx* ctx, void* p);
 template <typename T> static inline int dev_alloc_t(mgcr_ctx* ctx, size_t count, T** out) {

@@ -15,21 +15,57 @@ void mgcr_set_error(const char* fmt, ...) {
 extern "C" const char* mgcr_last_error(void) { return g_err; }
 extern "C" int mgcr_abi_version(void) { return 1; }
 
+static const size_t MEM_CACHE_LIMIT = (size_t)48 << 30;   // idle bytes kept before the cache is trimmed
+
+static void mem_trim(mgcr_ctx* ctx) {
+    if (ctx->mem_free.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->mem_free) cudaFree(kv.second);
+    ctx->mem_free.clear();
+    ctx->mem_free_bytes = 0;
+}
+
 int dev_alloc(mgcr_ctx* ctx, size_t bytes, void** out) {
     *out = nullptr;
-    if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+    HostTimer ht(&ctx->host_alloc_ms, &ctx->host_alloc_calls);
+    bytes = (bytes + 511) & ~(size_t)511;
+    if (bytes == 0) bytes = 512;
+    auto it = ctx->mem_free.lower_bound(bytes);
+    if (it != ctx->mem_free.end() && it->first <= bytes + bytes / 8) {   // close enough in size: recycle
+        *out = it->second;
+        ctx->mem_live[it->second] = it->first;
+        ctx->mem_free_bytes -= it->first;
+        ctx->mem_free.erase(it);
+        return MGCR_OK;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation && !ctx->mem_free.empty()) {      // give idle buffers back and retry
+        cudaGetLastError();
+        mem_trim(ctx);
+        e = cudaMalloc(out, bytes);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
+        *out = nullptr;
         mgcr_set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         return e == cudaErrorMemoryAllocation ? MGCR_ERR_OOM : MGCR_ERR_CUDA;
     }
+    ctx->mem_live[*out] = bytes;
     return MGCR_OK;
 }
 
 int dev_free(mgcr_ctx* ctx, void* p) {
     if (!p) return MGCR_OK;
-    CUDA_TRY(cudaFreeAsync(p, ctx->stream));
+    HostTimer ht(&ctx->host_alloc_ms, &ctx->host_alloc_calls);
+    auto it = ctx->mem_live.find(p);
+    if (it == ctx->mem_live.end()) {
+        mgcr_set_error("dev_free: pointer %p was not allocated by this context", p);
+        return MGCR_ERR_ARG;
+    }
+    ctx->mem_free.emplace(it->second, p);
+    ctx->mem_free_bytes += it->second;
+    ctx->mem_live.erase(it);
+    if (ctx->mem_free_bytes > MEM_CACHE_LIMIT) mem_trim(ctx);
     return MGCR_OK;
 }
 
@@ -65,11 +101,6 @@ extern "C" int mgcr_ctx_create(int device, mgcr_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->d_scratch, sizeof(double) * 256));
     CUDA_TRY(cudaMemset(c->d_scratch, 0, sizeof(double) * 256));
     CUDA_TRY(cudaMallocHost(&c->h_pinned, sizeof(double) * 256));
-    // keep freed blocks cached in the default pool: inner solves allocate/free workspaces on every call
-    cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     *out = c;
     return MGCR_OK;
 }
@@ -80,6 +111,8 @@ extern "C" int mgcr_ctx_destroy(mgcr_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->aux_stream);
     dist_destroy(c);
+    mem_trim(c);
+    for (auto& kv : c->mem_live) cudaFree(kv.first);
     cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned);
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_scal);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
@@ -142,12 +175,15 @@ extern "C" int mgcr_ctx_set_profile(mgcr_ctx* c, int enabled) {
     prof_drain(c);
     c->profile = enabled != 0;
     c->prof.clear();
+    c->host_alloc_ms = c->host_sync_ms = 0; c->host_alloc_calls = c->host_sync_calls = 0;
     return MGCR_OK;
 }
 
 extern "C" int mgcr_ctx_get_profile(mgcr_ctx* c, int cap, const char** names, double* ms, int64_t* calls, double* bytes, int* n_out) {
     ARG_CHECK(c && n_out, "ctx/n_out is NULL");
     prof_drain(c);
+    if (c->host_alloc_calls) { ProfEntry& e = c->prof["host_alloc"]; e.ms = c->host_alloc_ms; e.calls = c->host_alloc_calls; e.bytes = 0; }
+    if (c->host_sync_calls) { ProfEntry& e = c->prof["host_sync"]; e.ms = c->host_sync_ms; e.calls = c->host_sync_calls; e.bytes = 0; }
     int i = 0;
     for (auto& kv : c->prof) {
         if (i < cap) {

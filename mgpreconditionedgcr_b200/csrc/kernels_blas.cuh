@@ -76,10 +76,18 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gamma5(int64_t n, int64_
 enum { GCR_CHUNK = 16 };
 enum { S_ANUM = 0, S_ADEN = 2, S_BB = 3, S_RR = 4, S_BNUM = 5 };   // S_BDEN = S_BNUM + 2*storage
 
-// init: <r,Ap>, <Ap,Ap>, ||rhs||^2 (r = rhs at start) in one pass -> S_ANUM(2), S_ADEN, S_BB
+// Device-side stopping test (GCR.h:288) for solves the host does not watch (short smoother solves inside the multigrid
+// cycle): with guard != NULL every kernel of an iteration first checks ||r||^2 <= tol^2 ||rhs||^2 on the scalars the
+// previous kernels left and returns at once when the solve has converged, so x and r stop changing exactly where the
+// reference's loop would have stopped while the host keeps enqueueing without a read-back.
+__device__ __forceinline__ bool gcr_converged(const double* guard, double tol2) {
+    return guard != nullptr && guard[S_RR] <= tol2 * guard[S_BB];
+}
+
+// init: <r,Ap>, <Ap,Ap>, ||rhs||^2 (r = rhs at start) in one pass -> S_ANUM(2), S_ADEN, S_BB, S_RR (= ||rhs||^2)
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, const c128* __restrict__ r, const c128* __restrict__ Ap,
-                                                          int std_conj, double* partials, unsigned int* ticket, double* out4) {
-    double v[4] = {0., 0., 0., 0.};
+                                                          int std_conj, double* partials, unsigned int* ticket, double* out5) {
+    double v[5] = {0., 0., 0., 0., 0.};
     GRID_STRIDE(i, n) {
         c128 rv = ld_stream(r + i), av = ld_stream(Ap + i);
         c128 t = cmulc(rv, av);
@@ -88,13 +96,15 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, cons
         v[3] += rv.x * rv.x + rv.y * rv.y;
     }
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
-    grid_reduce<4>(v, partials, ticket, out4);
+    v[4] = v[3];
+    grid_reduce<5>(v, partials, ticket, out5);
 }
 
 // x += alpha p ; r -= alpha Ap ; ||r||^2 -> scal[S_RR]      (GCR.h:230-233)
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n, const c128* __restrict__ p, const c128* __restrict__ Ap,
                                                                c128* x, c128* r, double* scal, int bden_slot, double* partials,
-                                                               unsigned int* ticket) {
+                                                               unsigned int* ticket, const double* guard, double tol2) {
+    if (gcr_converged(guard, tol2)) return;
     const double aden = scal[S_ADEN];
     const c128 alpha = cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
     // ||Aps[cur]||^2 never changes while the slot lives: cache it for the beta denominators (GCR.h:258 recomputes it)
@@ -152,7 +162,8 @@ __device__ __forceinline__ void dot_hist_group(int64_t n, int64_t i0, int64_t T,
 template <int NK, int KS>
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                               int64_t stride, HistList hl, int nh, int std_conj, double* out /* 2*nh */,
-                                                              double* partials, unsigned int* ticket) {
+                                                              double* partials, unsigned int* ticket, const double* guard, double tol2) {
+    if (gcr_converged(guard, tol2)) return;
     constexpr int GT = RED_THREADS / KS;     // threads per group
     constexpr int GW = GT / 32;              // warps per group
     const int g = threadIdx.x / GT, tl = threadIdx.x % GT;
@@ -249,7 +260,9 @@ enum { DOT_TMA_MAX_STAGES = 16 };
 template <int NH>
 static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                                      int64_t stride, HistList hl, int std_conj, int ept, int stages,
-                                                                     double* out /* 2*NH */, double* partials, unsigned int* ticket) {
+                                                                     double* out /* 2*NH */, double* partials, unsigned int* ticket,
+                                                                     const double* guard, double tol2) {
+    if (gcr_converged(guard, tol2)) return;
     extern __shared__ __align__(128) unsigned char dot_smem[];
     __shared__ __align__(8) uint64_t full[DOT_TMA_MAX_STAGES];
     const int te = RED_THREADS * ept;                         // elements per tile
@@ -319,7 +332,8 @@ template <int NH, int MINB>
 static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps,
                                                                     c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
                                                                     c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, double* scal,
-                                                                    double* partials, unsigned int* ticket) {
+                                                                    double* partials, unsigned int* ticket, const double* guard, double tol2) {
+    if (gcr_converged(guard, tol2)) return;
     constexpr int NHS = NH > 0 ? NH : 1;
     __shared__ c128 beta[NHS];
     if ((int)threadIdx.x < NH) {

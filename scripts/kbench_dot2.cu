@@ -21,7 +21,7 @@ static float time_dot(bool writer, c128* Ar, c128* Aps, c128* src, double* part,
     for (int w = 0; w < reps + 2; w++) {
         if (writer) k_axpy<<<148 * 8, RED_THREADS>>>(N, cmake(1.0001, 0.), src, src, Ar);
         cudaEventRecord(e0);
-        k_gcr_dot_hist<NK, KS><<<148 * gps, RED_THREADS>>>(N, Ar, Aps, N, hl, NH, 0, out, part, ticket);
+        k_gcr_dot_hist<NK, KS><<<148 * gps, RED_THREADS>>>(N, Ar, Aps, N, hl, NH, 0, out, part, ticket, nullptr, 0.);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (w >= 2) total += ms;

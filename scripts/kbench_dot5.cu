@@ -27,7 +27,7 @@ static void run(c128* Ar, c128* Aps, c128* src, double* part, unsigned* ticket, 
         for (int w = 0; w < reps + 2; w++) {
             k_axpy<<<148 * 8, RED_THREADS>>>(N, cmake(1.0001, 0.), src, src, Ar);
             cudaEventRecord(e0);
-            k_gcr_dot_hist_tma<NH><<<148, RED_THREADS, smem>>>(N, Ar, Aps, N, hl, 0, ept, stages, out, part, ticket);
+            k_gcr_dot_hist_tma<NH><<<148, RED_THREADS, smem>>>(N, Ar, Aps, N, hl, 0, ept, stages, out, part, ticket, nullptr, 0.);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             if (w >= 2) total += ms;
