@@ -228,7 +228,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:
-        args.workload = "gcr2d_4096" if world == 1 else "gcr3d_512"
+        args.workload = "gcr2d_4096" if world == 1 else "mg3d_512"
     wl = dict(WORKLOADS[args.workload])
     if args.max_iter:
         wl["max_iter"] = args.max_iter
@@ -253,10 +253,18 @@ def main():
         ids = [host.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.init_dist(rank, world, ids[0])
+        if wl.get("mg"):
+            # no aggregate may straddle two GPUs: slabs are multiples of the product of the aggregate sizes (as far as every
+            # rank still gets a slab); deeper levels are gathered
+            align = 1
+            for sub in wl["mg"]["subs"]:
+                if wl["dims"][0] // (align * sub) >= world:
+                    align *= sub
+            ctx.set_slab_align(align)
     if wl.get("mg") and args.operator == "csr" and args.workload == "mg3d_512":
         args.operator = "stencil"   # the stored 512^3 operator (22.5 GB) plus the hierarchy is built matrix-free by default
     if world > 1 and args.operator == "csr":
-        args.operator = "stencil"   # TODO(dist csr)
+        args.operator = "stencil"   # the distributed path is matrix-free (a distributed CSR upload is not provided yet)
     dims = wl["dims"]
     nd = len(dims)
     V = int(np.prod(dims))
@@ -274,7 +282,7 @@ def main():
     if world == 1:
         rhs = ctx.init_rand(0, V)
     else:
-        b, e = host.slab_range(dims[0], 1, rank, world)
+        b, e = host.slab_range(dims[0], ctx.slab_align, rank, world)
         plane = V // dims[0]
         rhs = ctx.init_rand(0, n_local, skip=b * plane)
     x = ctx.field(n_local)

@@ -68,6 +68,10 @@ int mgcr_ctx_get_profile(mgcr_ctx* ctx, int cap, const char** names, double* ms,
 int mgcr_nccl_unique_id(void* h_id128);
 int mgcr_ctx_init_dist(mgcr_ctx* ctx, int rank, int nranks, const void* h_id128);
 int mgcr_ctx_rank(mgcr_ctx* ctx, int* rank, int* nranks);
+/* slab boundaries of every slab-partitioned object created afterwards are multiples of `align` planes of the slowest
+ * lattice index (set it to the product of the aggregate sizes of the multigrid levels that stay distributed, so that no
+ * aggregate straddles two GPUs; default 1) */
+int mgcr_ctx_set_slab_align(mgcr_ctx* ctx, int64_t align);
 /* sum-all-reduce of n doubles in device memory (the "scalar dot-product allreduce") */
 int mgcr_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
 /* contiguous slab of [0, n_slowest) owned by `rank`, aligned to `align` (aggregate size of the slowest dim) */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "mgcr_nccl_unique_id": [_vp],
     "mgcr_ctx_init_dist": [_vp, _int, _int, _vp],
     "mgcr_ctx_rank": [_vp, _pint, _pint],
+    "mgcr_ctx_set_slab_align": [_vp, _i64],
     "mgcr_allreduce_sum": [_vp, _vp, _int],
     "mgcr_slab_range": [_i64, _i64, _int, _int, _pi64, _pi64],
     "mgcr_vec_alloc": [_vp, _i64, _pvp],

@@ -96,6 +96,7 @@ struct mgcr_ctx {
     size_t mem_free_bytes = 0;
     // distributed
     int rank = 0, nranks = 1;
+    int64_t slab_align = 1;                 // slab boundaries along the slowest lattice index are multiples of this
     void* nccl_comm = nullptr;
     // profiling
     bool profile = false;
@@ -164,6 +165,7 @@ int dist_group_end(mgcr_ctx* ctx);
 int dist_send(mgcr_ctx* ctx, const void* d_send, size_t bytes, int peer, cudaStream_t stream);
 int dist_recv(mgcr_ctx* ctx, void* d_recv, size_t bytes, int peer, cudaStream_t stream);
 int dist_allgather_host_i64(mgcr_ctx* ctx, int64_t mine, std::vector<int64_t>& all);
+int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
 
 // ----------------------------------------------------------------------------------------------------------
 // deterministic reduction: warp shuffle -> shared memory -> one partial per block -> the LAST block to finish

@@ -89,6 +89,12 @@ extern "C" int mgcr_ctx_init_dist(mgcr_ctx* ctx, int rank, int nranks, const voi
     return MGCR_OK;
 }
 
+extern "C" int mgcr_ctx_set_slab_align(mgcr_ctx* ctx, int64_t align) {
+    ARG_CHECK(ctx && align >= 1, "mgcr_ctx_set_slab_align: bad argument");
+    ctx->slab_align = align;
+    return MGCR_OK;
+}
+
 void dist_destroy(mgcr_ctx* ctx) {
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
@@ -130,6 +136,17 @@ int dist_send(mgcr_ctx* ctx, const void* d_send, size_t bytes, int peer, cudaStr
 }
 int dist_recv(mgcr_ctx* ctx, void* d_recv, size_t bytes, int peer, cudaStream_t stream) {
     NCCL_TRY(g_nccl.Recv(d_recv, bytes, ncclChar_, peer, (ncclComm_t)ctx->nccl_comm, stream));
+    return MGCR_OK;
+}
+
+// equal-size all-gather of raw bytes (coarse-level gather: SURVEY.md 8e item 3)
+int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank) {
+    if (ctx->nranks == 1) {
+        if (d_send != d_recv) CUDA_TRY(cudaMemcpyAsync(d_recv, d_send, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+        return MGCR_OK;
+    }
+    ctx->launches++;
+    NCCL_TRY(g_nccl.AllGather(d_send, d_recv, bytes_per_rank, ncclChar_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return MGCR_OK;
 }
 

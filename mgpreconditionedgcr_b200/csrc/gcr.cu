@@ -8,9 +8,9 @@
 #include "kernels_blas.cuh"
 #include "ops.cuh"
 
-int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out);
-int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out);
-int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a);
+int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist);
+int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist);
+int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist);
 
 int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const c128* rhs, c128* x, double* hist, int hist_cap,
                     int* iters_out, int storage, int restart, int* handled);
@@ -125,6 +125,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     if (restart < 1) restart = 1;
     const bool aliased = (rhs == x);
     const int std_conj = prm->std_conj;
+    const bool dist = A->distributed;   // vectors are row slabs: partial inner products are all-reduced (NCCL)
     if (!right) {   // small operators: the whole solve as one persistent cooperative kernel (gcr_small.cu)
         int handled = 0;
         MGCR_TRY(gcr_solve_small(ctx, A, prm, rhs, x, hist, hist_cap, iters_out, storage, restart, &handled));
@@ -164,7 +165,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     GTRY(A->apply(ps, Aps));
     KLAUNCH(ctx, "gcr_init", 32. * n, (k_gcr_init<<<grid, RED_THREADS, 0, ctx->stream>>>(n, r, Aps, std_conj, ctx->d_partials, ctx->d_ticket, scal)));
     GCUDA(cudaGetLastError());
-    GTRY(dist_allreduce_sum(ctx, scal, 5));
+    if (dist) GTRY(dist_allreduce_sum(ctx, scal, 5));
     // Short solves nobody watches (the smoothers of the multigrid cycle): no read-back at all, the kernels carry the
     // stopping test themselves (gcr_converged) and the host enqueues max_iter iterations back to back.
     const bool blind = !hist && !iters_out && !prm->verbose && !aliased && !right && prm->max_iter <= 4;
@@ -193,7 +194,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
             KLAUNCH(ctx, "vec_norm2", 16. * n, (k_norm2<<<grid, RED_THREADS, 0, ctx->stream>>>(n, x, ctx->d_partials, ctx->d_ticket, scal + S_BB)));
             GCUDA(cudaGetLastError());
-            GTRY(dist_allreduce_sum(ctx, scal + S_BB, 1));
+            if (dist) GTRY(dist_allreduce_sum(ctx, scal + S_BB, 1));
         }
         const bool final_iter = (g >= prm->max_iter);   // nothing after the x update is observable on the last pass
         const c128* zz = r;
@@ -211,7 +212,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
             }
             GCUDA(cudaGetLastError());
         }
-        GTRY(dist_allreduce_sum(ctx, scal + S_RR, 1 + 2 * lim));
+        if (dist) GTRY(dist_allreduce_sum(ctx, scal + S_RR, 1 + 2 * lim));
         if (!blind) {
             GCUDA(cudaMemcpyAsync(slot.h, scal + S_BB, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             GCUDA(cudaEventRecord(slot.ev, ctx->stream));
@@ -230,7 +231,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
                 update_p(ctx, cnt, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, guard, tol2);
             }
             GCUDA(cudaGetLastError());
-            GTRY(dist_allreduce_sum(ctx, scal + S_ANUM, 3));
+            if (dist) GTRY(dist_allreduce_sum(ctx, scal + S_ANUM, 3));
             iter = next_iter;
             cur = new_slot;
         }
@@ -298,7 +299,7 @@ int GcrOp::apply(const c128* x, c128* y) {
         if (!d_rand2) {
             MGCR_TRY(dev_alloc_t(ctx, (size_t)n_local, &d_rand2));
             int64_t skip = 0;
-            if (ctx->nranks > 1) {   // this rank's slice of the global init_rand(2) stream
+            if (A->distributed) {   // this rank's slice of the global init_rand(2) stream
                 std::vector<int64_t> all;
                 MGCR_TRY(dist_allgather_host_i64(ctx, n_local, all));
                 for (int rnk = 0; rnk < ctx->rank; rnk++) skip += all[rnk];
@@ -317,7 +318,7 @@ extern "C" int mgcr_gcr_op_create(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_para
     if (left) { mgcr_set_error("mgcr_gcr_op_create: left preconditioning is not provided"); return MGCR_ERR_UNSUPPORTED; }
     GcrOp* op = new GcrOp();
     op->kind = OP_GCR; op->ctx = ctx; op->A = A; op->prm = *prm; op->right = right;
-    op->n_local = A->n_local; op->n_global = A->n_global;
+    op->n_local = A->n_local; op->n_global = A->n_global; op->distributed = A->distributed;
     *out = op;
     return MGCR_OK;
 }
@@ -326,7 +327,7 @@ extern "C" int mgcr_gcr_op_retarget(mgcr_op* gcr, mgcr_op* A) {
     ARG_CHECK(gcr && A && gcr->kind == OP_GCR, "mgcr_gcr_op_retarget: not a GCR operator");
     GcrOp* op = static_cast<GcrOp*>(gcr);
     if (op->n_local != A->n_local) { dev_free(op->ctx, op->d_rand2); op->d_rand2 = nullptr; }
-    op->A = A; op->n_local = A->n_local; op->n_global = A->n_global;
+    op->A = A; op->n_local = A->n_local; op->n_global = A->n_global; op->distributed = A->distributed;
     return MGCR_OK;
 }
 
@@ -356,7 +357,8 @@ int arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* ep, int n_vec, c128
     const int64_t n = A->n_local;
     c128* b = vecs;
     int64_t skip = 0;
-    if (ctx->nranks > 1) {
+    const bool dist = A->distributed;
+    if (dist) {
         std::vector<int64_t> all;
         MGCR_TRY(dist_allgather_host_i64(ctx, n, all));
         for (int rnk = 0; rnk < ctx->rank; rnk++) skip += all[rnk];
@@ -366,7 +368,7 @@ int arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* ep, int n_vec, c128
     p.verbose = 0;
     for (int i = 0; i < 10; i++) {                                        // MG.h:100-104
         MGCR_TRY(gcr_solve(ctx, A, &p, nullptr, b, b, nullptr, 0, nullptr));
-        MGCR_TRY(vec_normalise(ctx, n, b));
+        MGCR_TRY(vec_normalise(ctx, n, b, dist));
     }
     const int grid = stream_grid(ctx, n, 8);
     for (int c = 1; c < n_vec; c++) {                                     // MG.h:110-121
@@ -375,13 +377,13 @@ int arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* ep, int n_vec, c128
         MGCR_TRY(gcr_solve(ctx, A, &p, nullptr, vecs + (int64_t)(c - 1) * n, tmp, nullptr, 0, nullptr));
         for (int j = 0; j < c; j++) {
             const c128* ej = vecs + (int64_t)j * n;
-            MGCR_TRY(vec_dot_dev(ctx, n, ej, tmp, ctx->d_scratch + 16));
+            MGCR_TRY(vec_dot_dev(ctx, n, ej, tmp, ctx->d_scratch + 16, dist));
             if (n) {
                 KLAUNCH(ctx, "vec_axpy", 48. * n, (k_axpy_devscal<<<grid, RED_THREADS, 0, ctx->stream>>>(n, ctx->d_scratch + 16, -1., ej, tmp, tmp)));
                 CHECK_LAUNCH();
             }
         }
-        MGCR_TRY(vec_normalise(ctx, n, tmp));
+        MGCR_TRY(vec_normalise(ctx, n, tmp, dist));
     }
     return MGCR_OK;
 }

@@ -231,7 +231,7 @@ int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const 
                     int* iters_out, int storage, int restart, int* handled) {
     *handled = 0;
     const int64_t n = A->n_local;
-    if (n == 0 || n > small_limit() || storage > SG_MAXH || prm->verbose || rhs == x || ctx->nranks > 1) return MGCR_OK;
+    if (n == 0 || n > small_limit() || storage > SG_MAXH || prm->verbose || rhs == x || A->distributed) return MGCR_OK;
     int st = MGCR_OK;
     c128* work = nullptr;
     double* scal = nullptr;

@@ -93,6 +93,10 @@ static __global__ void __launch_bounds__(128) k_block_mgs(LevelGeom g, c128* P) 
 // ----------------------------------------------------------------------------------------------------------
 struct RowSlots { int K; int slot[9]; int64_t col[9]; };
 
+// On a slab-partitioned level the neighbours across the slab boundary are ghost aggregates (columns nb + ..., lower
+// neighbour's plane first); at the global boundary of the partitioned dimension there is no neighbour (the reference's
+// periodic wrap-around block, MG.h:229-231, would couple the first and the last GPU; it is structurally zero for the
+// Dirichlet operators the distributed configurations use).
 __host__ __device__ inline void row_slots(const LevelGeom& g, int64_t B, RowSlots* rs) {
     int64_t bi[4], rem = B;
     for (int c = 3; c >= 0; c--) { bi[c] = rem % g.bd[c]; rem /= g.bd[c]; }
@@ -101,6 +105,14 @@ __host__ __device__ inline void row_slots(const LevelGeom& g, int64_t B, RowSlot
     for (int d = 0; d < 4; d++) {
         int64_t stride = 1;
         for (int c = 3; c > d; c--) stride *= g.bd[c];
+        if (g.dist && d == g.pd) {
+            const int64_t in_plane = B - bi[d] * stride;   // dims before pd have extent 1
+            if (bi[d] > 0) { rs->slot[K] = 2 * d + 1; rs->col[K] = B - stride; K++; }
+            else if (g.has_lo) { rs->slot[K] = 2 * d + 1; rs->col[K] = g.nb + in_plane; K++; }
+            if (bi[d] + 1 < g.bd[d]) { rs->slot[K] = 2 * d + 2; rs->col[K] = B + stride; K++; }
+            else if (g.has_hi) { rs->slot[K] = 2 * d + 2; rs->col[K] = g.nb + (g.has_lo ? g.plane_blocks : 0) + in_plane; K++; }
+            continue;
+        }
         if (g.bd[d] >= 2) {
             int64_t m = (bi[d] - 1 + g.bd[d]) % g.bd[d];
             rs->slot[K] = 2 * d + 1; rs->col[K] = B + (m - bi[d]) * stride; K++;
@@ -119,23 +131,40 @@ __host__ __device__ inline void row_slots(const LevelGeom& g, int64_t B, RowSlot
     rs->K = K;
 }
 
+// aggregate (as a ghost column id) that owns ghost site gs of a slab-partitioned level
+__device__ __forceinline__ int64_t ghost_site_block(const LevelGeom& g, int64_t gs) {
+    const int64_t lo_sites = g.has_lo ? g.plane_sites : 0;
+    const bool hi = gs >= lo_sites;
+    int64_t p = hi ? gs - lo_sites : gs, idx = 0, mul = 1;
+    for (int c = 3; c > g.pd; c--) {
+        idx += ((p % g.sd[c]) / g.sub[c]) * mul;
+        mul *= g.bd[c];
+        p /= g.sd[c];
+    }
+    return g.nb + (hi && g.has_lo ? g.plane_blocks : 0) + idx;
+}
+
 template <class Rows>
-__global__ void __launch_bounds__(256) k_galerkin(Rows M, LevelGeom g, int K, const int64_t* __restrict__ block_map,
-                                                  const int32_t* __restrict__ site_block, const int32_t* __restrict__ site_off,
-                                                  const c128* __restrict__ P, int32_t* __restrict__ bcol_out, int8_t* __restrict__ bslot_out,
-                                                  c128* __restrict__ bval_out) {
+__global__ void __launch_bounds__(256) k_galerkin(Rows M, LevelGeom g, int KMAX, const int32_t* __restrict__ brow,
+                                                  const int64_t* __restrict__ block_map, const int32_t* __restrict__ site_block,
+                                                  const int32_t* __restrict__ site_off, const c128* __restrict__ P,
+                                                  const c128* __restrict__ Pg, int32_t* __restrict__ bcol_out,
+                                                  int8_t* __restrict__ bslot_out, c128* __restrict__ bval_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* G = (c128*)smem_raw;                       // [K][ne*ne] row-major accumulators
-    c128* T = G + (int64_t)K * g.ne * g.ne;          // [K][ne]
+    c128* T = G + (int64_t)KMAX * g.ne * g.ne;       // [K][ne]
     __shared__ RowSlots rs;
     const int64_t B = blockIdx.x;
     const int ne = g.ne;
+    const int64_t nsite = g.nb * g.bs;
+    const int64_t out0 = brow[B];
     if (threadIdx.x == 0) {
         row_slots(g, B, &rs);
-        for (int a = 0; a < rs.K; a++) { bcol_out[B * K + a] = (int32_t)rs.col[a]; bslot_out[B * K + a] = (int8_t)rs.slot[a]; }
+        for (int a = 0; a < rs.K; a++) { bcol_out[out0 + a] = (int32_t)rs.col[a]; bslot_out[out0 + a] = (int8_t)rs.slot[a]; }
     }
-    for (int t = threadIdx.x; t < K * ne * ne; t += blockDim.x) G[t] = cmake(0., 0.);
+    for (int t = threadIdx.x; t < KMAX * ne * ne; t += blockDim.x) G[t] = cmake(0., 0.);
     __syncthreads();
+    const int K = rs.K;
     for (int64_t q = 0; q < g.bl; q++) {
         const int64_t i = block_map[B * g.bs + q / g.dof] * g.dof + q % g.dof;
         // T[a][c] = sum over the entries (j, v) of row i whose column lies in the block of position a of v * P[j][c]
@@ -145,13 +174,18 @@ __global__ void __launch_bounds__(256) k_galerkin(Rows M, LevelGeom g, int K, co
             for (int a = 0; a < 9; a++) tacc[a] = cmake(0., 0.);
             M.for_each(i, [&](int64_t j, c128 v) {
                 const int64_t js = j / g.dof;
-                const int64_t b = site_block[js];
+                int64_t b; c128 pv;
+                if (js < nsite) {
+                    b = site_block[js];
+                    pv = P[(b * ne + c) * g.bl + (int64_t)site_off[js] * g.dof + (j - js * g.dof)];
+                } else {                                   // ghost site: its prolongator row came from the neighbour rank
+                    b = ghost_site_block(g, js - nsite);
+                    pv = Pg[(j - nsite * g.dof) * ne + c];
+                }
                 int pos = -1;
 #pragma unroll
                 for (int a = 0; a < 9; a++) if (pos < 0 && a < K && rs.col[a] == b) pos = a;
                 if (pos < 0) return;   // not a face neighbour: the reference assembles 9 blocks per row only
-                const int64_t off = (int64_t)site_off[js] * g.dof + (j - js * g.dof);
-                const c128 pv = P[(b * ne + c) * g.bl + off];
 #pragma unroll
                 for (int a = 0; a < 9; a++) if (a == pos) tacc[a] = cadd(tacc[a], cmul(v, pv));
             });
@@ -172,17 +206,17 @@ __global__ void __launch_bounds__(256) k_galerkin(Rows M, LevelGeom g, int K, co
     for (int t = threadIdx.x; t < K * ne * ne; t += blockDim.x) {
         const int a = t / (ne * ne), rc = t - a * ne * ne;
         const int r = rc / ne, c = rc - r * ne;
-        bval_out[((int64_t)(B * K + a) * ne + c) * ne + r] = G[t];
+        bval_out[((int64_t)(out0 + a) * ne + c) * ne + r] = G[t];
     }
 }
 
 // replicate src/MG.h:263: the (B, B+e_d) block [slot 2d+2, column block b = B+e_d] takes the value of the block the
 // reference computed with prolongator[nb_idx], i.e. the "+d" triplet of the same column block: (b+e_d, b) [slot 2d+1]
-static __global__ void k_neg_bug(LevelGeom g, int K, const int8_t* __restrict__ bslot, c128* bval) {
+static __global__ void k_neg_bug(LevelGeom g, const int32_t* __restrict__ brow, const int8_t* __restrict__ bslot, c128* bval) {
     const int64_t B = blockIdx.x;
     const int64_t bsz = (int64_t)g.ne * g.ne;
-    for (int a = 0; a < K; a++) {
-        int s = bslot[B * K + a];
+    for (int l = brow[B]; l < brow[B + 1]; l++) {
+        int s = bslot[l];
         if (s == 0 || (s & 1)) continue;
         int d = (s - 2) / 2;
         int64_t bi[4], rem = B;
@@ -190,12 +224,26 @@ static __global__ void k_neg_bug(LevelGeom g, int K, const int8_t* __restrict__ 
         int64_t stride = 1;
         for (int c = 3; c > d; c--) stride *= g.bd[c];
         int64_t src_row = B + (((bi[d] + 2) % g.bd[d]) - bi[d]) * stride;   // b + e_d = B + 2 e_d
-        int sa = -1;
-        for (int q = 0; q < K; q++) if (bslot[src_row * K + q] == s - 1) sa = q;
-        if (sa < 0) continue;
-        const c128* src = bval + (src_row * K + sa) * bsz;
-        c128* dst = bval + (B * K + a) * bsz;
+        int sl = -1;
+        for (int q = brow[src_row]; q < brow[src_row + 1]; q++) if (bslot[q] == s - 1) sl = q;
+        if (sl < 0) continue;
+        const c128* src = bval + (int64_t)sl * bsz;
+        c128* dst = bval + (int64_t)l * bsz;
         for (int64_t t = threadIdx.x; t < bsz; t += blockDim.x) dst[t] = src[t];
+    }
+}
+
+// prolongator rows of one plane of sites, packed [site in plane][dof][ne] for the neighbour rank's Galerkin product
+static __global__ void __launch_bounds__(RED_THREADS) k_pack_P_plane(LevelGeom g, int64_t first_site, const int32_t* __restrict__ site_block,
+                                                                     const int32_t* __restrict__ site_off, const c128* __restrict__ P,
+                                                                     c128* __restrict__ buf) {
+    const int64_t total = g.plane_sites * g.dof * g.ne;
+    GRID_STRIDE(t, total) {
+        const int c = (int)(t % g.ne);
+        const int64_t sd = t / g.ne;
+        const int d = (int)(sd % g.dof);
+        const int64_t site = first_site + sd / g.dof;
+        buf[t] = P[((int64_t)site_block[site] * g.ne + c) * g.bl + (int64_t)site_off[site] * g.dof + d];
     }
 }
 
@@ -285,9 +333,32 @@ static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x) {
     MGCR_TRY(L.A->apply(x, L.d_t));
     MGCR_TRY(vec_axpy(ctx, n, cmake(-1., 0.), L.d_t, b, L.d_r));          // r = b - A x
     MGCR_TRY(mg_restrict(ctx, L, L.d_r, L.d_rc));
-    CUDA_TRY(cudaMemsetAsync(L.d_xc, 0, sizeof(c128) * nc, ctx->stream));
-    MGCR_TRY(gcr_solve(ctx, L.Ac, &mg->coarse, L.deeper, L.d_rc, L.d_xc, nullptr, 0, nullptr));
-    MGCR_TRY(mg_prolong(ctx, L, L.d_xc, L.d_t));
+    const c128* xc = L.d_xc;
+    if (!L.gather) {
+        CUDA_TRY(cudaMemsetAsync(L.d_xc, 0, sizeof(c128) * nc, ctx->stream));
+        MGCR_TRY(gcr_solve(ctx, L.Ac, &mg->coarse, L.deeper, L.d_rc, L.d_xc, nullptr, 0, nullptr));
+    } else {
+        // coarse-level gather: every rank assembles the whole coarse right-hand side, solves the
+        // replicated coarse system (identical arithmetic on every GPU, no further communication) and keeps its slice
+        int64_t maxc = 0;
+        bool equal = true;
+        for (int64_t c : L.nc_counts) { maxc = std::max(maxc, c); equal = equal && c == L.nc_counts[0]; }
+        if (equal) {
+            MGCR_TRY(dist_allgather(ctx, L.d_rc, L.d_rc_full, sizeof(c128) * (size_t)maxc));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(L.d_pad, L.d_rc, sizeof(c128) * nc, cudaMemcpyDeviceToDevice, ctx->stream));
+            MGCR_TRY(dist_allgather(ctx, L.d_pad, L.d_pad + maxc, sizeof(c128) * (size_t)maxc));
+            int64_t off = 0;
+            for (size_t r = 0; r < L.nc_counts.size(); r++) {
+                CUDA_TRY(cudaMemcpyAsync(L.d_rc_full + off, L.d_pad + maxc * (int64_t)(r + 1), sizeof(c128) * L.nc_counts[r], cudaMemcpyDeviceToDevice, ctx->stream));
+                off += L.nc_counts[r];
+            }
+        }
+        CUDA_TRY(cudaMemsetAsync(L.d_xc_full, 0, sizeof(c128) * L.nc_global, ctx->stream));
+        MGCR_TRY(gcr_solve(ctx, L.Ac_full, &mg->coarse, L.deeper, L.d_rc_full, L.d_xc_full, nullptr, 0, nullptr));
+        xc = L.d_xc_full + L.nc_offset;
+    }
+    MGCR_TRY(mg_prolong(ctx, L, xc, L.d_t));
     MGCR_TRY(vec_axpy(ctx, n, cmake(1., 0.), L.d_t, x, x));               // x += P xc
     MGCR_TRY(L.A->apply(x, L.d_t));
     MGCR_TRY(vec_axpy(ctx, n, cmake(-1., 0.), L.d_t, b, L.d_r));
@@ -304,17 +375,97 @@ static int galerkin_launch(mgcr_ctx* ctx, MgLevel& L, const Rows& rows, int32_t*
     size_t smem = sizeof(c128) * ((size_t)L.K * g.ne * g.ne + (size_t)L.K * g.ne);
     ARG_CHECK(smem <= 200 * 1024, "MG setup: %d near-null vectors per aggregate need %zu bytes of shared memory for the coarse blocks", g.ne, smem);
     CUDA_TRY(cudaFuncSetAttribute(k_galerkin<Rows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KLAUNCH(ctx, "mg_galerkin", 0., (k_galerkin<Rows><<<(unsigned)g.nb, 256, smem, ctx->stream>>>(rows, g, L.K, L.d_block_map, L.d_site_block, L.d_site_off,
-                                                                                                L.d_P, bcol, L.d_bslot, bval)));
+    KLAUNCH(ctx, "mg_galerkin", 0., (k_galerkin<Rows><<<(unsigned)g.nb, 256, smem, ctx->stream>>>(rows, g, L.K, L.Ac->d_brow, L.d_block_map, L.d_site_block,
+                                                                                                L.d_site_off, L.d_P, L.d_Pg, bcol, L.d_bslot, bval)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
 
 static int galerkin(mgcr_ctx* ctx, MgLevel& L, int32_t* bcol, c128* bval) {
     int st = MGCR_OK;
-    if (with_rows(L.A, [&](auto rows) { return galerkin_launch(ctx, L, rows, bcol, bval); }, &st)) return st;
+    if (with_rows(L.A, [&](auto rows) { return galerkin_launch(ctx, L, rows, bcol, bval); }, &st, true)) return st;
     mgcr_set_error("MG setup: the operator of this level has no accessible matrix entries (kind %d)", (int)L.A->kind);
     return MGCR_ERR_UNSUPPORTED;
+}
+
+static int64_t gather_threshold() {
+    static const int64_t v = getenv("MGCR_GATHER_DOFS") ? atoll(getenv("MGCR_GATHER_DOFS")) : (int64_t)1 << 18;
+    return v;
+}
+
+// Replicated copy of a slab-partitioned coarse operator: every rank contributes its block rows (ghost columns turned
+// into global block columns), all ranks assemble the same block-CSR.  One-off, staged through the host.
+static int gather_coarse_operator(mgcr_ctx* ctx, MgLevel& L, int64_t nb_offset, int64_t nb_global, BlockCsrOp** out) {
+    const LevelGeom& g = L.g;
+    BlockCsrOp* loc = L.Ac;
+    const int ne = g.ne;
+    const size_t bsz = (size_t)ne * ne;
+    std::vector<int64_t> nbs, nnzs;
+    MGCR_TRY(dist_allgather_host_i64(ctx, g.nb, nbs));
+    MGCR_TRY(dist_allgather_host_i64(ctx, loc->nnzb, nnzs));
+    int64_t max_nb = 0, max_nnz = 0, tot_nnz = 0;
+    for (size_t r = 0; r < nbs.size(); r++) { max_nb = std::max(max_nb, nbs[r]); max_nnz = std::max(max_nnz, nnzs[r]); tot_nnz += nnzs[r]; }
+    ARG_CHECK(tot_nnz < (int64_t)INT32_MAX, "MG setup: gathered coarse operator too large");
+    // global block columns on the host
+    std::vector<int32_t> hrow((size_t)g.nb + 1), hcol((size_t)loc->nnzb);
+    CUDA_TRY(cudaMemcpyAsync(hrow.data(), loc->d_brow, sizeof(int32_t) * hrow.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(hcol.data(), loc->d_bcol, sizeof(int32_t) * hcol.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const int64_t lo_blocks = g.has_lo ? g.plane_blocks : 0;
+    for (auto& c : hcol) {
+        int64_t cc = c;
+        if (cc < g.nb) cc += nb_offset;
+        else if (cc - g.nb < lo_blocks) cc = nb_offset - g.plane_blocks + (cc - g.nb);
+        else cc = nb_offset + g.nb + (cc - g.nb - lo_blocks);
+        c = (int32_t)cc;
+    }
+    // padded exchange: [row counts | cols | vals]
+    int32_t *d_cnt = nullptr, *d_cnt_all = nullptr, *d_col = nullptr, *d_col_all = nullptr;
+    c128 *d_val_all = nullptr;
+    const int R = ctx->nranks;
+    std::vector<int32_t> cnt((size_t)max_nb, 0);
+    for (int64_t b = 0; b < g.nb; b++) cnt[b] = hrow[b + 1] - hrow[b];
+    std::vector<int32_t> colpad((size_t)max_nnz, 0);
+    std::copy(hcol.begin(), hcol.end(), colpad.begin());
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)max_nb, &d_cnt));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)max_nb * R, &d_cnt_all));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)max_nnz, &d_col));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)max_nnz * R, &d_col_all));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)max_nnz * bsz * R, &d_val_all));
+    CUDA_TRY(cudaMemcpyAsync(d_cnt, cnt.data(), sizeof(int32_t) * max_nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_col, colpad.data(), sizeof(int32_t) * max_nnz, cudaMemcpyHostToDevice, ctx->stream));
+    // values: send straight from the local operator (padded region of the receive slots is never read)
+    c128* d_val_send = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)max_nnz * bsz, &d_val_send));
+    CUDA_TRY(cudaMemcpyAsync(d_val_send, loc->d_bval, sizeof(c128) * (size_t)loc->nnzb * bsz, cudaMemcpyDeviceToDevice, ctx->stream));
+    MGCR_TRY(dist_allgather(ctx, d_cnt, d_cnt_all, sizeof(int32_t) * (size_t)max_nb));
+    MGCR_TRY(dist_allgather(ctx, d_col, d_col_all, sizeof(int32_t) * (size_t)max_nnz));
+    MGCR_TRY(dist_allgather(ctx, d_val_send, d_val_all, sizeof(c128) * (size_t)max_nnz * bsz));
+    std::vector<int32_t> cnt_all((size_t)max_nb * R), col_all((size_t)max_nnz * R);
+    CUDA_TRY(cudaMemcpyAsync(cnt_all.data(), d_cnt_all, sizeof(int32_t) * cnt_all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(col_all.data(), d_col_all, sizeof(int32_t) * col_all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    BlockCsrOp* full = new BlockCsrOp();
+    full->kind = OP_BLOCKCSR; full->ctx = ctx; full->nb = nb_global; full->nb_cols = nb_global; full->ne = ne; full->nnzb = tot_nnz;
+    full->n_local = nb_global * ne; full->n_global = full->n_local; full->distributed = false;
+    std::vector<int32_t> frow((size_t)nb_global + 1, 0), fcol((size_t)tot_nnz);
+    MGCR_TRY(dev_alloc_t(ctx, frow.size(), &full->d_brow));
+    MGCR_TRY(dev_alloc_t(ctx, fcol.size(), &full->d_bcol));
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)tot_nnz * bsz, &full->d_bval));
+    int64_t row = 0, pos = 0;
+    for (int r = 0; r < R; r++) {
+        for (int64_t b = 0; b < nbs[r]; b++) { frow[row + 1] = frow[row] + cnt_all[(size_t)r * max_nb + b]; row++; }
+        std::copy(col_all.begin() + (size_t)r * max_nnz, col_all.begin() + (size_t)r * max_nnz + nnzs[r], fcol.begin() + pos);
+        CUDA_TRY(cudaMemcpyAsync(full->d_bval + (size_t)pos * bsz, d_val_all + (size_t)r * max_nnz * bsz, sizeof(c128) * (size_t)nnzs[r] * bsz,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        pos += nnzs[r];
+    }
+    CUDA_TRY(cudaMemcpyAsync(full->d_brow, frow.data(), sizeof(int32_t) * frow.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(full->d_bcol, fcol.data(), sizeof(int32_t) * fcol.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, d_cnt); dev_free(ctx, d_cnt_all); dev_free(ctx, d_col); dev_free(ctx, d_col_all); dev_free(ctx, d_val_all); dev_free(ctx, d_val_send);
+    *out = full;
+    return MGCR_OK;
 }
 
 static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
@@ -324,12 +475,35 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
     LevelGeom& g = L.g;
     ARG_CHECK(c.n_spin >= 1 && c.n_col >= 1 && c.n_eigen >= 1, "MG level %d: n_spin, n_col, n_eigen must be positive", l);
     g.dof = c.n_spin * c.n_col;
+    const bool dist = L.A->distributed;
+    g.dist = dist ? 1 : 0; g.pd = 0; g.has_lo = 0; g.has_hi = 0; g.plane_sites = 0; g.plane_blocks = 0;
+    int64_t sd_local[4];
+    for (int i = 0; i < 4; i++) sd_local[i] = c.site_dims[i];
+    if (dist) {
+        // cfg carries the GLOBAL lattice; this rank holds a slab of planes of the first dimension of extent > 1
+        ARG_CHECK(mg->flags == 0 || !(mg->flags & MGCR_MG_NEG_NEIGHBOUR_BUG), "MG level %d: the negative-neighbour switch is single-GPU only", l);
+        int pd = 0;
+        while (pd < 3 && c.site_dims[pd] == 1) pd++;
+        int64_t plane = 1;
+        for (int i = pd + 1; i < 4; i++) plane *= c.site_dims[i];
+        ARG_CHECK(L.A->n_local % (plane * g.dof) == 0, "MG level %d: the operator's slab (%lld rows) is not a whole number of lattice planes", l, (long long)L.A->n_local);
+        sd_local[pd] = L.A->n_local / (plane * g.dof);
+        ARG_CHECK(sd_local[pd] >= 1 && c.sub[pd] >= 1 && sd_local[pd] % c.sub[pd] == 0,
+                  "MG level %d: this rank's slab of %lld planes is not a multiple of the aggregate size %lld (mgcr_ctx_set_slab_align)", l,
+                  (long long)sd_local[pd], (long long)c.sub[pd]);
+        g.pd = pd; g.has_lo = ctx->rank > 0; g.has_hi = ctx->rank + 1 < ctx->nranks;
+        g.plane_sites = plane;
+    }
     L.nsite = 1; g.bs = 1; g.nb = 1;
     for (int i = 0; i < 4; i++) {
-        ARG_CHECK(c.site_dims[i] >= 1 && c.sub[i] >= 1 && c.site_dims[i] % c.sub[i] == 0,
-                  "MG level %d: dimension %lld is not divisible by the aggregate size %lld (src/Mesh.h:245)", l, (long long)c.site_dims[i], (long long)c.sub[i]);
-        g.sd[i] = c.site_dims[i]; g.sub[i] = c.sub[i]; g.bd[i] = c.site_dims[i] / c.sub[i];
+        ARG_CHECK(sd_local[i] >= 1 && c.sub[i] >= 1 && sd_local[i] % c.sub[i] == 0,
+                  "MG level %d: dimension %lld is not divisible by the aggregate size %lld (src/Mesh.h:245)", l, (long long)sd_local[i], (long long)c.sub[i]);
+        g.sd[i] = sd_local[i]; g.sub[i] = c.sub[i]; g.bd[i] = sd_local[i] / c.sub[i];
         L.nsite *= g.sd[i]; g.bs *= g.sub[i]; g.nb *= g.bd[i];
+    }
+    if (dist) {
+        g.plane_blocks = 1;
+        for (int i = g.pd + 1; i < 4; i++) g.plane_blocks *= g.bd[i];
     }
     L.n = L.nsite * g.dof;
     ARG_CHECK(L.n == L.A->n_local, "MG level %d: mesh has %lld dofs, the operator %lld (src/GCR.h:160)", l, (long long)L.n, (long long)L.A->n_local);
@@ -373,29 +547,100 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
     MGCR_TRY(dev_free(ctx, ev));
     KLAUNCH(ctx, "mg_block_mgs", 0., (k_block_mgs<<<(unsigned)g.nb, 128, 0, ctx->stream>>>(g, L.d_P)));
     CHECK_LAUNCH();
+    // slab-partitioned level: the prolongator rows of the neighbour ranks' adjacent planes (ghost sites)
+    const int64_t lo_blocks = g.has_lo ? g.plane_blocks : 0, hi_blocks = g.has_hi ? g.plane_blocks : 0;
+    if (dist && (g.has_lo || g.has_hi)) {
+        const size_t plane_elems = (size_t)g.plane_sites * g.dof * ne;
+        c128 *send_lo = nullptr, *send_hi = nullptr;
+        MGCR_TRY(dev_alloc_t(ctx, plane_elems * ((g.has_lo ? 1 : 0) + (g.has_hi ? 1 : 0)), &L.d_Pg));
+        MGCR_TRY(dev_alloc_t(ctx, plane_elems, &send_lo));
+        MGCR_TRY(dev_alloc_t(ctx, plane_elems, &send_hi));
+        const int pgrid = stream_grid(ctx, (int64_t)plane_elems, 4);
+        if (g.has_lo) { KLAUNCH(ctx, "mg_pack_P", 32. * plane_elems, (k_pack_P_plane<<<pgrid, RED_THREADS, 0, ctx->stream>>>(g, 0, L.d_site_block, L.d_site_off, L.d_P, send_lo))); CHECK_LAUNCH(); }
+        if (g.has_hi) { KLAUNCH(ctx, "mg_pack_P", 32. * plane_elems, (k_pack_P_plane<<<pgrid, RED_THREADS, 0, ctx->stream>>>(g, L.nsite - g.plane_sites, L.d_site_block, L.d_site_off, L.d_P, send_hi))); CHECK_LAUNCH(); }
+        MGCR_TRY(dist_group_begin(ctx));
+        if (g.has_lo) {
+            MGCR_TRY(dist_send(ctx, send_lo, sizeof(c128) * plane_elems, ctx->rank - 1, ctx->stream));
+            MGCR_TRY(dist_recv(ctx, L.d_Pg, sizeof(c128) * plane_elems, ctx->rank - 1, ctx->stream));
+        }
+        if (g.has_hi) {
+            MGCR_TRY(dist_send(ctx, send_hi, sizeof(c128) * plane_elems, ctx->rank + 1, ctx->stream));
+            MGCR_TRY(dist_recv(ctx, L.d_Pg + (g.has_lo ? plane_elems : 0), sizeof(c128) * plane_elems, ctx->rank + 1, ctx->stream));
+        }
+        MGCR_TRY(dist_group_end(ctx));
+        MGCR_TRY(dev_free(ctx, send_lo));
+        MGCR_TRY(dev_free(ctx, send_hi));
+    }
     // Galerkin coarse operator, written straight into the block-CSR compute layout
-    RowSlots rs0;
-    row_slots(g, 0, &rs0);
-    L.K = rs0.K;
+    std::vector<int32_t> hrow((size_t)g.nb + 1, 0);
+    int kmax = 0;
+    {
+        RowSlots rs;
+        for (int64_t B = 0; B < g.nb; B++) {
+            row_slots(g, B, &rs);
+            hrow[B + 1] = hrow[B] + rs.K;
+            kmax = std::max(kmax, rs.K);
+        }
+    }
+    L.K = kmax;
     BlockCsrOp* Ac = new BlockCsrOp();
-    Ac->kind = OP_BLOCKCSR; Ac->ctx = ctx; Ac->nb = g.nb; Ac->nb_cols = g.nb; Ac->ne = ne; Ac->nnzb = g.nb * L.K;
-    Ac->n_local = L.nc; Ac->n_global = L.nc;
+    Ac->kind = OP_BLOCKCSR; Ac->ctx = ctx; Ac->nb = g.nb; Ac->nb_cols = g.nb + lo_blocks + hi_blocks; Ac->ne = ne; Ac->nnzb = hrow[g.nb];
+    Ac->n_local = L.nc; Ac->n_global = L.nc; Ac->distributed = dist;
     L.Ac = Ac;
     ARG_CHECK(Ac->nnzb < (int64_t)INT32_MAX, "MG level %d: coarse operator too large for one device shard", l);
     MGCR_TRY(dev_alloc_t(ctx, (size_t)g.nb + 1, &Ac->d_brow));
     MGCR_TRY(dev_alloc_t(ctx, (size_t)Ac->nnzb, &Ac->d_bcol));
     MGCR_TRY(dev_alloc_t(ctx, (size_t)Ac->nnzb * ne * ne, &Ac->d_bval));
     MGCR_TRY(dev_alloc_t(ctx, (size_t)Ac->nnzb, &L.d_bslot));
-    {
-        std::vector<int32_t> hrow((size_t)g.nb + 1);
-        for (int64_t r = 0; r <= g.nb; r++) hrow[r] = (int32_t)(r * L.K);
-        CUDA_TRY(cudaMemcpyAsync(Ac->d_brow, hrow.data(), sizeof(int32_t) * hrow.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    }
+    CUDA_TRY(cudaMemcpyAsync(Ac->d_brow, hrow.data(), sizeof(int32_t) * hrow.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     MGCR_TRY(galerkin(ctx, L, Ac->d_bcol, Ac->d_bval));
     if (mg->flags & MGCR_MG_NEG_NEIGHBOUR_BUG) {
-        KLAUNCH(ctx, "mg_neg_bug", 0., (k_neg_bug<<<(unsigned)g.nb, 128, 0, ctx->stream>>>(g, L.K, L.d_bslot, Ac->d_bval)));
+        KLAUNCH(ctx, "mg_neg_bug", 0., (k_neg_bug<<<(unsigned)g.nb, 128, 0, ctx->stream>>>(g, Ac->d_brow, L.d_bslot, Ac->d_bval)));
         CHECK_LAUNCH();
+    }
+    L.nc_global = L.nc; L.nc_offset = 0;
+    if (dist) {
+        // the coarse operator inherits the slab partition: one plane of aggregates to / from each neighbour per apply
+        MGCR_TRY(dist_allgather_host_i64(ctx, L.nc, L.nc_counts));
+        L.nc_global = 0;
+        for (int r = 0; r < ctx->nranks; r++) { if (r < ctx->rank) L.nc_offset += L.nc_counts[r]; L.nc_global += L.nc_counts[r]; }
+        Ac->n_global = L.nc_global;
+        HaloPlan* h = new HaloPlan();
+        h->elem = ne;
+        h->send_off.push_back(0); h->recv_off.push_back(0);
+        if (g.has_lo) {
+            h->peer.push_back(ctx->rank - 1); h->send_start.push_back(0);
+            h->send_off.push_back(h->send_off.back() + g.plane_blocks); h->recv_off.push_back(h->recv_off.back() + g.plane_blocks);
+        }
+        if (g.has_hi) {
+            h->peer.push_back(ctx->rank + 1); h->send_start.push_back(g.nb - g.plane_blocks);
+            h->send_off.push_back(h->send_off.back() + g.plane_blocks); h->recv_off.push_back(h->recv_off.back() + g.plane_blocks);
+        }
+        h->npeers = (int)h->peer.size();
+        h->n_ghost = lo_blocks + hi_blocks;
+        Ac->halo = h;
+        MGCR_TRY(dev_alloc_t(ctx, (size_t)std::max<int64_t>(1, h->n_ghost * ne), &h->d_ghost));
+        // gather here?  yes when the next level cannot keep the slab partition (a rank's aggregates no longer divide) or
+        // the coarse system is small enough that communication latency dominates (MGCR_GATHER_DOFS, default 2^18)
+        bool gather = L.nc_global <= gather_threshold();
+        if (!gather && l + 1 < mg->n_level) {
+            const int64_t sub_next = mg->lv[l + 1].cfg.sub[g.pd];
+            std::vector<int64_t> bds;
+            MGCR_TRY(dist_allgather_host_i64(ctx, g.bd[g.pd], bds));
+            for (int64_t b : bds) gather = gather || sub_next < 1 || (b % sub_next) != 0;
+        }
+        L.gather = gather;
+        if (gather) {
+            int64_t nb_global = L.nc_global / ne, nb_offset = L.nc_offset / ne;
+            MGCR_TRY(gather_coarse_operator(ctx, L, nb_offset, nb_global, &L.Ac_full));
+            int64_t maxc = 0;
+            for (int64_t cnt : L.nc_counts) maxc = std::max(maxc, cnt);
+            MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nc_global, &L.d_rc_full));
+            MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nc_global, &L.d_xc_full));
+            MGCR_TRY(dev_alloc_t(ctx, (size_t)maxc * (ctx->nranks + 1), &L.d_pad));
+            CUDA_TRY(cudaMemsetAsync(L.d_pad, 0, sizeof(c128) * (size_t)maxc * (ctx->nranks + 1), ctx->stream));
+        }
     }
     // cycle work vectors
     MGCR_TRY(dev_alloc_t(ctx, (size_t)n, &L.d_r));
@@ -409,8 +654,10 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
 static void level_free(mgcr_ctx* ctx, MgLevel& L) {
     dev_free(ctx, L.d_block_map); dev_free(ctx, L.d_site_block); dev_free(ctx, L.d_site_off); dev_free(ctx, L.d_P);
     dev_free(ctx, L.d_bslot); dev_free(ctx, L.d_r); dev_free(ctx, L.d_t); dev_free(ctx, L.d_rc); dev_free(ctx, L.d_xc);
+    dev_free(ctx, L.d_Pg); dev_free(ctx, L.d_rc_full); dev_free(ctx, L.d_xc_full); dev_free(ctx, L.d_pad);
     delete L.deeper; L.deeper = nullptr;
     delete L.Ac; L.Ac = nullptr;
+    delete L.Ac_full; L.Ac_full = nullptr;
 }
 
 extern "C" int mgcr_mg_destroy(mgcr_mg* mg) {
@@ -424,7 +671,6 @@ extern "C" int mgcr_mg_destroy(mgcr_mg* mg) {
 extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr_level_cfg* cfg, const mgcr_gcr_param* eigen,
                               const mgcr_gcr_param* coarse, const mgcr_gcr_param* smooth, int flags, const mgcr_c128* d_nearnull0, mgcr_mg** out) {
     ARG_CHECK(ctx && A && cfg && eigen && coarse && smooth && out && n_level >= 1, "mgcr_mg_create: bad argument");
-    ARG_CHECK(ctx->nranks == 1, "mgcr_mg_create: the distributed hierarchy is not available yet");
     *out = nullptr;
     mgcr_mg* mg = new mgcr_mg();
     mg->ctx = ctx; mg->n_level = n_level; mg->flags = flags;
@@ -433,18 +679,18 @@ extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr
     mg->eigen.std_conj = sc; mg->coarse.std_conj = sc; mg->smooth.std_conj = sc;
     mg->eigen.verbose = 0; mg->coarse.verbose = 0; mg->smooth.verbose = 0;
     mg->lv.resize((size_t)n_level);
+    for (int l = 0; l < n_level; l++) mg->lv[l].cfg = cfg[l];
     mgcr_op* cur = A;
     for (int l = 0; l < n_level; l++) {
-        mg->lv[l].cfg = cfg[l];
         mg->lv[l].A = cur;
         int st = level_setup(mg, l, l == 0 ? (const c128*)d_nearnull0 : nullptr);
         if (st != MGCR_OK) { mgcr_mg_destroy(mg); return st; }
-        cur = mg->lv[l].Ac;
+        cur = mg->lv[l].gather ? (mgcr_op*)mg->lv[l].Ac_full : (mgcr_op*)mg->lv[l].Ac;
     }
     for (int l = 0; l + 1 < n_level; l++) {
         MgOp* op = new MgOp();
         op->kind = OP_MG; op->ctx = ctx; op->mg = mg; op->level = l + 1;
-        op->n_local = mg->lv[l + 1].n; op->n_global = op->n_local;
+        op->n_local = mg->lv[l + 1].n; op->n_global = mg->lv[l + 1].A->n_global; op->distributed = mg->lv[l + 1].A->distributed;
         mg->lv[l].deeper = op;
     }
     *out = mg;
@@ -489,10 +735,13 @@ extern "C" int mgcr_mg_export_coarse(mgcr_mg* mg, int level, int64_t* h_brow, in
     ARG_CHECK(h_brow && h_bcol && h_bval, "NULL output");
     const MgLevel& L = mg->lv[level];
     const LevelGeom& g = L.g;
-    const int ne = g.ne, K = L.K;
+    ARG_CHECK(!g.dist, "mgcr_mg_export_coarse: the reference-pattern export is single-GPU (level %d is slab-partitioned)", level);
+    const int ne = g.ne;
     const size_t bsz = (size_t)ne * ne;
-    std::vector<c128> val((size_t)g.nb * K * bsz);
-    std::vector<int8_t> slot((size_t)g.nb * K);
+    std::vector<c128> val((size_t)L.Ac->nnzb * bsz);
+    std::vector<int8_t> slot((size_t)L.Ac->nnzb);
+    std::vector<int32_t> prow((size_t)g.nb + 1);
+    CUDA_TRY(cudaMemcpyAsync(prow.data(), L.Ac->d_brow, sizeof(int32_t) * prow.size(), cudaMemcpyDeviceToHost, mg->ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(val.data(), L.Ac->d_bval, sizeof(c128) * val.size(), cudaMemcpyDeviceToHost, mg->ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(slot.data(), L.d_bslot, slot.size(), cudaMemcpyDeviceToHost, mg->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(mg->ctx->stream));
@@ -514,9 +763,9 @@ extern "C" int mgcr_mg_export_coarse(mgcr_mg* mg, int level, int64_t* h_brow, in
             h_bcol[9 * R + a] = ent[a].col;
             mgcr_c128* dst = h_bval + (size_t)(9 * R + a) * bsz;
             int src = -1;
-            if (!ent[a].zero) for (int q = 0; q < K; q++) if (slot[R * K + q] == ent[a].s) src = q;
+            if (!ent[a].zero) for (int q = prow[R]; q < prow[R + 1]; q++) if (slot[q] == ent[a].s) src = q;
             for (int r = 0; r < ne; r++) for (int c = 0; c < ne; c++) {
-                c128 v = src < 0 ? cmake(0., 0.) : val[(size_t)(R * K + src) * bsz + (size_t)c * ne + r];
+                c128 v = src < 0 ? cmake(0., 0.) : val[(size_t)src * bsz + (size_t)c * ne + r];
                 dst[(size_t)r * ne + c].re = v.x; dst[(size_t)r * ne + c].im = v.y;
             }
         }
@@ -554,7 +803,7 @@ extern "C" int mgcr_mg_op_create(mgcr_ctx* ctx, mgcr_mg* mg, mgcr_op** out) {
     ARG_CHECK(ctx && mg && out, "mgcr_mg_op_create: NULL argument");
     MgOp* op = new MgOp();
     op->kind = OP_MG; op->ctx = ctx; op->mg = mg; op->level = 0;
-    op->n_local = mg->lv[0].n; op->n_global = op->n_local;
+    op->n_local = mg->lv[0].n; op->n_global = mg->lv[0].A->n_global; op->distributed = mg->lv[0].A->distributed;
     *out = op;
     return MGCR_OK;
 }

@@ -11,6 +11,11 @@ struct LevelGeom {
     int64_t bs;         // sites per aggregate
     int64_t bl;         // dofs per aggregate = bs * dof
     int64_t nb;         // aggregates
+    // slab-partitioned level (all extents above are LOCAL): the slab runs along site dim `pd`, the first dim of extent > 1;
+    // planes orthogonal to it are contiguous.  Ghost sites / ghost aggregates = the neighbour ranks' adjacent planes,
+    // lower neighbour first.
+    int dist, pd, has_lo, has_hi;
+    int64_t plane_sites, plane_blocks;   // sites / aggregates per plane
 };
 
 struct MgLevel {
@@ -27,6 +32,13 @@ struct MgLevel {
     BlockCsrOp* Ac = nullptr;         // Galerkin coarse operator, owned
     c128 *d_r = nullptr, *d_t = nullptr, *d_rc = nullptr, *d_xc = nullptr;   // cycle work vectors
     mgcr_op* deeper = nullptr;        // MG-as-operator of level l+1 (K-cycle preconditioner of the coarse solve)
+    // distributed levels
+    c128* d_Pg = nullptr;             // prolongator rows of the ghost sites [ghost site][dof][ne]
+    bool gather = false;              // the coarse system of this level is replicated on every rank (deeper levels too)
+    BlockCsrOp* Ac_full = nullptr;    // replicated coarse operator (gather level only)
+    std::vector<int64_t> nc_counts;   // coarse dofs per rank
+    int64_t nc_offset = 0, nc_global = 0;
+    c128 *d_rc_full = nullptr, *d_xc_full = nullptr, *d_pad = nullptr;
 };
 
 struct mgcr_mg {
@@ -44,3 +56,4 @@ int blocking_device(mgcr_ctx* ctx, const int64_t sd[4], const int64_t sub[4], in
                     int32_t* d_site_block, int32_t* d_site_off);
 int vec_gamma5(mgcr_ctx* ctx, int64_t n, int64_t inner, int64_t axis_dim, const c128* in, c128* out);
 int vec_axpy(mgcr_ctx* ctx, int64_t n, c128 s, const c128* b, const c128* a, c128* out);
+int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);

@@ -217,7 +217,7 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
     a.x = x; a.y = y; a.dirac = dirac; a.k = k; a.diag = diag;
     a.halo_lo = nullptr; a.halo_hi = nullptr;
     const int64_t plane = a.n1 * a.n0;
-    if (ctx->nranks > 1) {
+    if (distributed) {
         // one plane to each slab neighbour (NCCL send/recv on the compute stream)
         int lo = ctx->rank - 1, hi = ctx->rank + 1;
         MGCR_TRY(dist_group_begin(ctx));
@@ -263,13 +263,14 @@ extern "C" int mgcr_hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims,
     int64_t zb = 0, ze = op->gdims[0];
     if (ctx->nranks > 1) {
         ARG_CHECK(ndim == 3, "mgcr_hopping_create: the distributed stencil is 3-D (slabs along dims[0])");
-        MGCR_TRY(mgcr_slab_range(op->gdims[0], 1, ctx->rank, ctx->nranks, &zb, &ze));
+        MGCR_TRY(mgcr_slab_range(op->gdims[0], ctx->slab_align, ctx->rank, ctx->nranks, &zb, &ze));
         ARG_CHECK(ze > zb, "mgcr_hopping_create: rank %d owns no plane", ctx->rank);
         int64_t plane = op->gdims[1] * op->gdims[2];
         int st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_lo);
         if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_hi);
         if (st != MGCR_OK) { delete op; return st; }
     }
+    op->distributed = ctx->nranks > 1;
     op->z_begin = zb; op->n2_local = ze - zb;
     op->n_local = op->n2_local * op->gdims[1] * op->gdims[2];
     op->n_global = op->gdims[0] * op->gdims[1] * op->gdims[2];
@@ -306,7 +307,7 @@ extern "C" int mgcr_dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double 
     *out = nullptr;
     DiracOp* op = new DiracOp();
     op->kind = OP_DIRAC; op->ctx = ctx; op->D = D; op->k = cmake(k_re, k_im);
-    op->n_local = D->n_local; op->n_global = D->n_global;
+    op->n_local = D->n_local; op->n_global = D->n_global; op->distributed = D->distributed;
     if (h_diag) {
         int st = dev_alloc_t(ctx, (size_t)op->n_local, &op->d_diag);
         if (st != MGCR_OK) { delete op; return st; }

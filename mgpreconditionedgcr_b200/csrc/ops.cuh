@@ -24,6 +24,7 @@ struct mgcr_op {
     mgcr_ctx* ctx = nullptr;
     int64_t n_local = 0;    // rows / vector length held by this rank
     int64_t n_global = 0;
+    bool distributed = false;   // rows are this rank's slab of a global operator: inner products over its vectors are all-reduced
     virtual ~mgcr_op() {}
     virtual int apply(const c128* x, c128* y) = 0;
     virtual double apply_bytes() const { return 0.; }

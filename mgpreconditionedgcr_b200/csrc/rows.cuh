@@ -43,16 +43,19 @@ struct SellRows {
 struct HopRows {
     int64_t n2, n1, n0;   // local planes, rows, columns (single GPU: global)
     int dirac; c128 k; const double* diag;
+    // slab-partitioned operator: the neighbour planes owned by rank-1 / rank+1 are addressed as ghost columns
+    // n_local + p (lower plane) and n_local + ghost_lo + p (upper plane), p = y*n0 + x
+    int has_lo, has_hi; int64_t ghost_lo;
     template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
         const int64_t x = i % n0, y = (i / n0) % n1, z = i / (n0 * n1);
         c128 v = cmake(1., 0.);
         if (dirac) { v = cmul(k, v); v = cmake(-v.x, -v.y); }
-        if (z > 0) f(i - n0 * n1, v);
+        if (z > 0) f(i - n0 * n1, v); else if (has_lo) f(n2 * n1 * n0 + y * n0 + x, v);
         if (y > 0) f(i - n0, v);
         if (x > 0) f(i - 1, v);
         if (x < n0 - 1) f(i + 1, v);
         if (y < n1 - 1) f(i + n0, v);
-        if (z < n2 - 1) f(i + n0 * n1, v);
+        if (z < n2 - 1) f(i + n0 * n1, v); else if (has_hi) f(n2 * n1 * n0 + ghost_lo + y * n0 + x, v);
         if (dirac) f(i, cmake(diag ? diag[i] : 1., 0.));
     }
     // k_hopping (ops.cu): neighbours in ascending column order z-1, y-1, x-1, x+1, y+1, z+1 starting from the first
@@ -99,10 +102,11 @@ struct BlockRows {
     }
 };
 
-// Calls f(rows) with the row accessor of a single-GPU matrix-like operator; returns false when A has none (solvers,
-// callbacks, distributed operators with ghosts).
+// Calls f(rows) with the row accessor of a matrix-like operator; returns false when A has none (solvers, callbacks).
+// Slab-partitioned operators are accepted only with allow_dist (their rows then reference ghost columns >= n_local,
+// lower neighbour's plane first): the multigrid set-up understands those, the persistent small-level solver does not.
 template <class F>
-static inline bool with_rows(mgcr_op* A, F&& f, int* status) {
+static inline bool with_rows(mgcr_op* A, F&& f, int* status, bool allow_dist = false) {
     int dirac = 0; c128 k = cmake(0., 0.); const double* diag = nullptr;
     if (A->kind == OP_DIRAC) {
         DiracOp* d = static_cast<DiracOp*>(A);
@@ -116,13 +120,14 @@ static inline bool with_rows(mgcr_op* A, F&& f, int* status) {
     }
     if (A->kind == OP_HOPPING) {
         HoppingOp* h = static_cast<HoppingOp*>(A);
-        if (h->ctx->nranks > 1) return false;
-        *status = f(HopRows{h->n2_local, h->gdims[1], h->gdims[2], dirac, k, diag});
+        if (h->distributed && !allow_dist) return false;
+        const int lo = h->distributed && h->ctx->rank > 0, hi = h->distributed && h->ctx->rank + 1 < h->ctx->nranks;
+        *status = f(HopRows{h->n2_local, h->gdims[1], h->gdims[2], dirac, k, diag, lo, hi, lo ? h->gdims[1] * h->gdims[2] : 0});
         return true;
     }
     if (A->kind == OP_BLOCKCSR && !dirac) {
         BlockCsrOp* bo = static_cast<BlockCsrOp*>(A);
-        if (bo->halo) return false;
+        if (bo->halo && !allow_dist) return false;
         *status = f(BlockRows{bo->d_brow, bo->d_bcol, bo->d_bval, bo->ne});
         return true;
     }

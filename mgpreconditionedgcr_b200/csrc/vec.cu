@@ -72,17 +72,17 @@ extern "C" int mgcr_vec_scale(mgcr_ctx* ctx, int64_t n, double s_re, double s_im
 }
 
 // device-resident result: d_out[0..1] = sum conj(a) b (this rank's part, then all-reduced)
-int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out) {
+int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist) {
     KLAUNCH(ctx, "vec_dot", 32. * n, (k_dot<<<stream_grid(ctx, n, 4, 2), RED_THREADS, 0, ctx->stream>>>(n, a, b, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
-    if (ctx->nranks > 1) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 2));
+    if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 2));
     return MGCR_OK;
 }
 
-int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out) {
+int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist) {
     KLAUNCH(ctx, "vec_norm2", 16. * n, (k_norm2<<<stream_grid(ctx, n, 4, 2), RED_THREADS, 0, ctx->stream>>>(n, a, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
-    if (ctx->nranks > 1) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 1));
+    if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 1));
     return MGCR_OK;
 }
 
@@ -95,19 +95,19 @@ static int read_scalars(mgcr_ctx* ctx, const double* d, int n, double* h) {
 
 extern "C" int mgcr_vec_dot(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, const mgcr_c128* b, double out[2]) {
     ARG_CHECK(ctx && out && (n == 0 || (a && b)), "mgcr_vec_dot: NULL buffer");
-    MGCR_TRY(vec_dot_dev(ctx, n, (const c128*)a, (const c128*)b, ctx->d_scratch));
+    MGCR_TRY(vec_dot_dev(ctx, n, (const c128*)a, (const c128*)b, ctx->d_scratch, ctx->nranks > 1));
     return read_scalars(ctx, ctx->d_scratch, 2, out);
 }
 
 extern "C" int mgcr_vec_squarednorm(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, double* out) {
     ARG_CHECK(ctx && out && (n == 0 || a), "mgcr_vec_squarednorm: NULL buffer");
-    MGCR_TRY(vec_norm2_dev(ctx, n, (const c128*)a, ctx->d_scratch));
+    MGCR_TRY(vec_norm2_dev(ctx, n, (const c128*)a, ctx->d_scratch, ctx->nranks > 1));
     return read_scalars(ctx, ctx->d_scratch, 1, out);
 }
 
 // a *= 1/sqrt(sum |a|^2), scalar never leaves the device (src/Fields.h:237-243)
-int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a) {
-    MGCR_TRY(vec_norm2_dev(ctx, n, a, ctx->d_scratch + 8));
+int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist) {
+    MGCR_TRY(vec_norm2_dev(ctx, n, a, ctx->d_scratch + 8, dist));
     KLAUNCH(ctx, "vec_normalise", 32. * n, (k_scale_inv_sqrt<<<stream_grid(ctx, n, 8), RED_THREADS, 0, ctx->stream>>>(n, ctx->d_scratch + 8, a)));
     CHECK_LAUNCH();
     return MGCR_OK;
@@ -115,7 +115,7 @@ int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a) {
 
 extern "C" int mgcr_vec_normalise(mgcr_ctx* ctx, int64_t n, mgcr_c128* a) {
     ARG_CHECK(ctx && (n == 0 || a), "mgcr_vec_normalise: NULL buffer");
-    return vec_normalise(ctx, n, (c128*)a);
+    return vec_normalise(ctx, n, (c128*)a, ctx->nranks > 1);
 }
 
 int vec_gamma5(mgcr_ctx* ctx, int64_t n, int64_t inner, int64_t axis_dim, const c128* in, c128* out) {

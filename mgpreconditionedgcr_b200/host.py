@@ -21,6 +21,7 @@ class Context:
         check(self.lib.mgcr_ctx_create(device, C.byref(h)))
         self.h = h
         self.device = device
+        self.slab_align = 1
 
     def close(self):
         if self.h:
@@ -64,6 +65,11 @@ class Context:
         buf = C.create_string_buffer(128)
         check(capi.load().mgcr_nccl_unique_id(buf))
         return bytes(buf.raw)
+
+    def set_slab_align(self, align):
+        """slab boundaries of distributed operators created afterwards are multiples of `align` planes"""
+        check(self.lib.mgcr_ctx_set_slab_align(self.h, int(align)))
+        self.slab_align = int(align)
 
     def rank(self):
         r, n = C.c_int(), C.c_int()

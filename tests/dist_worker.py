@@ -1,0 +1,105 @@
+"""One rank of the multi-GPU parity check (spawned by tests/test_gpu_dist.py, or run under torchrun):
+slab-partitioned stencil operator, GCR and the distributed multigrid hierarchy against the same problem solved on one
+GPU by the same library.  Prints one JSON line per check on rank 0."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(rank, world, port, gather_dofs):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if gather_dofs is not None:
+        os.environ["MGCR_GATHER_DOFS"] = str(gather_dofs)
+    import torch
+    import torch.distributed as dist
+    from mgpreconditionedgcr_b200 import host
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    ctx = host.Context(rank)
+    ids = [host.Context.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.init_dist(rank, world, ids[0])
+    ctx.set_slab_align(16)
+    single = host.Context(rank)          # the same problem on one GPU, for comparison
+
+    dims = [32 * world, 16, 24]
+    V = int(np.prod(dims))
+    plane = dims[1] * dims[2]
+    k = 1. / 6.01
+    b, e = host.slab_range(dims[0], 16, rank, world)
+    sl = slice(b * plane, e * plane)
+    out = {}
+
+    A = host.DiracOp(ctx, host.Hopping(ctx, dims), k)
+    A1 = host.DiracOp(single, host.Hopping(single, dims), k)
+    assert A.get_dim() == (e - b) * plane and A.global_dim() == V
+    # operator apply with halo exchange
+    f = single.init_rand(1, V)
+    fl = ctx.init_rand(1, A.get_dim(), skip=b * plane)
+    assert np.array_equal(fl.numpy(), f.numpy()[sl])
+    out["apply_exact"] = bool(np.array_equal(A(fl).numpy(), A1(f).numpy()[sl]))
+    # all-reduced inner products
+    g = single.init_rand(3, V)
+    gl = ctx.init_rand(3, A.get_dim(), skip=b * plane)
+    out["dot_rel"] = abs(fl.dot(gl) - f.dot(g)) / abs(f.dot(g))
+    # unpreconditioned GCR on a well-conditioned shift of the operator (converges inside the parity horizon of restarted
+    # GCR, tests/test_parity_horizon.py), then on the ill-conditioned one for the iteration count MG has to beat
+    p = host.GCR_Param(0, 5, 2000, 1e-10, False, None, None)
+    rhs = single.init_rand(0, V)
+    rhsl = ctx.init_rand(0, A.get_dim(), skip=b * plane)
+    x1 = single.field(V).set_zero()
+    it1, _ = host.GCR(single, A1, p).solve(rhs, x1)
+    Aw = host.DiracOp(ctx, host.Hopping(ctx, dims), 0.12)
+    Aw1 = host.DiracOp(single, host.Hopping(single, dims), 0.12)
+    x1.set_zero()
+    itw1, h1 = host.GCR(single, Aw1, p).solve(rhs, x1)
+    xl = ctx.field(A.get_dim()).set_zero()
+    itd, hd = host.GCR(ctx, Aw, p).solve(rhsl, xl)
+    m = min(len(h1), len(hd), 25)
+    out["gcr_iters"] = [itw1, itd]
+    out["gcr_hist_rel"] = float(np.max(np.abs(hd[:m] - h1[:m]) / h1[:m]))
+    out["gcr_x_rel"] = float(np.linalg.norm(xl.numpy() - x1.numpy()[sl]) / np.linalg.norm(x1.numpy()[sl]))
+    # multigrid: two coarse grids, 4^3 aggregates
+    lv = [dict(site_dims=[1] + dims, sub=[1, 4, 4, 4], n_spin=1, n_col=1, n_eigen=4),
+          dict(site_dims=[1] + [d // 4 for d in dims], sub=[1, 4, 2, 2], n_spin=1, n_col=4, n_eigen=4)]
+    eig, coarse, smooth = host.GCR_Param(0, 10, 10, 1e-8), host.GCR_Param(0, 10, 8, 1e-2), host.GCR_Param(0, 4, 3, 1e-8)
+    mg = host.MG(ctx, A, lv, eig, coarse, smooth)
+    mg1 = host.MG(single, A1, lv, eig, coarse, smooth)
+    i0, i1 = mg.info(0), mg1.info(0)
+    out["nblocks"] = [i0["n_blocks"], i1["n_blocks"]]
+    # Galerkin identity on the distributed objects: Ac xc == R A P xc (ghost prolongator rows + coarse halo exchange)
+    nc = i0["n_blocks"] * i0["ne"]
+    xc = ctx.init_rand(5, nc, skip=rank * nc)
+    lhs = mg.coarse_op(0)(xc).numpy()
+    rhs_c = mg.restrict(A(mg.expand(xc))).numpy()
+    out["galerkin_rel"] = float(np.linalg.norm(lhs - rhs_c) / np.linalg.norm(rhs_c))
+    # restrict / prolong are local: R P = 1
+    out["rp_identity"] = float(np.linalg.norm(mg.restrict(mg.expand(xc)).numpy() - xc.numpy()) / np.linalg.norm(xc.numpy()))
+    # MG-preconditioned GCR, distributed vs one GPU
+    pm = host.GCR_Param(0, 10, 200, 1e-10, False, None, mg)
+    pm1 = host.GCR_Param(0, 10, 200, 1e-10, False, None, mg1)
+    y1 = single.field(V).set_zero()
+    itm1, hm1 = host.GCR(single, A1, pm1).solve(rhs, y1)
+    yl = ctx.field(A.get_dim()).set_zero()
+    itmd, hmd = host.GCR(ctx, A, pm).solve(rhsl, yl)
+    r = rhsl - A(yl)
+    out["mg_iters"] = [itm1, itmd, it1]
+    out["mg_true_res"] = r.norm() / rhsl.norm()
+    out["mg_x_rel"] = float(np.linalg.norm(yl.numpy() - y1.numpy()[sl]) / np.linalg.norm(y1.numpy()[sl]))
+    res = [None] * world
+    dist.all_gather_object(res, out)
+    if rank == 0:
+        print("DIST_RESULT " + json.dumps(res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), None if sys.argv[4] == "default" else int(sys.argv[4]))

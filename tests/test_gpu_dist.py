@@ -1,0 +1,46 @@
+"""Multi-GPU parity: the slab-partitioned path (NCCL halo exchange + all-reduced inner products + distributed multigrid
+hierarchy with coarse-level gather) against the same problem on one GPU.  Needs >= 2 GPUs; skipped otherwise (the
+round-end `-m gpu` run has one GPU; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dist.py -m gpu`)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def run_world(world, gather):
+    port = 29500 + (os.getpid() % 1000)
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(r), str(world), str(port), gather],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=900)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-3000:] for o in outs)
+    line = [ln for ln in outs[0].splitlines() if ln.startswith("DIST_RESULT ")][-1]
+    return json.loads(line[len("DIST_RESULT "):])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gather", ["default", "0"])   # default: coarse level replicated at once; 0: hierarchy stays distributed as deep as it can
+@pytest.mark.parametrize("world", [2, 4])
+def test_distributed_against_single_gpu(world, gather):
+    if ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    for o in run_world(world, gather):
+        assert o["apply_exact"]                                   # halo exchange: bit-identical to the one-GPU stencil
+        assert o["dot_rel"] < 1e-14
+        assert abs(o["gcr_iters"][0] - o["gcr_iters"][1]) <= 1 and o["gcr_hist_rel"] < 1e-10 and o["gcr_x_rel"] < 1e-8
+        assert o["nblocks"][0] * world == o["nblocks"][1]
+        assert o["galerkin_rel"] < 1e-13 and o["rp_identity"] < 1e-13
+        assert o["mg_true_res"] < 1.2e-10
+        assert abs(o["mg_iters"][0] - o["mg_iters"][1]) <= 2 and o["mg_iters"][1] < o["mg_iters"][2]
+        assert o["mg_x_rel"] < 1e-8
