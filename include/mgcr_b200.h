@@ -63,6 +63,11 @@ int mgcr_ctx_set_profile(mgcr_ctx* ctx, int enabled);
 /* copies up to cap entries (names are owned by the context); *n_out = number of kernel classes seen */
 int mgcr_ctx_get_profile(mgcr_ctx* ctx, int cap, const char** names, double* ms, int64_t* calls, double* bytes, int* n_out);
 
+/* tunables: "small_gcr_rows" (operators up to this many rows are solved by one persistent kernel, default 2^19; 0 = never),
+ * "gather_dofs" (distributed coarse systems up to this size are replicated on every rank, default 2^18),
+ * "dot_tma" (1 = TMA-staged batched inner products on long vectors, default 1) */
+int mgcr_ctx_set_option(mgcr_ctx* ctx, const char* key, int64_t value);
+
 /* Multi-GPU (nothing in the reference: it is single-process).  Rank 0 makes an id, the caller broadcasts the
  * 128 bytes by any means (torch.distributed, MPI, a file), every rank then calls init_dist. */
 int mgcr_nccl_unique_id(void* h_id128);

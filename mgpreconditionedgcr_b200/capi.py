@@ -52,6 +52,7 @@ SIGNATURES = {
     "mgcr_ctx_stream": [_vp, _pvp],
     "mgcr_ctx_launch_count": [_vp, _pi64],
     "mgcr_ctx_set_profile": [_vp, _int],
+    "mgcr_ctx_set_option": [_vp, C.c_char_p, _i64],
     "mgcr_ctx_get_profile": [_vp, _int, C.POINTER(C.c_char_p), _pdbl, _pi64, _pdbl, _pint],
     "mgcr_nccl_unique_id": [_vp],
     "mgcr_ctx_init_dist": [_vp, _int, _int, _vp],

@@ -97,6 +97,11 @@ struct mgcr_ctx {
     // distributed
     int rank = 0, nranks = 1;
     int64_t slab_align = 1;                 // slab boundaries along the slowest lattice index are multiples of this
+    // tunables (mgcr_ctx_set_option; defaults from the environment variables MGCR_SMALL_GCR_N / MGCR_GATHER_DOFS / MGCR_DOT_TMA)
+    int64_t small_gcr_rows = (int64_t)1 << 19;   // operators up to this many rows: whole GCR solve in one persistent kernel
+    int64_t gather_dofs = (int64_t)1 << 18;      // distributed coarse systems up to this size are replicated on every rank
+    int dot_tma = 1;                              // TMA-staged batched inner products for long vectors
+    int hopping_kernel = 1;                       // matrix-free stencil: 1 = register-marching / L1 form, 0 = shared-memory tile form
     void* nccl_comm = nullptr;
     // profiling
     bool profile = false;

@@ -15,7 +15,8 @@ void mgcr_set_error(const char* fmt, ...) {
 extern "C" const char* mgcr_last_error(void) { return g_err; }
 extern "C" int mgcr_abi_version(void) { return 1; }
 
-static const size_t MEM_CACHE_LIMIT = (size_t)48 << 30;   // idle bytes kept before the cache is trimmed
+// Idle buffers are kept until the device runs out of memory (dev_alloc then trims and retries): a 512^3 solve recycles
+// ~100 GB of Krylov workspaces between the levels of one cycle, a fixed cap only makes the cache thrash.
 
 static void mem_trim(mgcr_ctx* ctx) {
     if (ctx->mem_free.empty()) return;
@@ -65,7 +66,6 @@ int dev_free(mgcr_ctx* ctx, void* p) {
     ctx->mem_free.emplace(it->second, p);
     ctx->mem_free_bytes += it->second;
     ctx->mem_live.erase(it);
-    if (ctx->mem_free_bytes > MEM_CACHE_LIMIT) mem_trim(ctx);
     return MGCR_OK;
 }
 
@@ -101,7 +101,21 @@ extern "C" int mgcr_ctx_create(int device, mgcr_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->d_scratch, sizeof(double) * 256));
     CUDA_TRY(cudaMemset(c->d_scratch, 0, sizeof(double) * 256));
     CUDA_TRY(cudaMallocHost(&c->h_pinned, sizeof(double) * 256));
+    if (getenv("MGCR_SMALL_GCR_N")) c->small_gcr_rows = atoll(getenv("MGCR_SMALL_GCR_N"));
+    if (getenv("MGCR_GATHER_DOFS")) c->gather_dofs = atoll(getenv("MGCR_GATHER_DOFS"));
+    if (getenv("MGCR_DOT_TMA")) c->dot_tma = atoi(getenv("MGCR_DOT_TMA"));
+    if (getenv("MGCR_HOPPING_KERNEL")) c->hopping_kernel = atoi(getenv("MGCR_HOPPING_KERNEL"));
     *out = c;
+    return MGCR_OK;
+}
+
+extern "C" int mgcr_ctx_set_option(mgcr_ctx* c, const char* key, int64_t value) {
+    ARG_CHECK(c && key, "mgcr_ctx_set_option: NULL argument");
+    if (!strcmp(key, "small_gcr_rows")) c->small_gcr_rows = value;
+    else if (!strcmp(key, "gather_dofs")) c->gather_dofs = value;
+    else if (!strcmp(key, "dot_tma")) c->dot_tma = (int)value;
+    else if (!strcmp(key, "hopping_kernel")) c->hopping_kernel = (int)value;
+    else { mgcr_set_error("mgcr_ctx_set_option: unknown option '%s'", key); return MGCR_ERR_ARG; }
     return MGCR_OK;
 }
 

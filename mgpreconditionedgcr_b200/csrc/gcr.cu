@@ -55,8 +55,7 @@ static int launch_dot_hist_tma(mgcr_ctx* ctx, int64_t n, const c128* Ar, const c
 // <= NK vectors each; nh >= 3 on long vectors: TMA-staged ring (measured on B200, profiles/r01_kbench_dot.txt).
 static int dot_hist(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
                     int std_conj, double* out, const double* guard, double tol2) {
-    static const int use_tma = env_int("MGCR_DOT_TMA", 1);   // experiment knob
-    if (use_tma && nh >= 3 && n >= ((int64_t)1 << 20)) {
+    if (ctx->dot_tma && nh >= 3 && n >= ((int64_t)1 << 20)) {
         switch (nh) {
 #define C(NH) case NH: return launch_dot_hist_tma<NH>(ctx, n, Ar, Aps, stride, hl, std_conj, out, guard, tol2);
             C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)

@@ -206,11 +206,6 @@ __global__ void __launch_bounds__(SG_THREADS) k_gcr_small(Rows M, SmallGcrArgs a
 // ----------------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------------
-static int64_t small_limit() {
-    static const int64_t v = getenv("MGCR_SMALL_GCR_N") ? atoll(getenv("MGCR_SMALL_GCR_N")) : (int64_t)1 << 19;
-    return v;
-}
-
 template <class Rows>
 static int launch_small(mgcr_ctx* ctx, const Rows& rows, SmallGcrArgs& a, int* grid_out) {
     static thread_local int max_blocks_per_sm = -1;
@@ -231,7 +226,7 @@ int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const 
                     int* iters_out, int storage, int restart, int* handled) {
     *handled = 0;
     const int64_t n = A->n_local;
-    if (n == 0 || n > small_limit() || storage > SG_MAXH || prm->verbose || rhs == x || A->distributed) return MGCR_OK;
+    if (n == 0 || n > ctx->small_gcr_rows || storage > SG_MAXH || prm->verbose || rhs == x || A->distributed) return MGCR_OK;
     int st = MGCR_OK;
     c128* work = nullptr;
     double* scal = nullptr;

@@ -388,11 +388,6 @@ static int galerkin(mgcr_ctx* ctx, MgLevel& L, int32_t* bcol, c128* bval) {
     return MGCR_ERR_UNSUPPORTED;
 }
 
-static int64_t gather_threshold() {
-    static const int64_t v = getenv("MGCR_GATHER_DOFS") ? atoll(getenv("MGCR_GATHER_DOFS")) : (int64_t)1 << 18;
-    return v;
-}
-
 // Replicated copy of a slab-partitioned coarse operator: every rank contributes its block rows (ghost columns turned
 // into global block columns), all ranks assemble the same block-CSR.  One-off, staged through the host.
 static int gather_coarse_operator(mgcr_ctx* ctx, MgLevel& L, int64_t nb_offset, int64_t nb_global, BlockCsrOp** out) {
@@ -622,8 +617,8 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
         Ac->halo = h;
         MGCR_TRY(dev_alloc_t(ctx, (size_t)std::max<int64_t>(1, h->n_ghost * ne), &h->d_ghost));
         // gather here?  yes when the next level cannot keep the slab partition (a rank's aggregates no longer divide) or
-        // the coarse system is small enough that communication latency dominates (MGCR_GATHER_DOFS, default 2^18)
-        bool gather = L.nc_global <= gather_threshold();
+        // the coarse system is small enough that communication latency dominates (option gather_dofs, default 2^18)
+        bool gather = L.nc_global <= ctx->gather_dofs;
         if (!gather && l + 1 < mg->n_level) {
             const int64_t sub_next = mg->lv[l + 1].cfg.sub[g.pd];
             std::vector<int64_t> bds;

@@ -205,6 +205,55 @@ __global__ void __launch_bounds__(HOP_TX* HOP_TY) k_hopping(HopArgs a) {
     }
 }
 
+// Second form of the same stencil, without shared memory or block-wide barriers: a thread owns one (x, y) column of a z-chunk
+// and marches along z with the z-neighbours in registers (prev / cur / next, the plane after next already in flight); the
+// x and y neighbours are read through L1/L2 -- they were just loaded as own-column elements by the neighbouring lanes /
+// warps, so HBM sees every element once (ncu: dram read = 16 B per site, profiles/r01_ncu_full_mg3d_256.md).  Warps never
+// wait for each other.  The CTA's threads cover hl_tx consecutive x (whole rows when they fit: long contiguous DRAM bursts)
+// times HL_THREADS/hl_tx rows.  It is also the form for 2-D lattices, which are traversed as (ny, 1, nx): 4.4 TB/s against
+// 2.4 TB/s for the tile kernel.  Variants measured and rejected on B200 (profiles/r01_stencil_experiments.txt): deeper
+// register prefetch of the own column (3.6 TB/s), prefetching the in-plane neighbours one plane ahead (3.8 TB/s), x
+// neighbours by warp shuffle (3.4 TB/s), other tile shapes / chunk lengths (all 3.8-4.1 TB/s in 3-D).
+enum { HL_THREADS = 512 };
+
+__global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx) {
+    const int hl_ty = HL_THREADS / hl_tx;
+    const int64_t gx = (int64_t)blockIdx.x * hl_tx + threadIdx.x % hl_tx;
+    const int64_t gy = (int64_t)blockIdx.y * hl_ty + threadIdx.x / hl_tx;
+    if (gx >= a.n0 || gy >= a.n1) return;
+    const int64_t zs = (int64_t)blockIdx.z * a.zc;
+    const int64_t ze = min(zs + a.zc, a.n2);
+    const int64_t plane = a.n1 * a.n0;
+    const int64_t c_off = gy * a.n0 + gx;
+    const c128 zero = cmake(0., 0.);
+    const bool xm = gx > 0, xp = gx + 1 < a.n0, ym = gy > 0, yp = gy + 1 < a.n1;
+    auto load = [&](int64_t z) -> c128 {   // own column at plane z
+        const c128* p = z < 0 ? a.halo_lo : (z >= a.n2 ? a.halo_hi : a.x + z * plane);
+        return p ? __ldg(p + c_off) : zero;
+    };
+    c128 prev = load(zs - 1), cur = load(zs), next = load(zs + 1);
+    for (int64_t z = zs; z < ze; z++) {
+        const c128 next2 = (z + 2 <= ze) ? load(z + 2) : zero;   // z + 2 == ze is the chunk's upper neighbour plane
+        const c128* pc = a.x + z * plane + c_off;
+        const c128 vym = ym ? __ldg(pc - a.n0) : zero;
+        const c128 vxm = xm ? __ldg(pc - 1) : zero;
+        const c128 vxp = xp ? __ldg(pc + 1) : zero;
+        const c128 vyp = yp ? __ldg(pc + a.n0) : zero;
+        c128 s = cadd(prev, vym);
+        s = cadd(s, vxm);
+        s = cadd(s, vxp);
+        s = cadd(s, vyp);
+        s = cadd(s, next);
+        if (a.dirac) {
+            c128 xr = cur;
+            if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
+            s = csub(xr, cmul(a.k, s));
+        }
+        st_stream(a.y + z * plane + c_off, s);
+        prev = cur; cur = next; next = next2;
+    }
+}
+
 HoppingOp::~HoppingOp() {
     for (int d = 0; d < 3; d++) dev_free(ctx, d_face[d]);
     dev_free(ctx, d_halo_lo); dev_free(ctx, d_halo_hi);
@@ -234,15 +283,25 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
         MGCR_TRY(dist_group_end(ctx));
     }
     if (n_local == 0) return MGCR_OK;
-    dim3 grid((unsigned)((a.n0 + HOP_TX - 1) / HOP_TX), (unsigned)((a.n1 + HOP_TY - 1) / HOP_TY), 1);
+    const bool l1_form = ctx->hopping_kernel == 1;
+    int hl_tx = 32;
+    static const int hl_tx_max = getenv("MGCR_HL_TX") ? std::min(atoi(getenv("MGCR_HL_TX")), (int)HL_THREADS) : (int)HL_THREADS;   // experiment knob
+    while (hl_tx < hl_tx_max && hl_tx * 2 <= a.n0) hl_tx *= 2;
+    const int tx = l1_form ? hl_tx : (int)HOP_TX, ty = l1_form ? HL_THREADS / hl_tx : (int)HOP_TY;
+    dim3 grid((unsigned)((a.n0 + tx - 1) / tx), (unsigned)((a.n1 + ty - 1) / ty), 1);
     int64_t tiles = (int64_t)grid.x * grid.y;
     int64_t target = (int64_t)ctx->num_sms * 16;
     int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(a.n2, (target + tiles - 1) / tiles));
     a.zc = (a.n2 + nchunks - 1) / nchunks;
     if (a.zc < 8 && a.n2 >= 8) a.zc = 8;
+    static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;   // experiment knob
+    if (zc_env > 0) a.zc = std::min<int64_t>(zc_env, a.n2);
     grid.z = (unsigned)((a.n2 + a.zc - 1) / a.zc);
     ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
-    KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.), (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
+    if (l1_form)
+        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.), (k_hopping_l1<<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
+    else
+        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.), (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -260,6 +319,9 @@ extern "C" int mgcr_hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims,
         ARG_CHECK(dims[d] >= 1, "mgcr_hopping_create: dims[%d] < 1", d);
         op->gdims[3 - ndim + d] = dims[d];
     }
+    // a 2-D lattice (ny, nx) is traversed as (ny, 1, nx): the kernels stream along their slowest index with the neighbours
+    // in that direction held in registers; the operator and the order of the neighbour sum (y-1, x-1, x+1, y+1) are the same
+    if (ndim == 2) { op->gdims[0] = dims[0]; op->gdims[1] = 1; op->gdims[2] = dims[1]; }
     int64_t zb = 0, ze = op->gdims[0];
     if (ctx->nranks > 1) {
         ARG_CHECK(ndim == 3, "mgcr_hopping_create: the distributed stencil is 3-D (slabs along dims[0])");
@@ -352,6 +414,47 @@ __global__ void __launch_bounds__(256) k_blockcsr_apply(int64_t nb, int ne, cons
     st_stream(y + t, value);
 }
 
+// The same for a compile-time block size (the multigrid levels: ne = n_eigen or 2 n_eigen): the column loop is unrolled
+// and two blocks are in flight per thread, i.e. 2*NE independent 128-bit matrix loads per thread instead of 4.
+template <int NE>
+__global__ void __launch_bounds__(256) k_blockcsr_apply_ne(int64_t nb, const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+                                                           const c128* __restrict__ bval, const c128* __restrict__ x, const c128* __restrict__ ghost,
+                                                           int64_t nb_local_cols, c128* __restrict__ y) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t R = t / NE;
+    const int r = (int)(t - R * NE);
+    if (R >= nb) return;
+    c128 value = cmake(0., 0.);
+    const int lb = __ldg(brow + R), le = __ldg(brow + R + 1);
+    int l = lb;
+    for (; l + 1 < le; l += 2) {
+        const int64_t bc0 = __ldg(bcol + l), bc1 = __ldg(bcol + l + 1);
+        const c128* xb0 = bc0 < nb_local_cols ? x + bc0 * NE : ghost + (bc0 - nb_local_cols) * NE;
+        const c128* xb1 = bc1 < nb_local_cols ? x + bc1 * NE : ghost + (bc1 - nb_local_cols) * NE;
+        const c128* m0 = bval + (int64_t)l * NE * NE + r;
+        c128 a0[NE], a1[NE], x0[NE], x1[NE];
+#pragma unroll
+        for (int c = 0; c < NE; c++) { a0[c] = ld_stream(m0 + c * NE); a1[c] = ld_stream(m0 + NE * NE + c * NE); }
+#pragma unroll
+        for (int c = 0; c < NE; c++) { x0[c] = __ldg(xb0 + c); x1[c] = __ldg(xb1 + c); }
+        c128 o0 = cmake(0., 0.), o1 = cmake(0., 0.);
+#pragma unroll
+        for (int c = 0; c < NE; c++) { o0 = cadd(o0, cmul(a0[c], x0[c])); o1 = cadd(o1, cmul(a1[c], x1[c])); }
+        value = cadd(value, o0);
+        value = cadd(value, o1);
+    }
+    if (l < le) {
+        const int64_t bc = __ldg(bcol + l);
+        const c128* xb = bc < nb_local_cols ? x + bc * NE : ghost + (bc - nb_local_cols) * NE;
+        const c128* m = bval + (int64_t)l * NE * NE + r;
+        c128 o = cmake(0., 0.);
+#pragma unroll
+        for (int c = 0; c < NE; c++) o = cadd(o, cmul(ld_stream(m + c * NE), __ldg(xb + c)));
+        value = cadd(value, o);
+    }
+    st_stream(y + t, value);
+}
+
 BlockCsrOp::~BlockCsrOp() {
     dev_free(ctx, d_brow); dev_free(ctx, d_bcol); dev_free(ctx, d_bval);
     halo_free(ctx, halo);
@@ -364,7 +467,15 @@ int BlockCsrOp::apply(const c128* x, c128* y) {
     if (nb == 0) return MGCR_OK;
     int64_t threads = nb * ne;
     int grid = (int)((threads + 255) / 256);
-    KLAUNCH(ctx, "blockcsr_apply", apply_bytes(), (k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(nb, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y)));
+    {
+        ProfScope ps_(ctx, "blockcsr_apply", apply_bytes());
+        switch (ne) {
+            case 2: k_blockcsr_apply_ne<2><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y); break;
+            case 4: k_blockcsr_apply_ne<4><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y); break;
+            case 8: k_blockcsr_apply_ne<8><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y); break;
+            default: k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(nb, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y);
+        }
+    }
     CHECK_LAUNCH();
     return MGCR_OK;
 }

@@ -66,6 +66,9 @@ class Context:
         check(capi.load().mgcr_nccl_unique_id(buf))
         return bytes(buf.raw)
 
+    def set_option(self, key, value):
+        check(self.lib.mgcr_ctx_set_option(self.h, key.encode(), int(value)))
+
     def set_slab_align(self, align):
         """slab boundaries of distributed operators created afterwards are multiples of `align` planes"""
         check(self.lib.mgcr_ctx_set_slab_align(self.h, int(align)))

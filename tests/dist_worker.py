@@ -14,8 +14,6 @@ sys.path.insert(0, ROOT)
 def main(rank, world, port, gather_dofs):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    if gather_dofs is not None:
-        os.environ["MGCR_GATHER_DOFS"] = str(gather_dofs)
     import torch
     import torch.distributed as dist
     from mgpreconditionedgcr_b200 import host
@@ -27,6 +25,8 @@ def main(rank, world, port, gather_dofs):
     dist.broadcast_object_list(ids, src=0)
     ctx.init_dist(rank, world, ids[0])
     ctx.set_slab_align(16)
+    if gather_dofs is not None:
+        ctx.set_option("gather_dofs", gather_dofs)
     single = host.Context(rank)          # the same problem on one GPU, for comparison
 
     dims = [32 * world, 16, 24]

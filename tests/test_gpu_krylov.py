@@ -220,8 +220,17 @@ MODES = {"r5": (0, 5, 4000, 1e-13), "r2": (0, 2, 4000, 1e-13), "t5": (5, 0, 4000
          "r10": (0, 10, 4000, 1e-10), "full100": (0, 0, 100, 1e-10), "smooth0": (0, 10, 0, 1e-8)}
 
 
+@pytest.fixture(params=["persistent", "host_driven"])
+def solver_path(request, ctx):
+    """small operators are solved by ONE persistent cooperative kernel (csrc/gcr_small.cu) by default; with the option at 0
+    the same solve runs as the host-driven loop of fused kernels (csrc/gcr.cu) that large operators use"""
+    ctx.set_option("small_gcr_rows", (1 << 19) if request.param == "persistent" else 0)
+    yield request.param
+    ctx.set_option("small_gcr_rows", 1 << 19)
+
+
 @pytest.mark.parametrize("mode", list(MODES))
-def test_gcr_history_against_reference_golden(ctx, host, orc, golden, c1, mode):
+def test_gcr_history_against_reference_golden(ctx, host, orc, golden, c1, mode, solver_path):
     trunc, restart, max_iter, tol = MODES[mode]
     g = golden.gcr
     A = host.DiracOp(ctx, host.Sparse(ctx, c1["n"], c1["n"], c1["row"], c1["col"], c1["val"]), c1["k"])
@@ -258,7 +267,7 @@ def test_gcr_aliased_solve(ctx, host, golden, c1):
 
 @pytest.mark.parametrize("tag,dims", [("lap2d_48", [48, 48]), ("lap3d_12", [12, 12, 12])])
 @pytest.mark.parametrize("form", ["csr", "stencil"])
-def test_gcr_synthetic_against_reference_golden(ctx, host, orc, golden, tag, dims, form):
+def test_gcr_synthetic_against_reference_golden(ctx, host, orc, golden, tag, dims, form, solver_path):
     g = golden.gcr
     n = int(np.prod(dims))
     kk = 1.0 / (2 * len(dims) + 0.01)
@@ -282,7 +291,7 @@ def test_gcr_synthetic_against_reference_golden(ctx, host, orc, golden, tag, dim
 
 
 @pytest.mark.parametrize("trunc,restart,max_iter", [(0, 4, 60), (3, 0, 60), (0, 0, 25), (0, 20, 70), (18, 0, 50)])
-def test_gcr_random_operator_against_oracle(ctx, host, orc, trunc, restart, max_iter):
+def test_gcr_random_operator_against_oracle(ctx, host, orc, trunc, restart, max_iter, solver_path):
     rng = np.random.default_rng(7)
     n = 300
     row, col, val = random_csr(rng, n, 8)
@@ -373,3 +382,9 @@ def test_full_size_properties_config2(ctx, host):
     assert np.array_equal(h1, h2)
     r = a - A(x1)
     assert abs(r.norm() / a.norm() - h1[-1]) < 1e-10 * h1[-1] + 1e-14
+    # the batched inner products have two implementations on long vectors (TMA-staged ring / register-staged): same history
+    ctx.set_option("dot_tma", 0)
+    x3 = ctx.field(n).set_zero()
+    it3, h3 = host.GCR(ctx, A, p).solve(a, x3)
+    ctx.set_option("dot_tma", 1)
+    assert it3 == 30 and np.max(np.abs(h3 - h1) / h1) < 1e-11
