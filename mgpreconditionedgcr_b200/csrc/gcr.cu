@@ -159,10 +159,11 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     static const int grid_per_sm = getenv("MGCR_GRID_PER_SM") ? atoi(getenv("MGCR_GRID_PER_SM")) : 4;   // experiment knob
     const int grid = stream_grid(ctx, n, grid_per_sm, 2);
     // r = rhs ; p = z = R(r) or r ; Ap = A p                                                   (GCR.h:189-192)
-    if (n) GCUDA(cudaMemcpyAsync(r, rhs, sizeof(c128) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (right) GTRY(right->apply(r, ps)); else if (n) GCUDA(cudaMemcpyAsync(ps, r, sizeof(c128) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-    GTRY(A->apply(ps, Aps));
-    KLAUNCH(ctx, "gcr_init", 32. * n, (k_gcr_init<<<grid, RED_THREADS, 0, ctx->stream>>>(n, r, Aps, std_conj, ctx->d_partials, ctx->d_ticket, scal)));
+    // the operator / preconditioner read rhs directly; r (and p when there is no preconditioner) are written by the init
+    // kernel in the pass that forms the first inner products
+    if (right) GTRY(right->apply(rhs, ps));
+    GTRY(A->apply(right ? ps : rhs, Aps));
+    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (k_gcr_init<<<grid, RED_THREADS, 0, ctx->stream>>>(n, rhs, Aps, std_conj, r, right ? nullptr : ps, ctx->d_partials, ctx->d_ticket, scal)));
     GCUDA(cudaGetLastError());
     if (dist) GTRY(dist_allreduce_sum(ctx, scal, 5));
     // Short solves nobody watches (the smoothers of the multigrid cycle): no read-back at all, the kernels carry the

@@ -213,8 +213,11 @@ static int launch_small(mgcr_ctx* ctx, const Rows& rows, SmallGcrArgs& a, int* g
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, k_gcr_small<Rows>, SG_THREADS, 0));
         if (max_blocks_per_sm < 1) { mgcr_set_error("small GCR kernel does not fit on an SM"); return MGCR_ERR_CUDA; }
     }
-    int64_t want = (a.n + SG_THREADS - 1) / SG_THREADS;
-    int64_t cap = (int64_t)ctx->num_sms * std::min(max_blocks_per_sm, 2);
+    int64_t want = 0;
+    static const int per_sm = getenv("MGCR_SMALL_GRID_PER_SM") ? atoi(getenv("MGCR_SMALL_GRID_PER_SM")) : 2;   // experiment knob
+    int64_t cap = (int64_t)ctx->num_sms * std::min(max_blocks_per_sm, per_sm);
+    static const int min_rows = getenv("MGCR_SMALL_ROWS_PER_CTA") ? atoi(getenv("MGCR_SMALL_ROWS_PER_CTA")) : SG_THREADS;
+    want = (a.n + min_rows - 1) / min_rows;
     int grid = (int)std::max<int64_t>(1, std::min(want, cap));
     *grid_out = grid;
     return MGCR_OK;

@@ -85,11 +85,15 @@ __device__ __forceinline__ bool gcr_converged(const double* guard, double tol2) 
 }
 
 // init: <r,Ap>, <Ap,Ap>, ||rhs||^2 (r = rhs at start) in one pass -> S_ANUM(2), S_ADEN, S_BB, S_RR (= ||rhs||^2)
+// The same pass also makes the solver's working copies r = rhs and (without a preconditioner) p = r  (GCR.h:189-190).
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, const c128* __restrict__ r, const c128* __restrict__ Ap,
-                                                          int std_conj, double* partials, unsigned int* ticket, double* out5) {
+                                                          int std_conj, c128* __restrict__ r_out, c128* __restrict__ p_out,
+                                                          double* partials, unsigned int* ticket, double* out5) {
     double v[5] = {0., 0., 0., 0., 0.};
     GRID_STRIDE(i, n) {
         c128 rv = ld_stream(r + i), av = ld_stream(Ap + i);
+        if (r_out) st_stream(r_out + i, rv);
+        if (p_out) st_stream(p_out + i, rv);
         c128 t = cmulc(rv, av);
         v[0] += t.x; v[1] += t.y;
         v[2] += av.x * av.x + av.y * av.y;
@@ -110,7 +114,19 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n,
     // ||Aps[cur]||^2 never changes while the slot lives: cache it for the beta denominators (GCR.h:258 recomputes it)
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[bden_slot] = aden;
     double v[1] = {0.};
-    GRID_STRIDE(i, n) {
+    // two elements per trip: 8 independent 128-bit loads in flight per thread
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i + T < n; i += 2 * T) {
+        const c128 p0 = ld_stream(p + i), a0 = ld_stream(Ap + i), p1 = ld_stream(p + i + T), a1 = ld_stream(Ap + i + T);
+        c128 x0 = ld_plain(x + i), r0 = ld_plain(r + i), x1 = ld_plain(x + i + T), r1 = ld_plain(r + i + T);
+        x0 = cadd(x0, cmul(alpha, p0)); r0 = csub(r0, cmul(alpha, a0));
+        x1 = cadd(x1, cmul(alpha, p1)); r1 = csub(r1, cmul(alpha, a1));
+        st_stream(x + i, x0); st_stream(r + i, r0); st_stream(x + i + T, x1); st_stream(r + i + T, r1);
+        v[0] += r0.x * r0.x + r0.y * r0.y;
+        v[0] += r1.x * r1.x + r1.y * r1.y;
+    }
+    for (; i < n; i += T) {
         c128 pv = ld_stream(p + i), av = ld_stream(Ap + i);
         c128 xv = ld_plain(x + i), rv = ld_plain(r + i);
         xv = cadd(xv, cmul(alpha, pv));

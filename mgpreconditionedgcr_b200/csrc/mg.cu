@@ -275,9 +275,47 @@ static __global__ void __launch_bounds__(256) k_restrict(LevelGeom g, const int6
     }
 }
 
+// The same for small aggregates (up to 32*QPL dofs, the synthetic configurations: 4^3 sites x 1..4 dofs): one WARP per
+// aggregate, its slice of x held in registers, no shared memory and no block barrier; 8 aggregates per CTA keep ~10
+// independent 128-bit loads per lane in flight.  The per-lane accumulation order is that of k_restrict (q = lane, lane+32,
+// ..., then the shuffle tree), so both kernels give bit-identical results.
+template <int QPL>
+static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, const int64_t* __restrict__ block_map, const c128* __restrict__ P,
+                                                              const c128* __restrict__ xf, c128* __restrict__ xc) {
+    const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (b >= g.nb) return;
+    const int lane = threadIdx.x & 31;
+    c128 xs[QPL];
+#pragma unroll
+    for (int j = 0; j < QPL; j++) {
+        const int64_t q = lane + 32 * j;
+        if (q < g.bl) {
+            const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
+            xs[j] = __ldg(xf + site * g.dof + q % g.dof);
+        } else {
+            xs[j] = cmake(0., 0.);
+        }
+    }
+#pragma unroll 4
+    for (int e = 0; e < g.ne; e++) {
+        const c128* pv = P + (b * g.ne + e) * g.bl;
+        double sr = 0., si = 0.;
+#pragma unroll
+        for (int j = 0; j < QPL; j++) {
+            const int64_t q = lane + 32 * j;
+            if (q < g.bl) {
+                c128 t = cmulc(ld_stream(pv + q), xs[j]);
+                sr += t.x; si += t.y;
+            }
+        }
+        sr = warp_sum(sr); si = warp_sum(si);
+        if (lane == 0) xc[b * g.ne + e] = cmake(sr, si);
+    }
+}
+
 // x[map(b,q)] = sum_e xc[b*ne+e] P[b][e][q]   (MG.h:347-364): one thread per fine dof, e in the reference's order
 static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, int64_t total, const int64_t* __restrict__ block_map,
-                                                        const c128* __restrict__ P, const c128* __restrict__ xc, c128* __restrict__ xf) {
+                                                        const c128* __restrict__ P, const c128* __restrict__ xc, c128* __restrict__ xf, int add) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int64_t b = t / g.bl, q = t - b * g.bl;
@@ -287,23 +325,33 @@ static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, int64_t tot
 #pragma unroll 4
     for (int e = 0; e < g.ne; e++) acc = cadd(acc, cmul(__ldg(a + e), ld_stream(pv + (int64_t)e * g.bl)));
     const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
-    xf[site * g.dof + q % g.dof] = acc;
+    c128* dst = xf + site * g.dof + q % g.dof;
+    *dst = add ? cadd(*dst, acc) : acc;   // add: the cycle's x += P xc
 }
 
 static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
     const LevelGeom& g = L.g;
     if (g.nb == 0) return MGCR_OK;
-    int threads = 32 * (int)std::min<int64_t>(8, std::max<int64_t>(1, g.ne));
-    size_t smem = sizeof(c128) * (size_t)g.bl;
-    KLAUNCH(ctx, "mg_restrict", 16. * L.n * (1 + g.ne) + 16. * L.nc, (k_restrict<<<(unsigned)g.nb, threads, smem, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc)));
+    const double bytes = 16. * L.n * (1 + g.ne) + 16. * L.nc;
+    if (g.bl <= 256) {
+        const unsigned grid = (unsigned)((g.nb * 32 + 255) / 256);
+        ProfScope ps_(ctx, "mg_restrict", bytes);
+        if (g.bl <= 64) k_restrict_warp<2><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
+        else if (g.bl <= 128) k_restrict_warp<4><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
+        else k_restrict_warp<8><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
+    } else {
+        int threads = 32 * (int)std::min<int64_t>(8, std::max<int64_t>(1, g.ne));
+        size_t smem = sizeof(c128) * (size_t)g.bl;
+        KLAUNCH(ctx, "mg_restrict", bytes, (k_restrict<<<(unsigned)g.nb, threads, smem, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc)));
+    }
     CHECK_LAUNCH();
     return MGCR_OK;
 }
 
-static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf) {
+static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf, bool add = false) {
     const LevelGeom& g = L.g;
     if (L.n == 0) return MGCR_OK;
-    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne) + 16. * L.nc, (k_prolong<<<(unsigned)((L.n + 255) / 256), 256, 0, ctx->stream>>>(g, L.n, L.d_block_map, L.d_P, xc, xf)));
+    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc, (k_prolong<<<(unsigned)((L.n + 255) / 256), 256, 0, ctx->stream>>>(g, L.n, L.d_block_map, L.d_P, xc, xf, add ? 1 : 0)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -330,8 +378,7 @@ static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x) {
     ARG_CHECK(b != x, "MG cycle: input and output alias");
     CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(c128) * n, ctx->stream));
     MGCR_TRY(gcr_solve(ctx, L.A, &mg->smooth, nullptr, b, x, nullptr, 0, nullptr));
-    MGCR_TRY(L.A->apply(x, L.d_t));
-    MGCR_TRY(vec_axpy(ctx, n, cmake(-1., 0.), L.d_t, b, L.d_r));          // r = b - A x
+    MGCR_TRY(L.A->apply_residual(x, b, L.d_r));                            // r = b - A x, one kernel
     MGCR_TRY(mg_restrict(ctx, L, L.d_r, L.d_rc));
     const c128* xc = L.d_xc;
     if (!L.gather) {
@@ -358,10 +405,8 @@ static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x) {
         MGCR_TRY(gcr_solve(ctx, L.Ac_full, &mg->coarse, L.deeper, L.d_rc_full, L.d_xc_full, nullptr, 0, nullptr));
         xc = L.d_xc_full + L.nc_offset;
     }
-    MGCR_TRY(mg_prolong(ctx, L, xc, L.d_t));
-    MGCR_TRY(vec_axpy(ctx, n, cmake(1., 0.), L.d_t, x, x));               // x += P xc
-    MGCR_TRY(L.A->apply(x, L.d_t));
-    MGCR_TRY(vec_axpy(ctx, n, cmake(-1., 0.), L.d_t, b, L.d_r));
+    MGCR_TRY(mg_prolong(ctx, L, xc, x, true));                             // x += P xc, one kernel
+    MGCR_TRY(L.A->apply_residual(x, b, L.d_r));
     MGCR_TRY(gcr_solve(ctx, L.A, &mg->smooth, nullptr, L.d_r, x, nullptr, 0, nullptr));
     return MGCR_OK;
 }
@@ -639,7 +684,6 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
     }
     // cycle work vectors
     MGCR_TRY(dev_alloc_t(ctx, (size_t)n, &L.d_r));
-    MGCR_TRY(dev_alloc_t(ctx, (size_t)n, &L.d_t));
     MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nc, &L.d_rc));
     MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nc, &L.d_xc));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -648,7 +692,7 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
 
 static void level_free(mgcr_ctx* ctx, MgLevel& L) {
     dev_free(ctx, L.d_block_map); dev_free(ctx, L.d_site_block); dev_free(ctx, L.d_site_off); dev_free(ctx, L.d_P);
-    dev_free(ctx, L.d_bslot); dev_free(ctx, L.d_r); dev_free(ctx, L.d_t); dev_free(ctx, L.d_rc); dev_free(ctx, L.d_xc);
+    dev_free(ctx, L.d_bslot); dev_free(ctx, L.d_r); dev_free(ctx, L.d_rc); dev_free(ctx, L.d_xc);
     dev_free(ctx, L.d_Pg); dev_free(ctx, L.d_rc_full); dev_free(ctx, L.d_xc_full); dev_free(ctx, L.d_pad);
     delete L.deeper; L.deeper = nullptr;
     delete L.Ac; L.Ac = nullptr;

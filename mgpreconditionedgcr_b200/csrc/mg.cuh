@@ -30,7 +30,7 @@ struct MgLevel {
     c128* d_P = nullptr;              // compact prolongator [nb][ne][bl]: every fine dof lies in exactly one aggregate
     int8_t* d_bslot = nullptr;        // [nb*K] reference slot (0 self, 2d+1 from the block below in d, 2d+2 from above)
     BlockCsrOp* Ac = nullptr;         // Galerkin coarse operator, owned
-    c128 *d_r = nullptr, *d_t = nullptr, *d_rc = nullptr, *d_xc = nullptr;   // cycle work vectors
+    c128 *d_r = nullptr, *d_rc = nullptr, *d_xc = nullptr;   // cycle work vectors
     mgcr_op* deeper = nullptr;        // MG-as-operator of level l+1 (K-cycle preconditioner of the coarse solve)
     // distributed levels
     c128* d_Pg = nullptr;             // prolongator rows of the ghost sites [ghost site][dof][ne]

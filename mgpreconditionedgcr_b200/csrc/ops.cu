@@ -12,7 +12,8 @@
 template <bool DIRAC>
 __global__ void __launch_bounds__(256) k_sell_spmv(int64_t nrow, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ col,
                                                    const c128* __restrict__ val, const c128* __restrict__ x, const c128* __restrict__ ghost,
-                                                   int64_t n_local, c128 k, const double* __restrict__ diag, c128* __restrict__ y) {
+                                                   int64_t n_local, c128 k, const double* __restrict__ diag, const c128* __restrict__ bsub,
+                                                   c128* __restrict__ y) {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t slice = row >> 5;
     const int lane = threadIdx.x & 31;
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) k_sell_spmv(int64_t nrow, const int64_t* 
             if (diag) { double d = __ldg(diag + row); xr = cmake(d * xr.x, d * xr.y); }
             sum = csub(xr, cmul(k, sum));
         }
+        if (bsub) sum = csub(__ldg(bsub + row), sum);   // residual b - A x
         st_stream(y + row, sum);
     }
 }
@@ -44,7 +46,7 @@ SellOp::~SellOp() {
     halo_free(ctx, halo);
 }
 
-static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, const double* diag) {
+static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, const double* diag, const c128* bsub = nullptr) {
     mgcr_ctx* ctx = op->ctx;
     ARG_CHECK(x != y, "operator apply: input and output alias");
     const c128* ghost = nullptr;
@@ -52,14 +54,14 @@ static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, c
     if (op->nrow == 0) return MGCR_OK;
     int grid = (int)((op->nslices * 32 + 255) / 256);
     if (dirac)
-        KLAUNCH(ctx, "sell_dirac", op->apply_bytes(), (k_sell_spmv<true><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, y)));
+        KLAUNCH(ctx, "sell_dirac", op->apply_bytes(), (k_sell_spmv<true><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, bsub, y)));
     else
-        KLAUNCH(ctx, "sell_spmv", op->apply_bytes(), (k_sell_spmv<false><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, y)));
+        KLAUNCH(ctx, "sell_spmv", op->apply_bytes(), (k_sell_spmv<false><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, bsub, y)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
 int SellOp::apply(const c128* x, c128* y) { return sell_launch(this, x, y, false, cmake(0., 0.), nullptr); }
-int SellOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag) { return sell_launch(this, x, y, true, k, diag); }
+int SellOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag, const c128* bsub) { return sell_launch(this, x, y, true, k, diag, bsub); }
 
 // host CSR (int64) -> device sliced-ELL.  `ncol_local`: columns < ncol_local address x, the rest the ghost buffer.
 int sell_build(mgcr_ctx* ctx, int64_t nrow, int64_t ncol_addressable, const int64_t* row, const int64_t* col, const mgcr_c128* val, SellOp* op) {
@@ -143,6 +145,7 @@ struct HopArgs {
     const c128* x; c128* y;
     const c128* halo_lo; const c128* halo_hi;   // plane below local z=0 / above z=n2-1 (NULL = Dirichlet)
     int dirac; c128 k; const double* diag;
+    const c128* bsub;        // non-NULL: store b - (A x) (the multigrid residual)
 };
 
 __global__ void __launch_bounds__(HOP_TX* HOP_TY) k_hopping(HopArgs a) {
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(HOP_TX* HOP_TY) k_hopping(HopArgs a) {
                 if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
                 s = csub(xr, cmul(a.k, s));
             }
+            if (a.bsub) s = csub(__ldg(a.bsub + z * plane + c_off), s);
             st_stream(a.y + z * plane + c_off, s);
         }
         prev = cur; cur = next; hx = nhx; hy = nhy;
@@ -249,6 +253,7 @@ __global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx)
             if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
             s = csub(xr, cmul(a.k, s));
         }
+        if (a.bsub) s = csub(__ldg(a.bsub + z * plane + c_off), s);
         st_stream(a.y + z * plane + c_off, s);
         prev = cur; cur = next; next = next2;
     }
@@ -259,9 +264,10 @@ HoppingOp::~HoppingOp() {
     dev_free(ctx, d_halo_lo); dev_free(ctx, d_halo_hi);
 }
 
-int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag) {
+int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag, const c128* bsub) {
     ARG_CHECK(x != y, "operator apply: input and output alias");
     HopArgs a;
+    a.bsub = bsub;
     a.n2 = n2_local; a.n1 = gdims[1]; a.n0 = gdims[2];
     a.x = x; a.y = y; a.dirac = dirac; a.k = k; a.diag = diag;
     a.halo_lo = nullptr; a.halo_hi = nullptr;
@@ -299,14 +305,14 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
     grid.z = (unsigned)((a.n2 + a.zc - 1) / a.zc);
     ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
     if (l1_form)
-        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.), (k_hopping_l1<<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
+        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.) + (bsub ? 16. * n_local : 0.), (k_hopping_l1<<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
     else
-        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.), (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
+        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.) + (bsub ? 16. * n_local : 0.), (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
 int HoppingOp::apply(const c128* x, c128* y) { return run(x, y, 0, cmake(0., 0.), nullptr); }
-int HoppingOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag) { return run(x, y, 1, k, diag); }
+int HoppingOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag, const c128* bsub) { return run(x, y, 1, k, diag, bsub); }
 
 extern "C" int mgcr_hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims, const double* const* h_face, mgcr_op** out) {
     ARG_CHECK(ctx && dims && out, "mgcr_hopping_create: NULL argument");
@@ -364,6 +370,19 @@ int DiracOp::apply(const c128* x, c128* y) {
     return MGCR_OK;
 }
 
+int DiracOp::apply_residual(const c128* x, const c128* b, c128* r) {
+    ARG_CHECK(b != r, "residual: right-hand side and output alias");
+    if (D->kind == OP_SELL) return static_cast<SellOp*>(D)->apply_dirac(x, r, k, d_diag, b);
+    if (D->kind == OP_HOPPING) return static_cast<HoppingOp*>(D)->apply_dirac(x, r, k, d_diag, b);
+    return mgcr_op::apply_residual(x, b, r);
+}
+
+int vec_axpy(mgcr_ctx* ctx, int64_t n, c128 s, const c128* b, const c128* a, c128* out);
+int mgcr_op::apply_residual(const c128* x, const c128* b, c128* r) {
+    MGCR_TRY(apply(x, r));
+    return vec_axpy(ctx, n_local, cmake(-1., 0.), r, b, r);   // r = b + (-1) r, exactly b - r
+}
+
 extern "C" int mgcr_dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* h_diag, mgcr_op** out) {
     ARG_CHECK(ctx && D && out, "mgcr_dirac_create: NULL argument");
     *out = nullptr;
@@ -395,7 +414,7 @@ extern "C" int mgcr_dirac_set_k(mgcr_op* op, double k_re, double k_im) {
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_blockcsr_apply(int64_t nb, int ne, const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
                                                         const c128* __restrict__ bval, const c128* __restrict__ x, const c128* __restrict__ ghost,
-                                                        int64_t nb_local_cols, c128* __restrict__ y) {
+                                                        int64_t nb_local_cols, const c128* __restrict__ bsub, c128* __restrict__ y) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t R = t / ne;
     const int r = (int)(t - R * ne);
@@ -411,6 +430,7 @@ __global__ void __launch_bounds__(256) k_blockcsr_apply(int64_t nb, int ne, cons
         for (int c = 0; c < ne; c++) o = cadd(o, cmul(ld_stream(m + (int64_t)c * ne), __ldg(xb + c)));
         value = cadd(value, o);
     }
+    if (bsub) value = csub(__ldg(bsub + t), value);
     st_stream(y + t, value);
 }
 
@@ -419,7 +439,7 @@ __global__ void __launch_bounds__(256) k_blockcsr_apply(int64_t nb, int ne, cons
 template <int NE>
 __global__ void __launch_bounds__(256) k_blockcsr_apply_ne(int64_t nb, const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
                                                            const c128* __restrict__ bval, const c128* __restrict__ x, const c128* __restrict__ ghost,
-                                                           int64_t nb_local_cols, c128* __restrict__ y) {
+                                                           int64_t nb_local_cols, const c128* __restrict__ bsub, c128* __restrict__ y) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t R = t / NE;
     const int r = (int)(t - R * NE);
@@ -452,6 +472,7 @@ __global__ void __launch_bounds__(256) k_blockcsr_apply_ne(int64_t nb, const int
         for (int c = 0; c < NE; c++) o = cadd(o, cmul(ld_stream(m + c * NE), __ldg(xb + c)));
         value = cadd(value, o);
     }
+    if (bsub) value = csub(__ldg(bsub + t), value);
     st_stream(y + t, value);
 }
 
@@ -460,7 +481,13 @@ BlockCsrOp::~BlockCsrOp() {
     halo_free(ctx, halo);
 }
 
-int BlockCsrOp::apply(const c128* x, c128* y) {
+int BlockCsrOp::apply(const c128* x, c128* y) { return run(x, y, nullptr); }
+int BlockCsrOp::apply_residual(const c128* x, const c128* b, c128* r) {
+    ARG_CHECK(b != r, "residual: right-hand side and output alias");
+    return run(x, r, b);
+}
+
+int BlockCsrOp::run(const c128* x, c128* y, const c128* bsub) {
     ARG_CHECK(x != y, "operator apply: input and output alias");
     const c128* ghost = nullptr;
     if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x)); ghost = halo->d_ghost; }
@@ -468,12 +495,12 @@ int BlockCsrOp::apply(const c128* x, c128* y) {
     int64_t threads = nb * ne;
     int grid = (int)((threads + 255) / 256);
     {
-        ProfScope ps_(ctx, "blockcsr_apply", apply_bytes());
+        ProfScope ps_(ctx, "blockcsr_apply", apply_bytes() + (bsub ? 16. * n_local : 0.));
         switch (ne) {
-            case 2: k_blockcsr_apply_ne<2><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y); break;
-            case 4: k_blockcsr_apply_ne<4><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y); break;
-            case 8: k_blockcsr_apply_ne<8><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y); break;
-            default: k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(nb, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, y);
+            case 2: k_blockcsr_apply_ne<2><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y); break;
+            case 4: k_blockcsr_apply_ne<4><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y); break;
+            case 8: k_blockcsr_apply_ne<8><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y); break;
+            default: k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(nb, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y);
         }
     }
     CHECK_LAUNCH();

@@ -27,6 +27,8 @@ struct mgcr_op {
     bool distributed = false;   // rows are this rank's slab of a global operator: inner products over its vectors are all-reduced
     virtual ~mgcr_op() {}
     virtual int apply(const c128* x, c128* y) = 0;
+    // r = b - A x (the residual of the multigrid cycle); operators with their own kernels fold `b -` into the apply's store
+    virtual int apply_residual(const c128* x, const c128* b, c128* r);
     virtual double apply_bytes() const { return 0.; }
 };
 
@@ -41,7 +43,7 @@ struct SellOp : mgcr_op {
     HaloPlan* halo = nullptr;
     ~SellOp() override;
     int apply(const c128* x, c128* y) override;
-    int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag);
+    int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag, const c128* bsub = nullptr);
     double apply_bytes() const override { return (double)nnz_padded * 20. + (double)(nslices + 1) * 8. + 16. * (double)ncol + 16. * (double)nrow; }
 };
 
@@ -54,8 +56,8 @@ struct HoppingOp : mgcr_op {
     c128* d_halo_lo = nullptr; c128* d_halo_hi = nullptr;   // neighbour planes (distributed)
     ~HoppingOp() override;
     int apply(const c128* x, c128* y) override;
-    int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag);
-    int run(const c128* x, c128* y, int dirac, c128 k, const double* d_diag);
+    int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag, const c128* bsub = nullptr);
+    int run(const c128* x, c128* y, int dirac, c128 k, const double* d_diag, const c128* bsub = nullptr);
     double apply_bytes() const override { return 32. * (double)n_local; }
 };
 
@@ -65,6 +67,7 @@ struct DiracOp : mgcr_op {
     double* d_diag = nullptr;
     ~DiracOp() override;
     int apply(const c128* x, c128* y) override;
+    int apply_residual(const c128* x, const c128* b, c128* r) override;
     double apply_bytes() const override { return D->apply_bytes() + (d_diag ? 8. * (double)n_local : 0.); }
 };
 
@@ -81,6 +84,8 @@ struct BlockCsrOp : mgcr_op {
     HaloPlan* halo = nullptr;
     ~BlockCsrOp() override;
     int apply(const c128* x, c128* y) override;
+    int apply_residual(const c128* x, const c128* b, c128* r) override;
+    int run(const c128* x, c128* y, const c128* bsub);
     double apply_bytes() const override { return (double)nnzb * (16. * ne * ne + 4.) + 32. * (double)nb * ne; }
 };
 
