@@ -379,7 +379,7 @@ def main():
     peak, peak_src = peaks()
     host = {kname: prof.pop(kname) for kname in list(prof) if kname.startswith("host_")}
     total_ms = sum(v["ms"] for v in prof.values())
-    dom = max(prof, key=lambda kname: prof[kname]["ms"])
+    dom = max((kname for kname in prof if not kname.startswith("nccl_")), key=lambda kname: prof[kname]["ms"])   # NCCL time is reported, not rooflined
     classes = {kname: {"ms_per_launch": v["ms"] / max(v["calls"], 1), "launches": v["calls"], "share": v["ms"] / total_ms,
                        "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None} for kname, v in prof.items()}
     d = prof[dom]

@@ -103,6 +103,9 @@ struct mgcr_ctx {
     int dot_tma = 1;                              // TMA-staged batched inner products for long vectors
     int hopping_kernel = 1;                       // matrix-free stencil: 1 = register-marching / L1 form, 0 = shared-memory tile form
     void* nccl_comm = nullptr;
+    void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
+    int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,
+                                            // the exchanges are latency- and skew-bound; profiles/r01_halo_overlap_n8.txt)
     // profiling
     bool profile = false;
     std::map<std::string, ProfEntry> prof;
@@ -165,6 +168,10 @@ void dist_destroy(mgcr_ctx* ctx);
 int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
 int dist_sendrecv(mgcr_ctx* ctx, const void* d_send, size_t send_bytes, int send_peer, void* d_recv, size_t recv_bytes,
                   int recv_peer, cudaStream_t stream);
+bool dist_halo_overlap(mgcr_ctx* ctx);
+int dist_halo_begin(mgcr_ctx* ctx, cudaStream_t* stream_out);
+int dist_halo_end(mgcr_ctx* ctx);
+int dist_halo_wait(mgcr_ctx* ctx);
 int dist_group_begin(mgcr_ctx* ctx);
 int dist_group_end(mgcr_ctx* ctx);
 int dist_send(mgcr_ctx* ctx, const void* d_send, size_t bytes, int peer, cudaStream_t stream);

@@ -19,6 +19,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;   // optional (NCCL >= 2.18)
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -52,6 +53,7 @@ static int nccl_load() {
     BIND(GroupEnd, "ncclGroupEnd");
     BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
+    *(void**)(&g_nccl.CommSplit) = dlsym(lib, "ncclCommSplit");
     g_nccl.lib = lib;
     return MGCR_OK;
 }
@@ -86,6 +88,12 @@ extern "C" int mgcr_ctx_init_dist(mgcr_ctx* ctx, int rank, int nranks, const voi
     ncclComm_t comm;
     NCCL_TRY(g_nccl.CommInitRank(&comm, nranks, id, rank));
     ctx->nccl_comm = comm; ctx->rank = rank; ctx->nranks = nranks;
+    // a second communicator for the halo exchanges: they run on the auxiliary stream while interior rows are computed, and
+    // NCCL orders all operations of ONE communicator, whatever stream they are on
+    if (g_nccl.CommSplit) {
+        ncclComm_t halo = nullptr;
+        if (g_nccl.CommSplit(comm, 0, rank, &halo, nullptr) == ncclSuccess_) ctx->nccl_comm_halo = halo;
+    }
     return MGCR_OK;
 }
 
@@ -96,8 +104,9 @@ extern "C" int mgcr_ctx_set_slab_align(mgcr_ctx* ctx, int64_t align) {
 }
 
 void dist_destroy(mgcr_ctx* ctx) {
+    if (ctx->nccl_comm_halo && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm_halo);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
-    ctx->nccl_comm = nullptr;
+    ctx->nccl_comm = nullptr; ctx->nccl_comm_halo = nullptr;
 }
 
 extern "C" int mgcr_ctx_rank(mgcr_ctx* ctx, int* rank, int* nranks) {
@@ -109,7 +118,7 @@ extern "C" int mgcr_ctx_rank(mgcr_ctx* ctx, int* rank, int* nranks) {
 
 int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
     if (ctx->nranks == 1) return MGCR_OK;
-    ctx->launches++;
+    ProfScope ps_(ctx, "nccl_allreduce", 8. * n);
     NCCL_TRY(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat64_, ncclSum_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return MGCR_OK;
 }
@@ -119,23 +128,57 @@ extern "C" int mgcr_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
     return dist_allreduce_sum(ctx, d_buf, n);
 }
 
+// halo exchanges overlap with interior compute when the second communicator exists and the option is on
+bool dist_halo_overlap(mgcr_ctx* ctx) { return ctx->nranks > 1 && ctx->nccl_comm_halo != nullptr && ctx->halo_overlap != 0; }
+
+// Bracket of one halo exchange.  Overlapped: the sends / receives go to the auxiliary stream (after everything enqueued so
+// far on the main stream, which produced the data being sent); the caller launches its interior work on the main stream
+// and then calls dist_halo_wait() before the work that reads the ghosts.
+int dist_halo_begin(mgcr_ctx* ctx, cudaStream_t* stream_out) {
+    *stream_out = ctx->stream;
+    if (ctx->nranks == 1) return MGCR_OK;
+    ctx->launches++;
+    if (dist_halo_overlap(ctx)) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_a, ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_a, 0));
+        *stream_out = ctx->aux_stream;
+    } else if (ctx->profile) {
+        prof_begin(ctx, "nccl_halo", 0.);
+    }
+    NCCL_TRY(g_nccl.GroupStart());
+    return MGCR_OK;
+}
+int dist_halo_end(mgcr_ctx* ctx) {
+    if (ctx->nranks == 1) return MGCR_OK;
+    NCCL_TRY(g_nccl.GroupEnd());
+    if (dist_halo_overlap(ctx)) CUDA_TRY(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
+    else if (ctx->profile) prof_end(ctx);
+    return MGCR_OK;
+}
+int dist_halo_wait(mgcr_ctx* ctx) {
+    if (dist_halo_overlap(ctx)) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    return MGCR_OK;
+}
 int dist_group_begin(mgcr_ctx* ctx) {
     if (ctx->nranks == 1) return MGCR_OK;
+    ctx->launches++;
     NCCL_TRY(g_nccl.GroupStart());
     return MGCR_OK;
 }
 int dist_group_end(mgcr_ctx* ctx) {
     if (ctx->nranks == 1) return MGCR_OK;
-    ctx->launches++;
     NCCL_TRY(g_nccl.GroupEnd());
     return MGCR_OK;
 }
+static ncclComm_t comm_for(mgcr_ctx* ctx, cudaStream_t stream) {
+    return (ncclComm_t)((stream == ctx->aux_stream && ctx->nccl_comm_halo) ? ctx->nccl_comm_halo : ctx->nccl_comm);
+}
 int dist_send(mgcr_ctx* ctx, const void* d_send, size_t bytes, int peer, cudaStream_t stream) {
-    NCCL_TRY(g_nccl.Send(d_send, bytes, ncclChar_, peer, (ncclComm_t)ctx->nccl_comm, stream));
+    NCCL_TRY(g_nccl.Send(d_send, bytes, ncclChar_, peer, comm_for(ctx, stream), stream));
     return MGCR_OK;
 }
 int dist_recv(mgcr_ctx* ctx, void* d_recv, size_t bytes, int peer, cudaStream_t stream) {
-    NCCL_TRY(g_nccl.Recv(d_recv, bytes, ncclChar_, peer, (ncclComm_t)ctx->nccl_comm, stream));
+    NCCL_TRY(g_nccl.Recv(d_recv, bytes, ncclChar_, peer, comm_for(ctx, stream), stream));
     return MGCR_OK;
 }
 
@@ -145,7 +188,7 @@ int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes
         if (d_send != d_recv) CUDA_TRY(cudaMemcpyAsync(d_recv, d_send, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
         return MGCR_OK;
     }
-    ctx->launches++;
+    ProfScope ps_(ctx, "nccl_allgather", (double)bytes_per_rank * ctx->nranks);
     NCCL_TRY(g_nccl.AllGather(d_send, d_recv, bytes_per_rank, ncclChar_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return MGCR_OK;
 }

@@ -212,7 +212,8 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
             }
             GCUDA(cudaGetLastError());
         }
-        if (dist) GTRY(dist_allreduce_sum(ctx, scal + S_RR, 1 + 2 * lim));
+        // (the last pass of a solve nobody watches leaves nothing to reduce: x is final, ||r||^2 is not read)
+        if (dist && !(blind && final_iter)) GTRY(dist_allreduce_sum(ctx, scal + S_RR, 1 + 2 * lim));
         if (!blind) {
             GCUDA(cudaMemcpyAsync(slot.h, scal + S_BB, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             GCUDA(cudaEventRecord(slot.ev, ctx->stream));

@@ -660,6 +660,7 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
         h->npeers = (int)h->peer.size();
         h->n_ghost = lo_blocks + hi_blocks;
         Ac->halo = h;
+        Ac->halo_rows_lo = lo_blocks; Ac->halo_rows_hi = hi_blocks;
         MGCR_TRY(dev_alloc_t(ctx, (size_t)std::max<int64_t>(1, h->n_ghost * ne), &h->d_ghost));
         // gather here?  yes when the next level cannot keep the slab partition (a rank's aggregates no longer divide) or
         // the coarse system is small enough that communication latency dominates (option gather_dofs, default 2^18)

@@ -50,7 +50,7 @@ static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, c
     mgcr_ctx* ctx = op->ctx;
     ARG_CHECK(x != y, "operator apply: input and output alias");
     const c128* ghost = nullptr;
-    if (op->halo) { MGCR_TRY(halo_exchange(ctx, op->halo, x)); ghost = op->halo->d_ghost; }
+    if (op->halo) { MGCR_TRY(halo_exchange(ctx, op->halo, x)); MGCR_TRY(dist_halo_wait(ctx)); ghost = op->halo->d_ghost; }
     if (op->nrow == 0) return MGCR_OK;
     int grid = (int)((op->nslices * 32 + 255) / 256);
     if (dirac)
@@ -142,6 +142,7 @@ enum { HOP_TX = 32, HOP_TY = 16 };
 struct HopArgs {
     int64_t n2, n1, n0;      // local planes, rows, columns
     int64_t zc;              // planes per z-chunk
+    int64_t z_lo, z_hi;      // planes [z_lo, z_hi) are computed by this launch (interior / boundary split of the halo overlap)
     const c128* x; c128* y;
     const c128* halo_lo; const c128* halo_hi;   // plane below local z=0 / above z=n2-1 (NULL = Dirichlet)
     int dirac; c128 k; const double* diag;
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(HOP_TX* HOP_TY) k_hopping(HopArgs a) {
     const int tx = threadIdx.x % HOP_TX, ty = threadIdx.x / HOP_TX;
     const int64_t x0 = (int64_t)blockIdx.x * HOP_TX, y0 = (int64_t)blockIdx.y * HOP_TY;
     const int64_t gx = x0 + tx, gy = y0 + ty;
-    const int64_t zs = (int64_t)blockIdx.z * a.zc;
-    const int64_t ze = min(zs + a.zc, a.n2);
+    const int64_t zs = a.z_lo + (int64_t)blockIdx.z * a.zc;
+    const int64_t ze = min(zs + a.zc, a.z_hi);
     const int64_t plane = a.n1 * a.n0;
     const bool inb = gx < a.n0 && gy < a.n1;
     const c128 zero = cmake(0., 0.);
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx)
     const int64_t gx = (int64_t)blockIdx.x * hl_tx + threadIdx.x % hl_tx;
     const int64_t gy = (int64_t)blockIdx.y * hl_ty + threadIdx.x / hl_tx;
     if (gx >= a.n0 || gy >= a.n1) return;
-    const int64_t zs = (int64_t)blockIdx.z * a.zc;
-    const int64_t ze = min(zs + a.zc, a.n2);
+    const int64_t zs = a.z_lo + (int64_t)blockIdx.z * a.zc;
+    const int64_t ze = min(zs + a.zc, a.z_hi);
     const int64_t plane = a.n1 * a.n0;
     const int64_t c_off = gy * a.n0 + gx;
     const c128 zero = cmake(0., 0.);
@@ -272,43 +273,63 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
     a.x = x; a.y = y; a.dirac = dirac; a.k = k; a.diag = diag;
     a.halo_lo = nullptr; a.halo_hi = nullptr;
     const int64_t plane = a.n1 * a.n0;
+    const int lo = ctx->rank - 1, hi = ctx->rank + 1;
+    const bool has_lo = distributed && lo >= 0, has_hi = distributed && hi < ctx->nranks;
     if (distributed) {
-        // one plane to each slab neighbour (NCCL send/recv on the compute stream)
-        int lo = ctx->rank - 1, hi = ctx->rank + 1;
-        MGCR_TRY(dist_group_begin(ctx));
-        if (lo >= 0) {
-            MGCR_TRY(dist_send(ctx, x, sizeof(c128) * plane, lo, ctx->stream));
-            MGCR_TRY(dist_recv(ctx, d_halo_lo, sizeof(c128) * plane, lo, ctx->stream));
+        // one plane to each slab neighbour (NCCL send/recv; on the auxiliary stream when the exchange is overlapped)
+        cudaStream_t hs;
+        MGCR_TRY(dist_halo_begin(ctx, &hs));
+        if (has_lo) {
+            MGCR_TRY(dist_send(ctx, x, sizeof(c128) * plane, lo, hs));
+            MGCR_TRY(dist_recv(ctx, d_halo_lo, sizeof(c128) * plane, lo, hs));
             a.halo_lo = d_halo_lo;
         }
-        if (hi < ctx->nranks) {
-            MGCR_TRY(dist_send(ctx, x + (n2_local - 1) * plane, sizeof(c128) * plane, hi, ctx->stream));
-            MGCR_TRY(dist_recv(ctx, d_halo_hi, sizeof(c128) * plane, hi, ctx->stream));
+        if (has_hi) {
+            MGCR_TRY(dist_send(ctx, x + (n2_local - 1) * plane, sizeof(c128) * plane, hi, hs));
+            MGCR_TRY(dist_recv(ctx, d_halo_hi, sizeof(c128) * plane, hi, hs));
             a.halo_hi = d_halo_hi;
         }
-        MGCR_TRY(dist_group_end(ctx));
+        MGCR_TRY(dist_halo_end(ctx));
     }
-    if (n_local == 0) return MGCR_OK;
+    if (n_local == 0) return dist_halo_wait(ctx);
     const bool l1_form = ctx->hopping_kernel == 1;
     int hl_tx = 32;
     static const int hl_tx_max = getenv("MGCR_HL_TX") ? std::min(atoi(getenv("MGCR_HL_TX")), (int)HL_THREADS) : (int)HL_THREADS;   // experiment knob
     while (hl_tx < hl_tx_max && hl_tx * 2 <= a.n0) hl_tx *= 2;
     const int tx = l1_form ? hl_tx : (int)HOP_TX, ty = l1_form ? HL_THREADS / hl_tx : (int)HOP_TY;
-    dim3 grid((unsigned)((a.n0 + tx - 1) / tx), (unsigned)((a.n1 + ty - 1) / ty), 1);
-    int64_t tiles = (int64_t)grid.x * grid.y;
-    int64_t target = (int64_t)ctx->num_sms * 16;
-    int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(a.n2, (target + tiles - 1) / tiles));
-    a.zc = (a.n2 + nchunks - 1) / nchunks;
-    if (a.zc < 8 && a.n2 >= 8) a.zc = 8;
     static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;   // experiment knob
-    if (zc_env > 0) a.zc = std::min<int64_t>(zc_env, a.n2);
-    grid.z = (unsigned)((a.n2 + a.zc - 1) / a.zc);
-    ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
-    if (l1_form)
-        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.) + (bsub ? 16. * n_local : 0.), (k_hopping_l1<<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
-    else
-        KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", apply_bytes() + (diag ? 8. * n_local : 0.) + (bsub ? 16. * n_local : 0.), (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
-    CHECK_LAUNCH();
+    const double bytes_per_plane = (apply_bytes() + (diag ? 8. * n_local : 0.) + (bsub ? 16. * n_local : 0.)) / (double)a.n2;
+    auto launch = [&](int64_t z_lo, int64_t z_hi) -> int {   // planes [z_lo, z_hi)
+        if (z_hi <= z_lo) return MGCR_OK;
+        const int64_t nz = z_hi - z_lo;
+        dim3 grid((unsigned)((a.n0 + tx - 1) / tx), (unsigned)((a.n1 + ty - 1) / ty), 1);
+        int64_t tiles = (int64_t)grid.x * grid.y;
+        int64_t target = (int64_t)ctx->num_sms * 16;
+        int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(nz, (target + tiles - 1) / tiles));
+        a.zc = (nz + nchunks - 1) / nchunks;
+        if (a.zc < 8 && nz >= 8) a.zc = 8;
+        if (zc_env > 0) a.zc = std::min<int64_t>(zc_env, nz);
+        grid.z = (unsigned)((nz + a.zc - 1) / a.zc);
+        ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
+        a.z_lo = z_lo; a.z_hi = z_hi;
+        if (l1_form)
+            KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (k_hopping_l1<<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
+        else
+            KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
+        CHECK_LAUNCH();
+        return MGCR_OK;
+    };
+    if (distributed && dist_halo_overlap(ctx) && a.n2 >= 4) {
+        // interior planes need no ghost data: they run while the halo planes are in flight
+        const int64_t zi0 = has_lo ? 1 : 0, zi1 = has_hi ? a.n2 - 1 : a.n2;
+        MGCR_TRY(launch(zi0, zi1));
+        MGCR_TRY(dist_halo_wait(ctx));
+        MGCR_TRY(launch(0, zi0));
+        MGCR_TRY(launch(zi1, a.n2));
+    } else {
+        MGCR_TRY(dist_halo_wait(ctx));
+        MGCR_TRY(launch(0, a.n2));
+    }
     return MGCR_OK;
 }
 int HoppingOp::apply(const c128* x, c128* y) { return run(x, y, 0, cmake(0., 0.), nullptr); }
@@ -414,8 +435,9 @@ extern "C" int mgcr_dirac_set_k(mgcr_op* op, double k_re, double k_im) {
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_blockcsr_apply(int64_t nb, int ne, const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
                                                         const c128* __restrict__ bval, const c128* __restrict__ x, const c128* __restrict__ ghost,
-                                                        int64_t nb_local_cols, const c128* __restrict__ bsub, c128* __restrict__ y) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                                                        int64_t nb_local_cols, const c128* __restrict__ bsub, c128* __restrict__ y,
+                                                        int64_t row0) {
+    const int64_t t = row0 * ne + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // block rows [row0, nb) of this launch
     const int64_t R = t / ne;
     const int r = (int)(t - R * ne);
     if (R >= nb) return;
@@ -439,8 +461,9 @@ __global__ void __launch_bounds__(256) k_blockcsr_apply(int64_t nb, int ne, cons
 template <int NE>
 __global__ void __launch_bounds__(256) k_blockcsr_apply_ne(int64_t nb, const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
                                                            const c128* __restrict__ bval, const c128* __restrict__ x, const c128* __restrict__ ghost,
-                                                           int64_t nb_local_cols, const c128* __restrict__ bsub, c128* __restrict__ y) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                                                           int64_t nb_local_cols, const c128* __restrict__ bsub, c128* __restrict__ y,
+                                                           int64_t row0) {
+    const int64_t t = row0 * NE + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // block rows [row0, nb) of this launch
     const int64_t R = t / NE;
     const int r = (int)(t - R * NE);
     if (R >= nb) return;
@@ -491,17 +514,29 @@ int BlockCsrOp::run(const c128* x, c128* y, const c128* bsub) {
     ARG_CHECK(x != y, "operator apply: input and output alias");
     const c128* ghost = nullptr;
     if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x)); ghost = halo->d_ghost; }
-    if (nb == 0) return MGCR_OK;
-    int64_t threads = nb * ne;
-    int grid = (int)((threads + 255) / 256);
-    {
-        ProfScope ps_(ctx, "blockcsr_apply", apply_bytes() + (bsub ? 16. * n_local : 0.));
+    if (nb == 0) return dist_halo_wait(ctx);
+    const double bytes_per_row = (apply_bytes() + (bsub ? 16. * n_local : 0.)) / (double)nb;
+    auto launch = [&](int64_t r0, int64_t r1) -> int {   // block rows [r0, r1)
+        if (r1 <= r0) return MGCR_OK;
+        const int grid = (int)(((r1 - r0) * ne + 255) / 256);
+        ProfScope ps_(ctx, "blockcsr_apply", bytes_per_row * (r1 - r0));
         switch (ne) {
-            case 2: k_blockcsr_apply_ne<2><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y); break;
-            case 4: k_blockcsr_apply_ne<4><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y); break;
-            case 8: k_blockcsr_apply_ne<8><<<grid, 256, 0, ctx->stream>>>(nb, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y); break;
-            default: k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(nb, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y);
+            case 2: k_blockcsr_apply_ne<2><<<grid, 256, 0, ctx->stream>>>(r1, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
+            case 4: k_blockcsr_apply_ne<4><<<grid, 256, 0, ctx->stream>>>(r1, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
+            case 8: k_blockcsr_apply_ne<8><<<grid, 256, 0, ctx->stream>>>(r1, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
+            default: k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(r1, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0);
         }
+        return MGCR_OK;
+    };
+    if (halo && dist_halo_overlap(ctx) && nb > halo_rows_lo + halo_rows_hi) {
+        // only the first / last plane of aggregates has ghost columns: everything else runs while the halo is in flight
+        MGCR_TRY(launch(halo_rows_lo, nb - halo_rows_hi));
+        MGCR_TRY(dist_halo_wait(ctx));
+        MGCR_TRY(launch(0, halo_rows_lo));
+        MGCR_TRY(launch(nb - halo_rows_hi, nb));
+    } else {
+        MGCR_TRY(dist_halo_wait(ctx));
+        MGCR_TRY(launch(0, nb));
     }
     CHECK_LAUNCH();
     return MGCR_OK;
@@ -619,17 +654,18 @@ int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x) {
         KLAUNCH(ctx, "halo_pack", 36. * n_send * h->elem, (k_pack<<<stream_grid(ctx, n_send * h->elem, 4), RED_THREADS, 0, ctx->stream>>>(n_send, h->elem, h->d_send_idx, x, h->d_send_buf)));
         CHECK_LAUNCH();
     }
-    MGCR_TRY(dist_group_begin(ctx));
+    cudaStream_t hs;
+    MGCR_TRY(dist_halo_begin(ctx, &hs));
     for (int p = 0; p < h->npeers; p++) {
         int64_t ns = h->send_off[p + 1] - h->send_off[p], nr = h->recv_off[p + 1] - h->recv_off[p];
         if (ns > 0) {
             const c128* src = h->d_send_idx ? h->d_send_buf + h->send_off[p] * h->elem : x + h->send_start[p] * h->elem;
-            MGCR_TRY(dist_send(ctx, src, sizeof(c128) * ns * h->elem, h->peer[p], ctx->stream));
+            MGCR_TRY(dist_send(ctx, src, sizeof(c128) * ns * h->elem, h->peer[p], hs));
         }
-        if (nr > 0) MGCR_TRY(dist_recv(ctx, h->d_ghost + h->recv_off[p] * h->elem, sizeof(c128) * nr * h->elem, h->peer[p], ctx->stream));
+        if (nr > 0) MGCR_TRY(dist_recv(ctx, h->d_ghost + h->recv_off[p] * h->elem, sizeof(c128) * nr * h->elem, h->peer[p], hs));
     }
-    MGCR_TRY(dist_group_end(ctx));
-    return MGCR_OK;
+    MGCR_TRY(dist_halo_end(ctx));
+    return MGCR_OK;   // the caller issues dist_halo_wait() before the work that reads the ghosts
 }
 
 void halo_free(mgcr_ctx* ctx, HaloPlan* h) {

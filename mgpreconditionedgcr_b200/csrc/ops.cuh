@@ -82,6 +82,7 @@ struct BlockCsrOp : mgcr_op {
     int32_t* d_bcol = nullptr;   // [nnzb]
     c128* d_bval = nullptr;      // [nnzb][ne(col)][ne(row)]
     HaloPlan* halo = nullptr;
+    int64_t halo_rows_lo = 0, halo_rows_hi = 0;   // leading / trailing block rows that reference ghost columns
     ~BlockCsrOp() override;
     int apply(const c128* x, c128* y) override;
     int apply_residual(const c128* x, const c128* b, c128* r) override;

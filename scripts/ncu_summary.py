@@ -21,9 +21,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # kernel symbol -> profile class name used by the library (KLAUNCH names)
-CLASS = {"k_sell_spmv<1>": "sell_dirac", "k_sell_spmv<0>": "sell_spmv", "k_hopping": "hopping_dirac", "k_gcr_update_xr": "gcr_update_xr",
-         "k_gcr_dot_hist": "gcr_dot_hist", "k_gcr_update_p": "gcr_update_p", "k_gcr_init": "gcr_init", "k_blockcsr_apply": "blockcsr_apply",
-         "k_restrict": "mg_restrict", "k_prolong": "mg_prolong"}
+CLASS = {"k_sell_spmv<1>": "sell_dirac", "k_sell_spmv<0>": "sell_spmv", "k_hopping": "hopping_dirac", "k_hopping_l1": "hopping_dirac",
+         "k_gcr_update_xr": "gcr_update_xr", "k_gcr_dot_hist": "gcr_dot_hist", "k_gcr_dot_hist_tma": "gcr_dot_hist", "k_gcr_update_p": "gcr_update_p",
+         "k_gcr_init": "gcr_init", "k_blockcsr_apply": "blockcsr_apply", "k_blockcsr_apply_ne": "blockcsr_apply", "k_restrict": "mg_restrict",
+         "k_restrict_warp": "mg_restrict", "k_prolong": "mg_prolong"}
 
 
 def short(name):
@@ -92,7 +93,7 @@ def full(src, dst, workload=None):
             name, r[col["launch__grid_size"]], r[col["launch__block_size"]], r[col["launch__registers_per_thread"]], t, rd / 1e6, wr / 1e6,
             (rd + wr) / 1e6, (rd + wr) / t / 1e3, r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]],
             r[col["sm__warps_active.avg.pct_of_peak_sustained_active"]]))
-        base = re.sub(r"<\d+>$", "", name) if name.startswith(("k_gcr_dot_hist", "k_gcr_update_p")) else name
+        base = re.sub(r"<[^>]*>$", "", name)
         cls = CLASS.get(name) or CLASS.get(base)
         if cls:
             traffic.setdefault(cls, []).append(rd + wr)
@@ -103,8 +104,9 @@ def full(src, dst, workload=None):
         allt = json.load(open(tf)) if os.path.exists(tf) else {}
         allt.setdefault(workload, {})
         for cls, v in traffic.items():
-            allt[workload][cls] = sum(v) / len(v)
-        allt[workload]["_source"] = os.path.basename(dst)
+            allt[workload][cls] = max(v)   # the largest (fine-level) launch of the class
+        allt[workload]["_source"] = (allt[workload].get("_source", "") + " " + os.path.basename(dst)).strip()
+        allt[workload]["_note"] = "DRAM bytes read + written by ONE launch of the class at the fine level (the largest launch captured)"
         json.dump(allt, open(tf, "w"), indent=1, sort_keys=True)
         print("updated", tf)
 
