@@ -332,17 +332,65 @@ extern "C" int mgcr_gcr_op_retarget(mgcr_op* gcr, mgcr_op* A) {
     return MGCR_OK;
 }
 
-// glibc rand() stream of Field::init_rand(seed), elements [skip, skip+n)
+// glibc rand() stream of Field::init_rand(seed), elements [skip, skip+n).
+// rand() itself costs ~10 ns per draw (a lock per call): 2.7 s for a 512^3 field.  glibc's generator is the additive
+// feedback r[i] = r[i-3] + r[i-31] (TYPE_3, seeded by the Lehmer sequence 16807 r mod 2^31-1, first 310 outputs dropped,
+// output r >> 1); GlibcRand restates it and is verified against the C library's rand() on every use -- if the first
+// draws ever differ (another libc), the C library's own rand() is used instead.
+struct GlibcRand {
+    uint32_t ring[31];
+    int f, b;
+    void seed(unsigned int s) {
+        if (s == 0) s = 1;
+        int32_t word = (int32_t)s;
+        ring[0] = (uint32_t)word;
+        for (int i = 1; i < 31; i++) {
+            long hi = word / 127773, lo = word % 127773;
+            word = (int32_t)(16807 * lo - 2836 * hi);
+            if (word < 0) word += 2147483647;
+            ring[i] = (uint32_t)word;
+        }
+        f = 3; b = 0;
+        for (int i = 0; i < 310; i++) next();
+    }
+    inline uint32_t next() {
+        ring[f] += ring[b];
+        const uint32_t out = ring[f] >> 1;
+        if (++f == 31) f = 0;
+        if (++b == 31) b = 0;
+        return out;
+    }
+};
+
+static bool glibc_rand_matches(int seed) {
+    GlibcRand g;
+    g.seed((unsigned int)seed);
+    srand(seed);
+    for (int i = 0; i < 64; i++) if ((int)g.next() != rand()) return false;
+    return true;
+}
+
 int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d_out) {
     if (n == 0) return MGCR_OK;
     c128* h = nullptr;
     CUDA_TRY(cudaMallocHost(&h, sizeof(c128) * (size_t)n));
-    srand(seed);
-    for (int64_t i = 0; i < 2 * skip; i++) (void)rand();
-    for (int64_t i = 0; i < n; i++) {
-        double im = (rand() % 2000) / 1000. - 1;
-        double re = (rand() % 2000) / 1000. - 1;
-        h[i] = cmake(re, im);
+    if (glibc_rand_matches(seed)) {
+        GlibcRand g;
+        g.seed((unsigned int)seed);
+        for (int64_t i = 0; i < 2 * skip; i++) (void)g.next();
+        for (int64_t i = 0; i < n; i++) {
+            double im = (int)(g.next() % 2000) / 1000. - 1;     // the imaginary argument is evaluated first (g++), SURVEY.md 8a row a9
+            double re = (int)(g.next() % 2000) / 1000. - 1;
+            h[i] = cmake(re, im);
+        }
+    } else {
+        srand(seed);
+        for (int64_t i = 0; i < 2 * skip; i++) (void)rand();
+        for (int64_t i = 0; i < n; i++) {
+            double im = (rand() % 2000) / 1000. - 1;
+            double re = (rand() % 2000) / 1000. - 1;
+            h[i] = cmake(re, im);
+        }
     }
     cudaError_t e = cudaMemcpyAsync(d_out, h, sizeof(c128) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

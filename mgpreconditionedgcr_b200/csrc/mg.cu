@@ -152,12 +152,13 @@ __global__ void __launch_bounds__(256) k_galerkin(Rows M, LevelGeom g, int KMAX,
                                                   int8_t* __restrict__ bslot_out, c128* __restrict__ bval_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* G = (c128*)smem_raw;                       // [K][ne*ne] row-major accumulators
-    c128* T = G + (int64_t)KMAX * g.ne * g.ne;       // [K][ne]
+    c128* T = G + (int64_t)KMAX * g.ne * g.ne;       // [QC][K][ne]: (M P) rows of the QC fine rows of one pass
     __shared__ RowSlots rs;
     const int64_t B = blockIdx.x;
     const int ne = g.ne;
     const int64_t nsite = g.nb * g.bs;
     const int64_t out0 = brow[B];
+    const int QC = max(1, (int)blockDim.x / ne);     // fine rows per pass: thread (qq, c) forms row q0+qq, near-null vector c
     if (threadIdx.x == 0) {
         row_slots(g, B, &rs);
         for (int a = 0; a < rs.K; a++) { bcol_out[out0 + a] = (int32_t)rs.col[a]; bslot_out[out0 + a] = (int8_t)rs.slot[a]; }
@@ -165,41 +166,50 @@ __global__ void __launch_bounds__(256) k_galerkin(Rows M, LevelGeom g, int KMAX,
     for (int t = threadIdx.x; t < KMAX * ne * ne; t += blockDim.x) G[t] = cmake(0., 0.);
     __syncthreads();
     const int K = rs.K;
-    for (int64_t q = 0; q < g.bl; q++) {
-        const int64_t i = block_map[B * g.bs + q / g.dof] * g.dof + q % g.dof;
-        // T[a][c] = sum over the entries (j, v) of row i whose column lies in the block of position a of v * P[j][c]
-        for (int c = threadIdx.x; c < ne; c += blockDim.x) {
-            c128 tacc[9];
+    for (int64_t q0 = 0; q0 < g.bl; q0 += QC) {
+        const int nq = (int)min((int64_t)QC, g.bl - q0);
+        // T[qq][a][c] = sum over the entries (j, v) of fine row i(q0+qq) whose column lies in the block of position a of v * P[j][c]
+        {
+            const int qq = threadIdx.x / ne, c = threadIdx.x - qq * ne;
+            if (qq < nq) {
+                const int64_t q = q0 + qq;
+                const int64_t i = block_map[B * g.bs + q / g.dof] * g.dof + q % g.dof;
+                c128 tacc[9];
 #pragma unroll
-            for (int a = 0; a < 9; a++) tacc[a] = cmake(0., 0.);
-            M.for_each(i, [&](int64_t j, c128 v) {
-                const int64_t js = j / g.dof;
-                int64_t b; c128 pv;
-                if (js < nsite) {
-                    b = site_block[js];
-                    pv = P[(b * ne + c) * g.bl + (int64_t)site_off[js] * g.dof + (j - js * g.dof)];
-                } else {                                   // ghost site: its prolongator row came from the neighbour rank
-                    b = ghost_site_block(g, js - nsite);
-                    pv = Pg[(j - nsite * g.dof) * ne + c];
-                }
-                int pos = -1;
+                for (int a = 0; a < 9; a++) tacc[a] = cmake(0., 0.);
+                M.for_each(i, [&](int64_t j, c128 v) {
+                    const int64_t js = j / g.dof;
+                    int64_t b; c128 pv;
+                    if (js < nsite) {
+                        b = site_block[js];
+                        pv = P[(b * ne + c) * g.bl + (int64_t)site_off[js] * g.dof + (j - js * g.dof)];
+                    } else {                                   // ghost site: its prolongator row came from the neighbour rank
+                        b = ghost_site_block(g, js - nsite);
+                        pv = Pg[(j - nsite * g.dof) * ne + c];
+                    }
+                    int pos = -1;
 #pragma unroll
-                for (int a = 0; a < 9; a++) if (pos < 0 && a < K && rs.col[a] == b) pos = a;
-                if (pos < 0) return;   // not a face neighbour: the reference assembles 9 blocks per row only
+                    for (int a = 0; a < 9; a++) if (pos < 0 && a < K && rs.col[a] == b) pos = a;
+                    if (pos < 0) return;   // not a face neighbour: the reference assembles 9 blocks per row only
 #pragma unroll
-                for (int a = 0; a < 9; a++) if (a == pos) tacc[a] = cadd(tacc[a], cmul(v, pv));
-            });
+                    for (int a = 0; a < 9; a++) if (a == pos) tacc[a] = cadd(tacc[a], cmul(v, pv));
+                });
 #pragma unroll
-            for (int a = 0; a < 9; a++) if (a < K) T[a * ne + c] = tacc[a];
+                for (int a = 0; a < 9; a++) if (a < K) T[((int64_t)qq * K + a) * ne + c] = tacc[a];
+            }
         }
         __syncthreads();
-        for (int t = threadIdx.x; t < ne * ne; t += blockDim.x) {
-            const int r = t / ne, c = t - r * ne;
-            const c128 pr = P[(B * ne + r) * g.bl + q];
-            for (int a = 0; a < K; a++) {
-                const c128 tv = T[a * ne + c];
-                if (tv.x != 0. || tv.y != 0.) G[(int64_t)a * ne * ne + t] = cadd(G[(int64_t)a * ne * ne + t], cmulc(pr, tv));
+        // G[a][r][c] += conj(P_B[q][r]) T[q][a][c], q ascending (the order of the one-row-at-a-time formulation)
+        for (int t = threadIdx.x; t < K * ne * ne; t += blockDim.x) {
+            const int a = t / (ne * ne), rc = t - a * ne * ne;
+            const int r = rc / ne, c = rc - r * ne;
+            c128 acc = G[t];
+            const c128* pr = P + (B * ne + r) * g.bl + q0;
+            for (int qq = 0; qq < nq; qq++) {
+                const c128 tv = T[((int64_t)qq * K + a) * ne + c];
+                if (tv.x != 0. || tv.y != 0.) acc = cadd(acc, cmulc(pr[qq], tv));
             }
+            G[t] = acc;
         }
         __syncthreads();
     }
@@ -417,7 +427,8 @@ static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x) {
 template <class Rows>
 static int galerkin_launch(mgcr_ctx* ctx, MgLevel& L, const Rows& rows, int32_t* bcol, c128* bval) {
     const LevelGeom& g = L.g;
-    size_t smem = sizeof(c128) * ((size_t)L.K * g.ne * g.ne + (size_t)L.K * g.ne);
+    const int qc = std::max(1, 256 / g.ne);
+    size_t smem = sizeof(c128) * ((size_t)L.K * g.ne * g.ne + (size_t)qc * L.K * g.ne);
     ARG_CHECK(smem <= 200 * 1024, "MG setup: %d near-null vectors per aggregate need %zu bytes of shared memory for the coarse blocks", g.ne, smem);
     CUDA_TRY(cudaFuncSetAttribute(k_galerkin<Rows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KLAUNCH(ctx, "mg_galerkin", 0., (k_galerkin<Rows><<<(unsigned)g.nb, 256, smem, ctx->stream>>>(rows, g, L.K, L.Ac->d_brow, L.d_block_map, L.d_site_block,
