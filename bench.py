@@ -55,15 +55,88 @@ WORKLOADS.update({
 })
 
 
+# BASELINE.json configs[4]: anisotropic variable-coefficient operator (generator: host.synthetic_bonds),
+# A = diag - H with bonds eps_d * face-averaged exp(0.5 g_d), eps = (1e-4, 1e-2, 1) from the slowest to the fastest dim,
+# diag = sum of the site's bonds + 0.01.  Five levels 1024x512x512 -> 1024x512x64 -> 512x256x16 -> 128x64x4 -> 32x16x1: the
+# first aggregates are lines along the strongly coupled direction (the y / z oscillations of an isotropic 4^3 aggregate are
+# near-null vectors the coarse space would miss: 118 outer iterations against 42 on the CPU oracle at 64^3).
+ANISO = dict(eps=(1e-4, 1e-2, 1.0), sigma=0.5, m2=0.01, seed=12345)
+WORKLOADS.update({
+    "mg3d_aniso": dict(dims=[1024, 512, 512], aniso=ANISO, restart=3, tol=1e-10, max_iter=1000,
+                       mg=dict(subs=[(1, 1, 8), (2, 2, 4), (4, 4, 4), (4, 4, 4)], n_eigen=[2, 4, 4, 4], **MG_DEFAULT),
+                       desc="3-D 7-point anisotropic variable-coefficient 1024x512x512 (bonds eps_d*exp(0.5 g), eps = 1e-4/1e-2/1, diag = sum + 0.01), "
+                            "5-level MG (aggregates 1x1x8, 2x2x4, 4^3, 4^3; 2/4/4/4 near-null vectors) preconditioned restart-3 GCR to 1e-10",
+                       cpu_sample=[64, 64, 64], cpu_mg=dict(subs=[(1, 1, 8), (2, 2, 4), (4, 4, 2)], n_eigen=[2, 4, 4]), cpu_iters=0),
+    # the same operator and hierarchy shape at 1/8 of the volume (fits the single-GPU profiling passes comfortably)
+    "mg3d_aniso_512": dict(dims=[512, 256, 512], aniso=ANISO, restart=3, tol=1e-10, max_iter=1000,
+                           mg=dict(subs=[(1, 1, 8), (2, 2, 4), (4, 4, 4), (4, 4, 4)], n_eigen=[2, 4, 4, 4], **MG_DEFAULT),
+                           desc="3-D 7-point anisotropic variable-coefficient 512x256x512, 5-level MG preconditioned restart-3 GCR to 1e-10",
+                           cpu_sample=[64, 64, 64], cpu_mg=dict(subs=[(1, 1, 8), (2, 2, 4), (4, 4, 2)], n_eigen=[2, 4, 4]), cpu_iters=0),
+})
+
+
 def scalar_levels(dims, subs, n_eigen):
     """MG level configs of a 3-D scalar lattice: site_dims = [1, nz, ny, nx]; the dof of a coarse level is the number of
-    near-null vectors of the level above (coarse index = block * ne + e, reference src/MG.h:359,378)"""
+    near-null vectors of the level above (coarse index = block * ne + e, reference src/MG.h:359,378).  An entry of subs is
+    the aggregate edge, or a (z, y, x) tuple."""
     lv, cur, ncol = [], list(dims), 1
     for sub, ne in zip(subs, n_eigen):
-        lv.append(dict(site_dims=[1] + cur, sub=[1] + [sub] * 3, n_spin=1, n_col=ncol, n_eigen=ne))
-        cur = [d // sub for d in cur]
+        sub3 = [sub] * 3 if isinstance(sub, int) else list(sub)
+        lv.append(dict(site_dims=[1] + cur, sub=[1] + sub3, n_spin=1, n_col=ncol, n_eigen=ne))
+        cur = [d // q for d, q in zip(cur, sub3)]
         ncol = ne
     return lv
+
+
+def device_synthetic_bonds(torch, dims, z0, z1, eps, sigma, m2, seed, device):
+    """host.synthetic_bonds for planes [z0, z1) computed on the GPU with torch integer ops (input generation only: the
+    hash is a pure function of the global site index, so every rank builds its slab independently).  Returns
+    (faces[3], diag) as flat float64 CUDA tensors."""
+    nzg, ny, nx = dims
+    M = (1 << 64) - 1
+
+    def s64(v):   # two's-complement image of a 64-bit constant
+        v &= M
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def hash_unit(site, d):
+        z = site * 3 + d + s64(seed * 0x9E3779B97F4A7C15)
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * s64(0xBF58476D1CE4E5B9)
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * s64(0x94D049BB133111EB)
+        z = z ^ ((z >> 31) & ((1 << 33) - 1))
+        return ((z >> 11) & ((1 << 53) - 1)).to(torch.float64) * (2.0 / (1 << 53)) - 1.0
+
+    zz = torch.arange(z0, z1, dtype=torch.int64, device=device)[:, None, None]
+    site = (zz * ny + torch.arange(ny, dtype=torch.int64, device=device)[None, :, None]) * nx \
+        + torch.arange(nx, dtype=torch.int64, device=device)[None, None, :]
+    stride = (ny * nx, nx, 1)
+
+    def bond(st, d):
+        f = eps[d] * ((torch.exp(sigma * hash_unit(st, d)) + torch.exp(sigma * hash_unit(st + stride[d], d))) * 0.5)
+        return f
+
+    faces = []
+    for d in range(3):
+        f = bond(site, d)
+        if d == 0:
+            f[(zz == nzg - 1).expand_as(f)] = 0.0
+        elif d == 1:
+            f[:, ny - 1, :] = 0.0
+        else:
+            f[:, :, nx - 1] = 0.0
+        faces.append(f)
+    fz, fy, fx = faces
+    diag = torch.full_like(fz, m2)
+    diag += fz
+    diag[1:] += fz[:-1]
+    if z0 > 0:   # bond to the lower slab neighbour's last plane
+        lo = bond(site[0:1] - stride[0], 0)
+        diag[0:1] += lo
+    diag += fy
+    diag[:, 1:, :] += fy[:, :-1, :]
+    diag += fx
+    diag[:, :, 1:] += fx[:, :, :-1]
+    return [f.reshape(-1) for f in faces], diag.reshape(-1)
 
 
 # iteration counts measured on B200 (parity-checked against the CPU oracle at reduced size); used by the reference
@@ -144,9 +217,16 @@ def reference_cpu_sample(wl):
         # run this workload.  The CPU arm is the C restatement of the same algorithm (oracle/mgcr_oracle.c), 1 thread.
         import numpy as np  # noqa: F401
         from oracle import pyoracle as orc
-        m = wl["mg"]
-        H = orc.hopping(dims)
-        A = orc.dirac(H, 1.0 / (2 * len(dims) + wl["m2"]))
+        m = dict(wl["mg"], **wl.get("cpu_mg", {}))   # a hierarchy of the same shape that fits the sample lattice
+        if wl.get("aniso"):
+            from mgpreconditionedgcr_b200 import host as host_mirror
+            an = wl["aniso"]
+            faces, diag = host_mirror.synthetic_bonds(dims, eps=an["eps"], sigma=an["sigma"], m2=an["m2"], seed=an["seed"])
+            H = orc.hopping(dims, faces)
+            A = orc.dirac(H, 1.0, diag)
+        else:
+            H = orc.hopping(dims)
+            A = orc.dirac(H, 1.0 / (2 * len(dims) + wl["m2"]))
         lv = scalar_levels(dims, m["subs"], m["n_eigen"])
         t0 = time.perf_counter()
         mg = orc.MG(A, lv, orc.gcr_param(*m["eigen"]), orc.gcr_param(*m["coarse"]), orc.gcr_param(*m["smooth"]))
@@ -263,9 +343,12 @@ def main():
             # rank still gets a slab); deeper levels are gathered
             align = 1
             for sub in wl["mg"]["subs"]:
-                if wl["dims"][0] // (align * sub) >= world:
-                    align *= sub
+                sub0 = sub if isinstance(sub, int) else sub[0]
+                if wl["dims"][0] // (align * sub0) >= world:
+                    align *= sub0
             ctx.set_slab_align(align)
+    if wl.get("aniso"):
+        args.operator = "stencil"   # configs[4] is defined matrix-free (its CSR would be 45 GB)
     if wl.get("mg") and args.operator == "csr" and args.workload == "mg3d_512":
         args.operator = "stencil"   # the stored 512^3 operator (22.5 GB) plus the hierarchy is built matrix-free by default
     if world > 1 and args.operator == "csr":
@@ -273,15 +356,26 @@ def main():
     dims = wl["dims"]
     nd = len(dims)
     V = int(np.prod(dims))
-    k = 1.0 / (2 * nd + wl["m2"])
     # operator
-    if args.operator == "stencil":
-        D = host.Hopping(ctx, dims)
+    if wl.get("aniso"):
+        an = wl["aniso"]
+        zb, ze = (0, dims[0]) if world == 1 else host.slab_range(dims[0], ctx.slab_align, rank, world)
+        tf, td = device_synthetic_bonds(torch, dims, zb, ze, an["eps"], an["sigma"], an["m2"], an["seed"], "cuda:%d" % local_rank)
+        torch.cuda.synchronize()
+        D = host.Hopping(ctx, dims, faces_dev=[t.data_ptr() for t in tf])
+        A = host.DiracOp(ctx, D, 1.0, diag_dev=td.data_ptr())
+        ctx.sync()
+        del tf, td
+        torch.cuda.empty_cache()
     else:
-        row, col, val = host.hopping_csr(dims)
-        D = host.Sparse(ctx, V, V, row, col, val)
-        del row, col, val
-    A = host.DiracOp(ctx, D, k)
+        k = 1.0 / (2 * nd + wl["m2"])
+        if args.operator == "stencil":
+            D = host.Hopping(ctx, dims)
+        else:
+            row, col, val = host.hopping_csr(dims)
+            D = host.Sparse(ctx, V, V, row, col, val)
+            del row, col, val
+        A = host.DiracOp(ctx, D, k)
     n_local = A.get_dim()
     # right-hand side: Field::init_rand(0) stream of the reference (this rank's slab of it)
     if world == 1:

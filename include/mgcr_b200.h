@@ -130,15 +130,21 @@ int mgcr_csr_create(mgcr_ctx* ctx, int64_t nrow, int64_t ncol, const int64_t* h_
 int mgcr_csr_create_dist(mgcr_ctx* ctx, int64_t nrow_global, int64_t row_begin, int64_t row_end, const int64_t* h_row,
                          const int64_t* h_col, const mgcr_c128* h_val, mgcr_op** out);
 /* Matrix-free nearest-neighbour hopping operator H of an ndim (1..3) Dirichlet lattice, row-major site index
- * (src/Mesh.h:146-154): (H x)_i = sum of the in-range +-1 neighbours -- what make_hopping()+Sparse give, without
- * storing the matrix.  h_face[d] (optional, may be NULL = all ones) is a HOST array of V doubles: the coefficient
- * of the bond between site i and site i+e_d.  In a distributed context dims[0] is split into slabs and the
- * coefficient arrays are the local slab (plus nothing: the bond to the upper neighbour plane lives with the lower
- * site). */
+ * (src/Mesh.h:146-154): (H x)_i = sum over the in-range +-1 neighbours j of f_ij x_j -- what a Sparse built through the
+ * raw-CSR constructor (src/Operator.h:64) with those entries gives (same ascending-column summation order,
+ * src/Operator.h:336-343), without storing the matrix.  h_face == NULL: unit hopping, f = 1.  Otherwise h_face[d]
+ * (d = 0..ndim-1, dims order) is a HOST array of n_local doubles: h_face[d][i] = the real, symmetric coefficient of the
+ * bond between site i and its +1 neighbour in dim d (entries whose neighbour is outside the lattice are ignored).  In a
+ * distributed context dims[0] is split into slabs and the arrays are the local slab; the bond to the upper neighbour's
+ * first plane lives with the lower site, the library forwards it once at creation (collective). */
 int mgcr_hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* h_dims, const double* const* h_face, mgcr_op** out);
+/* the same with the bond arrays already in DEVICE memory (they are copied; the caller keeps ownership) */
+int mgcr_hopping_create_dev(mgcr_ctx* ctx, int ndim, const int64_t* h_dims, const double* const* d_face, mgcr_op** out);
 /* DiracOp<num_type>(D, k) = 1 - k D (Operator.h:105-122, 556-574).  D is borrowed and must outlive the result.
  * h_diag (optional, HOST array of n doubles) generalises the identity to a real diagonal: y = diag.x - k D x. */
 int mgcr_dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* h_diag, mgcr_op** out);
+/* the same with the diagonal already in DEVICE memory (copied) */
+int mgcr_dirac_create_dev(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* d_diag, mgcr_op** out);
 int mgcr_dirac_set_k(mgcr_op* dirac, double k_re, double k_im);                      /* Operator.h:118 */
 /* HierarchicalSparse<num_type,int>(block_rows, block_cols, triplets, n) (HierarchicalSparse.h:58-98) from an
  * already sorted block-CSR: nb block rows of dense ne x ne row-major blocks (Dense, Operator.h:32-54). */

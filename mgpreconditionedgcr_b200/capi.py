@@ -78,7 +78,9 @@ SIGNATURES = {
     "mgcr_csr_create": [_vp, _i64, _i64, _vp, _vp, _vp, _pvp],
     "mgcr_csr_create_dist": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _pvp],
     "mgcr_hopping_create": [_vp, _int, _pi64, _vp, _pvp],
+    "mgcr_hopping_create_dev": [_vp, _int, _pi64, _vp, _pvp],
     "mgcr_dirac_create": [_vp, _vp, _dbl, _dbl, _vp, _pvp],
+    "mgcr_dirac_create_dev": [_vp, _vp, _dbl, _dbl, _vp, _pvp],
     "mgcr_dirac_set_k": [_vp, _dbl, _dbl],
     "mgcr_blockcsr_create": [_vp, _i64, _int, _vp, _vp, _vp, _pvp],
     "mgcr_callback_op_create": [_vp, _i64, _vp, _vp, _pvp],

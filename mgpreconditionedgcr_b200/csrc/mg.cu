@@ -323,6 +323,36 @@ static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, const
     }
 }
 
+// Tiny aggregates (up to G = 8 or 16 dofs, e.g. the 1x1x8 line aggregates of the anisotropic configuration): G lanes per
+// aggregate, 32/G aggregates per warp, so that no lane idles.  Lane q of the group holds dof q; the group's shuffle tree
+// (xor G/2 .. 1) is the tail of the full warp tree, whose upper steps would only add zeros: bit-identical to k_restrict_warp.
+template <int G>
+static __global__ void __launch_bounds__(256) k_restrict_sub(LevelGeom g, const int64_t* __restrict__ block_map, const c128* __restrict__ P,
+                                                             const c128* __restrict__ xf, c128* __restrict__ xc) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t b = t / G;
+    const int q = (int)(t % G);
+    const bool on = b < g.nb && q < g.bl;
+    c128 xv = cmake(0., 0.);
+    if (on) {
+        const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
+        xv = __ldg(xf + site * g.dof + q % g.dof);
+    }
+    for (int e = 0; e < g.ne; e++) {
+        double sr = 0., si = 0.;
+        if (on) {
+            c128 v = cmulc(ld_stream(P + (b * g.ne + e) * g.bl + q), xv);
+            sr = v.x; si = v.y;
+        }
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            si += __shfl_xor_sync(0xffffffffu, si, o);
+        }
+        if (on && q == 0) xc[b * g.ne + e] = cmake(sr, si);
+    }
+}
+
 // x[map(b,q)] = sum_e xc[b*ne+e] P[b][e][q]   (MG.h:347-364): one thread per fine dof, e in the reference's order
 static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, int64_t total, const int64_t* __restrict__ block_map,
                                                         const c128* __restrict__ P, const c128* __restrict__ xc, c128* __restrict__ xf, int add) {
@@ -346,7 +376,9 @@ static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
     if (g.bl <= 256) {
         const unsigned grid = (unsigned)((g.nb * 32 + 255) / 256);
         ProfScope ps_(ctx, "mg_restrict", bytes);
-        if (g.bl <= 64) k_restrict_warp<2><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
+        if (g.bl <= 8) k_restrict_sub<8><<<(unsigned)((g.nb * 8 + 255) / 256), 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
+        else if (g.bl <= 16) k_restrict_sub<16><<<(unsigned)((g.nb * 16 + 255) / 256), 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
+        else if (g.bl <= 64) k_restrict_warp<2><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
         else if (g.bl <= 128) k_restrict_warp<4><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
         else k_restrict_warp<8><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
     } else {

@@ -1,5 +1,7 @@
 // csrc/ops.cu -- operator applies: sliced-ELL SpMV (Sparse::operator(), src/Operator.h:330-346), fused DiracOp
 // (src/Operator.h:569-574), matrix-free hopping stencil, block-CSR coarse operator (src/HierarchicalSparse.h:101-161).
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include <algorithm>
 
 #include "kernels_blas.cuh"
@@ -147,6 +149,9 @@ struct HopArgs {
     const c128* halo_lo; const c128* halo_hi;   // plane below local z=0 / above z=n2-1 (NULL = Dirichlet)
     int dirac; c128 k; const double* diag;
     const c128* bsub;        // non-NULL: store b - (A x) (the multigrid residual)
+    // variable bond coefficients (NULL = unit hopping): fx[i] / fy[i] = bond between site i and i+1 / i+n0,
+    // fz[z*plane + c] = bond between plane z-1 and plane z (n2+1 planes: the first / last is the bond to the slab neighbour)
+    const double* fz; const double* fy; const double* fx;
 };
 
 __global__ void __launch_bounds__(HOP_TX* HOP_TY) k_hopping(HopArgs a) {
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(HOP_TX* HOP_TY) k_hopping(HopArgs a) {
 // neighbours by warp shuffle (3.4 TB/s), other tile shapes / chunk lengths (all 3.8-4.1 TB/s in 3-D).
 enum { HL_THREADS = 512 };
 
+template <bool VAR>
 __global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx) {
     const int hl_ty = HL_THREADS / hl_tx;
     const int64_t gx = (int64_t)blockIdx.x * hl_tx + threadIdx.x % hl_tx;
@@ -237,18 +243,35 @@ __global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx)
         return p ? __ldg(p + c_off) : zero;
     };
     c128 prev = load(zs - 1), cur = load(zs), next = load(zs + 1);
+    double fzm = 0., fzp = 0.;   // bonds to the plane below / above the current one
+    if (VAR) { fzm = __ldg(a.fz + zs * plane + c_off); fzp = __ldg(a.fz + (zs + 1) * plane + c_off); }
     for (int64_t z = zs; z < ze; z++) {
         const c128 next2 = (z + 2 <= ze) ? load(z + 2) : zero;   // z + 2 == ze is the chunk's upper neighbour plane
+        double fzp2 = 0.;
+        if (VAR && z + 1 < ze) fzp2 = __ldg(a.fz + (z + 2) * plane + c_off);
         const c128* pc = a.x + z * plane + c_off;
-        const c128 vym = ym ? __ldg(pc - a.n0) : zero;
-        const c128 vxm = xm ? __ldg(pc - 1) : zero;
-        const c128 vxp = xp ? __ldg(pc + 1) : zero;
-        const c128 vyp = yp ? __ldg(pc + a.n0) : zero;
-        c128 s = cadd(prev, vym);
+        c128 vym = ym ? __ldg(pc - a.n0) : zero;
+        c128 vxm = xm ? __ldg(pc - 1) : zero;
+        c128 vxp = xp ? __ldg(pc + 1) : zero;
+        c128 vyp = yp ? __ldg(pc + a.n0) : zero;
+        c128 vzm = prev, vzp = next;
+        if (VAR) {   // real bond x complex neighbour: what the CSR product (f + 0i) * x gives, up to the sign of a zero
+            const double* fyc = a.fy + z * plane + c_off;
+            const double* fxc = a.fx + z * plane + c_off;
+            const double cym = ym ? __ldg(fyc - a.n0) : 0., cxm = xm ? __ldg(fxc - 1) : 0.;
+            const double cxp = xp ? __ldg(fxc) : 0., cyp = yp ? __ldg(fyc) : 0.;
+            vzm = cmake(fzm * vzm.x, fzm * vzm.y);
+            vym = cmake(cym * vym.x, cym * vym.y);
+            vxm = cmake(cxm * vxm.x, cxm * vxm.y);
+            vxp = cmake(cxp * vxp.x, cxp * vxp.y);
+            vyp = cmake(cyp * vyp.x, cyp * vyp.y);
+            vzp = cmake(fzp * vzp.x, fzp * vzp.y);
+        }
+        c128 s = cadd(vzm, vym);
         s = cadd(s, vxm);
         s = cadd(s, vxp);
         s = cadd(s, vyp);
-        s = cadd(s, next);
+        s = cadd(s, vzp);
         if (a.dirac) {
             c128 xr = cur;
             if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
@@ -257,7 +280,164 @@ __global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx)
         if (a.bsub) s = csub(__ldg(a.bsub + z * plane + c_off), s);
         st_stream(a.y + z * plane + c_off, s);
         prev = cur; cur = next; next = next2;
+        fzm = fzp; fzp = fzp2;
     }
+}
+
+// Third form: the planes are staged through a shared-memory ring by TMA tensor copies.  A CTA owns a TX x TY tile of the
+// (n1, n0) plane and a chunk of planes; ONE producer thread issues, for every plane zs-1 .. ze, a 3-D box copy
+// (TX+2) x (TY+2) x 1 of the operand (cp.async.bulk.tensor, completion on an mbarrier) -- elements outside the lattice are
+// zero-filled by the copy engine, which is exactly the Dirichlet boundary, so the consumers have no bounds logic on the
+// neighbour reads.  16 consumer warps (one site per thread and plane) read the 4 in-plane neighbours and the next plane's
+// centre from shared memory (prev / cur stay in registers) and release the stage through a second mbarrier: nobody waits
+// on a block-wide barrier, and the bytes in flight per SM are stages x tile, independent of the compiler's load scheduling
+// (the register-marching form has one HBM-bound load per thread in flight and sits at 0.63 of the copy peak).
+// The operand is described as doubles (2 per element) because the tensor-map element types stop at 8 bytes.
+template <int TX, int TY>
+struct HopTmaCfg {
+    static constexpr int CONSUMERS = TX * TY;
+    static constexpr int THREADS = CONSUMERS + 32;
+    static constexpr int ROW = TX + 2;
+    static constexpr int TILE = ROW * (TY + 2);                       // c128 per stage
+    static constexpr int STAGE_BYTES = ((TILE * 16 + 127) / 128) * 128;
+};
+enum { HOP_TMA_MAX_STAGES = 12 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(HopTmaCfg<TX, TY>::THREADS, 2) k_hopping_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_lo,
+                                                                              const __grid_constant__ CUtensorMap map_hi, HopArgs a, int stages) {
+    typedef HopTmaCfg<TX, TY> C;
+    extern __shared__ unsigned char hop_smem_raw[];
+    __shared__ __align__(8) uint64_t full[HOP_TMA_MAX_STAGES], empty[HOP_TMA_MAX_STAGES];
+    unsigned char* ring = (unsigned char*)(((uintptr_t)hop_smem_raw + 127) & ~(uintptr_t)127);
+    const int64_t x0 = (int64_t)blockIdx.x * TX, y0 = (int64_t)blockIdx.y * TY;
+    const int64_t zs = a.z_lo + (int64_t)blockIdx.z * a.zc;
+    const int64_t ze = min(zs + a.zc, a.z_hi);
+    const int nplanes = (int)(ze - zs) + 2;                            // planes zs-1 .. ze
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], C::CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x >= C::CONSUMERS) {
+        // ---- producer: one elected thread of the last warp ----
+        if (threadIdx.x == C::CONSUMERS) {
+            for (int p = 0; p < nplanes; p++) {
+                const int s = p % stages;
+                if (p >= stages) mbar_wait(&empty[s], (uint32_t)((p / stages - 1) & 1));
+                const int64_t z = zs - 1 + p;
+                const CUtensorMap* m = &map_x;
+                int zc = (int)z;                                       // z = -1 / n2 without a slab neighbour: out of range, zero-filled
+                if (z < 0 && a.halo_lo) { m = &map_lo; zc = 0; }
+                else if (z >= a.n2 && a.halo_hi) { m = &map_hi; zc = 0; }
+                mbar_expect_tx(&full[s], (uint32_t)(C::TILE * 16));
+                tma_load_3d(ring + (size_t)s * C::STAGE_BYTES, m, (int)(2 * (x0 - 1)), (int)(y0 - 1), zc, &full[s]);
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, lane = threadIdx.x & 31;
+    const int64_t gx = x0 + tx, gy = y0 + ty;
+    const bool inb = gx < a.n0 && gy < a.n1;
+    const int64_t plane = a.n1 * a.n0;
+    const int64_t c_off = gy * a.n0 + gx;
+    const int ctr = (ty + 1) * C::ROW + tx + 1;
+    auto tile = [&](int p) -> const c128* { return (const c128*)(ring + (size_t)(p % stages) * C::STAGE_BYTES); };
+    mbar_wait(&full[0], 0);
+    c128 prev = tile(0)[ctr];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[0]);
+    mbar_wait(&full[1 % stages], (uint32_t)((1 / stages) & 1));
+    c128 cur = tile(1)[ctr];
+    for (int p = 1; p + 1 < nplanes; p++) {
+        const int64_t z = zs - 1 + p;
+        mbar_wait(&full[(p + 1) % stages], (uint32_t)(((p + 1) / stages) & 1));
+        const c128 next = tile(p + 1)[ctr];
+        const c128* t = tile(p);
+        c128 s = cadd(prev, t[ctr - C::ROW]);
+        s = cadd(s, t[ctr - 1]);
+        s = cadd(s, t[ctr + 1]);
+        s = cadd(s, t[ctr + C::ROW]);
+        s = cadd(s, next);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[p % stages]);               // this warp is done with plane z's stage
+        if (inb) {
+            if (a.dirac) {
+                c128 xr = cur;
+                if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
+                s = csub(xr, cmul(a.k, s));
+            }
+            if (a.bsub) s = csub(__ldg(a.bsub + z * plane + c_off), s);
+            st_stream(a.y + z * plane + c_off, s);
+        }
+        prev = cur; cur = next;
+    }
+}
+
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tensor_map_encode_fn tensor_map_encoder() {
+    static tensor_map_encode_fn fn = []() -> tensor_map_encode_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return (tensor_map_encode_fn)p;
+    }();
+    return fn;
+}
+// tensor map of `planes` planes of n1 x n0 c128 at `base`, box (tx+2) x (ty+2) x 1, out-of-range elements read as zero
+static int hop_tensor_map(CUtensorMap* m, const c128* base, int64_t n0, int64_t n1, int64_t planes, int tx, int ty) {
+    tensor_map_encode_fn enc = tensor_map_encoder();
+    if (!enc) { mgcr_set_error("cuTensorMapEncodeTiled is not available from this driver"); return MGCR_ERR_CUDA; }
+    const cuuint64_t gdim[3] = {(cuuint64_t)(2 * n0), (cuuint64_t)n1, (cuuint64_t)planes};
+    const cuuint64_t gstride[2] = {(cuuint64_t)(16 * n0), (cuuint64_t)(16 * n0 * n1)};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * (tx + 2)), (cuuint32_t)(ty + 2), 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { mgcr_set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %lld x %lld lattice", (int)r, (long long)planes, (long long)n1, (long long)n0); return MGCR_ERR_CUDA; }
+    return MGCR_OK;
+}
+
+template <int TX, int TY>
+static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_t z_hi, const char* name, double bytes) {
+    typedef HopTmaCfg<TX, TY> C;
+    HopArgs a = a0;
+    static const int stages_env = getenv("MGCR_HOP_STAGES") ? atoi(getenv("MGCR_HOP_STAGES")) : 0;   // experiment knobs
+    static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;
+    const int stages = std::max(3, std::min((int)HOP_TMA_MAX_STAGES, stages_env > 0 ? stages_env : 6));
+    const size_t smem = (size_t)stages * C::STAGE_BYTES + 128;
+    CUtensorMap mx, mlo, mhi;
+    MGCR_TRY(hop_tensor_map(&mx, a.x, a.n0, a.n1, a.n2, TX, TY));
+    mlo = mx; mhi = mx;
+    if (a.halo_lo) MGCR_TRY(hop_tensor_map(&mlo, a.halo_lo, a.n0, a.n1, 1, TX, TY));
+    if (a.halo_hi) MGCR_TRY(hop_tensor_map(&mhi, a.halo_hi, a.n0, a.n1, 1, TX, TY));
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_hopping_tma<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HOP_TMA_MAX_STAGES * C::STAGE_BYTES + 128))); attr_set = true; }
+    const int64_t nz = z_hi - z_lo;
+    dim3 grid((unsigned)((a.n0 + TX - 1) / TX), (unsigned)((a.n1 + TY - 1) / TY), 1);
+    // chunks of planes: enough CTAs for ~8 waves of the resident set (the last, partial wave is the tail), but chunks of
+    // at least 16 planes (each chunk re-reads its two boundary planes)
+    const int64_t tiles = (int64_t)grid.x * grid.y;
+    const int64_t resident = (int64_t)ctx->num_sms * std::max<int64_t>(1, std::min<int64_t>(2, (int64_t)(220 * 1024) / (int64_t)smem));   // 2 CTAs per SM by registers
+    int64_t nchunks = std::max<int64_t>(1, (8 * resident + tiles - 1) / tiles);
+    a.zc = std::max<int64_t>((nz + nchunks - 1) / nchunks, std::min<int64_t>(16, nz));
+    if (zc_env > 0) a.zc = std::min<int64_t>(zc_env, nz);
+    grid.z = (unsigned)((nz + a.zc - 1) / a.zc);
+    ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
+    a.z_lo = z_lo; a.z_hi = z_hi;
+    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY><<<grid, C::THREADS, smem, ctx->stream>>>(mx, mlo, mhi, a, stages)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
 }
 
 HoppingOp::~HoppingOp() {
@@ -272,6 +452,7 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
     a.n2 = n2_local; a.n1 = gdims[1]; a.n0 = gdims[2];
     a.x = x; a.y = y; a.dirac = dirac; a.k = k; a.diag = diag;
     a.halo_lo = nullptr; a.halo_hi = nullptr;
+    a.fz = d_face[0]; a.fy = d_face[1]; a.fx = d_face[2];
     const int64_t plane = a.n1 * a.n0;
     const int lo = ctx->rank - 1, hi = ctx->rank + 1;
     const bool has_lo = distributed && lo >= 0, has_hi = distributed && hi < ctx->nranks;
@@ -292,16 +473,24 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
         MGCR_TRY(dist_halo_end(ctx));
     }
     if (n_local == 0) return dist_halo_wait(ctx);
-    const bool l1_form = ctx->hopping_kernel == 1;
+    const bool l1_form = ctx->hopping_kernel == 1 || var;   // the tile kernel is unit-hopping only
     int hl_tx = 32;
     static const int hl_tx_max = getenv("MGCR_HL_TX") ? std::min(atoi(getenv("MGCR_HL_TX")), (int)HL_THREADS) : (int)HL_THREADS;   // experiment knob
     while (hl_tx < hl_tx_max && hl_tx * 2 <= a.n0) hl_tx *= 2;
     const int tx = l1_form ? hl_tx : (int)HOP_TX, ty = l1_form ? HL_THREADS / hl_tx : (int)HOP_TY;
     static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;   // experiment knob
     const double bytes_per_plane = (apply_bytes() + (diag ? 8. * n_local : 0.) + (bsub ? 16. * n_local : 0.)) / (double)a.n2;
+    // TMA-staged form: unit hopping on lattices at least one tile wide (narrower ones are latency-bound anyway)
+    static const int tma_tile_env = getenv("MGCR_HOP_TILE") ? atoi(getenv("MGCR_HOP_TILE")) : 0;   // experiment knob: 1 = 32 x 16 tile
+    const bool tma_form = ctx->hopping_kernel == 2 && !var && a.n0 >= 64 && a.n1 >= 8;
     auto launch = [&](int64_t z_lo, int64_t z_hi) -> int {   // planes [z_lo, z_hi)
         if (z_hi <= z_lo) return MGCR_OK;
         const int64_t nz = z_hi - z_lo;
+        if (tma_form) {
+            const char* nm = dirac ? "hopping_dirac" : "hopping";
+            return tma_tile_env == 1 ? hop_tma_launch<32, 16>(ctx, a, z_lo, z_hi, nm, bytes_per_plane * nz)
+                                     : hop_tma_launch<64, 8>(ctx, a, z_lo, z_hi, nm, bytes_per_plane * nz);
+        }
         dim3 grid((unsigned)((a.n0 + tx - 1) / tx), (unsigned)((a.n1 + ty - 1) / ty), 1);
         int64_t tiles = (int64_t)grid.x * grid.y;
         int64_t target = (int64_t)ctx->num_sms * 16;
@@ -312,8 +501,10 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
         grid.z = (unsigned)((nz + a.zc - 1) / a.zc);
         ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
         a.z_lo = z_lo; a.z_hi = z_hi;
-        if (l1_form)
-            KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (k_hopping_l1<<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
+        if (var)
+            KLAUNCH(ctx, dirac ? "hopping_var_dirac" : "hopping_var", bytes_per_plane * nz, (k_hopping_l1<true><<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
+        else if (l1_form)
+            KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (k_hopping_l1<false><<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
         else
             KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
         CHECK_LAUNCH();
@@ -335,36 +526,80 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
 int HoppingOp::apply(const c128* x, c128* y) { return run(x, y, 0, cmake(0., 0.), nullptr); }
 int HoppingOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag, const c128* bsub) { return run(x, y, 1, k, diag, bsub); }
 
-extern "C" int mgcr_hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims, const double* const* h_face, mgcr_op** out) {
+// faces: ndim pointers (HOST or DEVICE arrays of n_local doubles, dims order) or NULL for unit hopping
+static int hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims, const double* const* face, bool face_on_device, mgcr_op** out) {
     ARG_CHECK(ctx && dims && out, "mgcr_hopping_create: NULL argument");
     ARG_CHECK(ndim >= 1 && ndim <= 3, "mgcr_hopping_create: ndim must be 1..3 (got %d)", ndim);
-    if (h_face) { mgcr_set_error("mgcr_hopping_create: variable bond coefficients are not available yet"); return MGCR_ERR_UNSUPPORTED; }
     *out = nullptr;
     HoppingOp* op = new HoppingOp();
     op->kind = OP_HOPPING; op->ctx = ctx; op->ndim = ndim;
     for (int d = 0; d < ndim; d++) {
-        ARG_CHECK(dims[d] >= 1, "mgcr_hopping_create: dims[%d] < 1", d);
+        if (dims[d] < 1) { delete op; mgcr_set_error("mgcr_hopping_create: dims[%d] < 1", d); return MGCR_ERR_ARG; }
         op->gdims[3 - ndim + d] = dims[d];
     }
     // a 2-D lattice (ny, nx) is traversed as (ny, 1, nx): the kernels stream along their slowest index with the neighbours
     // in that direction held in registers; the operator and the order of the neighbour sum (y-1, x-1, x+1, y+1) are the same
     if (ndim == 2) { op->gdims[0] = dims[0]; op->gdims[1] = 1; op->gdims[2] = dims[1]; }
     int64_t zb = 0, ze = op->gdims[0];
+    const int64_t plane = op->gdims[1] * op->gdims[2];
     if (ctx->nranks > 1) {
-        ARG_CHECK(ndim == 3, "mgcr_hopping_create: the distributed stencil is 3-D (slabs along dims[0])");
-        MGCR_TRY(mgcr_slab_range(op->gdims[0], ctx->slab_align, ctx->rank, ctx->nranks, &zb, &ze));
-        ARG_CHECK(ze > zb, "mgcr_hopping_create: rank %d owns no plane", ctx->rank);
-        int64_t plane = op->gdims[1] * op->gdims[2];
-        int st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_lo);
+        if (ndim != 3) { delete op; mgcr_set_error("mgcr_hopping_create: the distributed stencil is 3-D (slabs along dims[0])"); return MGCR_ERR_ARG; }
+        int st = mgcr_slab_range(op->gdims[0], ctx->slab_align, ctx->rank, ctx->nranks, &zb, &ze);
+        if (st == MGCR_OK && ze <= zb) { mgcr_set_error("mgcr_hopping_create: rank %d owns no plane", ctx->rank); st = MGCR_ERR_ARG; }
+        if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_lo);
         if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_hi);
         if (st != MGCR_OK) { delete op; return st; }
     }
     op->distributed = ctx->nranks > 1;
     op->z_begin = zb; op->n2_local = ze - zb;
-    op->n_local = op->n2_local * op->gdims[1] * op->gdims[2];
-    op->n_global = op->gdims[0] * op->gdims[1] * op->gdims[2];
+    op->n_local = op->n2_local * plane;
+    op->n_global = op->gdims[0] * plane;
+    if (face) {
+        // slot of dims[d] among (z, y, x); the z bonds get one more leading plane: the bond to the lower slab neighbour
+        const int slot_of[3][3] = {{2, -1, -1}, {0, 2, -1}, {0, 1, 2}};
+        const double* src[3] = {nullptr, nullptr, nullptr};
+        for (int d = 0; d < ndim; d++) {
+            if (!face[d]) { delete op; mgcr_set_error("mgcr_hopping_create: face[%d] is NULL", d); return MGCR_ERR_ARG; }
+            src[slot_of[ndim - 1][d]] = face[d];
+        }
+        const cudaMemcpyKind kind = face_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        const size_t nl = (size_t)op->n_local;
+        int st = dev_alloc_t(ctx, nl + (size_t)plane, &op->d_face[0]);
+        if (st == MGCR_OK && src[1]) st = dev_alloc_t(ctx, nl, &op->d_face[1]);
+        if (st == MGCR_OK) st = dev_alloc_t(ctx, nl, &op->d_face[2]);
+        cudaError_t e = cudaSuccess;
+        if (st == MGCR_OK) {
+            e = cudaMemsetAsync(op->d_face[0], 0, sizeof(double) * (size_t)plane, ctx->stream);
+            if (e == cudaSuccess) e = src[0] ? cudaMemcpyAsync(op->d_face[0] + plane, src[0], sizeof(double) * nl, kind, ctx->stream)
+                                             : cudaMemsetAsync(op->d_face[0] + plane, 0, sizeof(double) * nl, ctx->stream);
+            if (e == cudaSuccess && src[1]) e = cudaMemcpyAsync(op->d_face[1], src[1], sizeof(double) * nl, kind, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(op->d_face[2], src[2], sizeof(double) * nl, kind, ctx->stream);
+        }
+        if (st == MGCR_OK && e == cudaSuccess && op->distributed) {
+            // the bond between my first plane and the lower neighbour's last plane lives with the lower neighbour
+            st = dist_group_begin(ctx);
+            if (st == MGCR_OK && ctx->rank + 1 < ctx->nranks) st = dist_send(ctx, op->d_face[0] + (size_t)op->n2_local * plane, sizeof(double) * plane, ctx->rank + 1, ctx->stream);
+            if (st == MGCR_OK && ctx->rank > 0) st = dist_recv(ctx, op->d_face[0], sizeof(double) * plane, ctx->rank - 1, ctx->stream);
+            if (st == MGCR_OK) st = dist_group_end(ctx);
+        }
+        // no bond leaves the lattice (Dirichlet): whatever the caller stored for the top plane's upward bonds is dropped
+        if (st == MGCR_OK && e == cudaSuccess && ctx->rank + 1 == ctx->nranks)
+            e = cudaMemsetAsync(op->d_face[0] + (size_t)op->n2_local * plane, 0, sizeof(double) * (size_t)plane, ctx->stream);
+        if (st == MGCR_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (st == MGCR_OK && e != cudaSuccess) { mgcr_set_error("mgcr_hopping_create: bond upload: %s", cudaGetErrorString(e)); st = MGCR_ERR_CUDA; }
+        if (st != MGCR_OK) { delete op; return st; }
+        op->var = true;
+    }
     *out = op;
     return MGCR_OK;
+}
+
+extern "C" int mgcr_hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims, const double* const* h_face, mgcr_op** out) {
+    return hopping_create(ctx, ndim, dims, h_face, false, out);
+}
+extern "C" int mgcr_hopping_create_dev(mgcr_ctx* ctx, int ndim, const int64_t* dims, const double* const* d_face, mgcr_op** out) {
+    ARG_CHECK(d_face, "mgcr_hopping_create_dev: NULL bond arrays");
+    return hopping_create(ctx, ndim, dims, d_face, true, out);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -404,7 +639,7 @@ int mgcr_op::apply_residual(const c128* x, const c128* b, c128* r) {
     return vec_axpy(ctx, n_local, cmake(-1., 0.), r, b, r);   // r = b + (-1) r, exactly b - r
 }
 
-extern "C" int mgcr_dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* h_diag, mgcr_op** out) {
+static int dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* h_diag, bool diag_on_device, mgcr_op** out) {
     ARG_CHECK(ctx && D && out, "mgcr_dirac_create: NULL argument");
     *out = nullptr;
     DiracOp* op = new DiracOp();
@@ -413,12 +648,19 @@ extern "C" int mgcr_dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double 
     if (h_diag) {
         int st = dev_alloc_t(ctx, (size_t)op->n_local, &op->d_diag);
         if (st != MGCR_OK) { delete op; return st; }
-        cudaError_t e = cudaMemcpyAsync(op->d_diag, h_diag, sizeof(double) * op->n_local, cudaMemcpyHostToDevice, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(op->d_diag, h_diag, sizeof(double) * op->n_local, diag_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { delete op; mgcr_set_error("dirac diag upload: %s", cudaGetErrorString(e)); return MGCR_ERR_CUDA; }
     }
     *out = op;
     return MGCR_OK;
+}
+
+extern "C" int mgcr_dirac_create(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* h_diag, mgcr_op** out) {
+    return dirac_create(ctx, D, k_re, k_im, h_diag, false, out);
+}
+extern "C" int mgcr_dirac_create_dev(mgcr_ctx* ctx, mgcr_op* D, double k_re, double k_im, const double* d_diag, mgcr_op** out) {
+    return dirac_create(ctx, D, k_re, k_im, d_diag, true, out);
 }
 
 extern "C" int mgcr_dirac_set_k(mgcr_op* op, double k_re, double k_im) {

@@ -52,13 +52,17 @@ struct HoppingOp : mgcr_op {
     int ndim = 3;
     int64_t gdims[3] = {1, 1, 1};   // global (n2, n1, n0), missing leading dims are 1
     int64_t n2_local = 1, z_begin = 0;
-    double* d_face[3] = {nullptr, nullptr, nullptr};   // optional bond coefficients per dim (z, y, x)
+    // variable bond coefficients (var): d_face[2][i] / d_face[1][i] = bond between site i and i+1 / i+n0; d_face[0] holds
+    // n2_local+1 planes, plane z = bonds between plane z-1 and plane z (plane 0: to the lower slab neighbour, zero at the
+    // global boundary)
+    bool var = false;
+    double* d_face[3] = {nullptr, nullptr, nullptr};
     c128* d_halo_lo = nullptr; c128* d_halo_hi = nullptr;   // neighbour planes (distributed)
     ~HoppingOp() override;
     int apply(const c128* x, c128* y) override;
     int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag, const c128* bsub = nullptr);
     int run(const c128* x, c128* y, int dirac, c128 k, const double* d_diag, const c128* bsub = nullptr);
-    double apply_bytes() const override { return 32. * (double)n_local; }
+    double apply_bytes() const override { return (var ? 32. + 8. * ndim : 32.) * (double)n_local; }
 };
 
 struct DiracOp : mgcr_op {

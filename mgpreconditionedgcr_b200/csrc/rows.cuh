@@ -46,27 +46,44 @@ struct HopRows {
     // slab-partitioned operator: the neighbour planes owned by rank-1 / rank+1 are addressed as ghost columns
     // n_local + p (lower plane) and n_local + ghost_lo + p (upper plane), p = y*n0 + x
     int has_lo, has_hi; int64_t ghost_lo;
+    // variable bonds (NULL = unit hopping), layout of HoppingOp::d_face
+    const double* fz; const double* fy; const double* fx;
+    __device__ __forceinline__ c128 entry(double f) const {
+        c128 v = cmake(f, 0.);
+        if (dirac) { v = cmul(k, v); v = cmake(-v.x, -v.y); }
+        return v;
+    }
     template <class F> __device__ __forceinline__ void for_each(int64_t i, F f) const {
         const int64_t x = i % n0, y = (i / n0) % n1, z = i / (n0 * n1);
-        c128 v = cmake(1., 0.);
-        if (dirac) { v = cmul(k, v); v = cmake(-v.x, -v.y); }
-        if (z > 0) f(i - n0 * n1, v); else if (has_lo) f(n2 * n1 * n0 + y * n0 + x, v);
-        if (y > 0) f(i - n0, v);
-        if (x > 0) f(i - 1, v);
-        if (x < n0 - 1) f(i + 1, v);
-        if (y < n1 - 1) f(i + n0, v);
-        if (z < n2 - 1) f(i + n0 * n1, v); else if (has_hi) f(n2 * n1 * n0 + ghost_lo + y * n0 + x, v);
+        const int64_t plane = n0 * n1;
+        const bool var = fx != nullptr;
+        const c128 v = entry(1.);
+        if (z > 0) f(i - plane, var ? entry(fz[i]) : v); else if (has_lo) f(n2 * plane + y * n0 + x, var ? entry(fz[i]) : v);
+        if (y > 0) f(i - n0, var ? entry(fy[i - n0]) : v);
+        if (x > 0) f(i - 1, var ? entry(fx[i - 1]) : v);
+        if (x < n0 - 1) f(i + 1, var ? entry(fx[i]) : v);
+        if (y < n1 - 1) f(i + n0, var ? entry(fy[i]) : v);
+        if (z < n2 - 1) f(i + plane, var ? entry(fz[i + plane]) : v); else if (has_hi) f(n2 * plane + ghost_lo + y * n0 + x, var ? entry(fz[i + plane]) : v);
         if (dirac) f(i, cmake(diag ? diag[i] : 1., 0.));
     }
     // k_hopping (ops.cu): neighbours in ascending column order z-1, y-1, x-1, x+1, y+1, z+1 starting from the first
     __device__ __forceinline__ c128 apply_row(int64_t i, const c128* x) const {
         const int64_t cx = i % n0, cy = (i / n0) % n1, cz = i / (n0 * n1);
+        const int64_t plane = n0 * n1;
         const c128 zero = cmake(0., 0.);
-        c128 s = cadd(cz > 0 ? x[i - n0 * n1] : zero, cy > 0 ? x[i - n0] : zero);
-        s = cadd(s, cx > 0 ? x[i - 1] : zero);
-        s = cadd(s, cx < n0 - 1 ? x[i + 1] : zero);
-        s = cadd(s, cy < n1 - 1 ? x[i + n0] : zero);
-        s = cadd(s, cz < n2 - 1 ? x[i + n0 * n1] : zero);
+        c128 vzm = cz > 0 ? x[i - plane] : zero, vym = cy > 0 ? x[i - n0] : zero, vxm = cx > 0 ? x[i - 1] : zero;
+        c128 vxp = cx < n0 - 1 ? x[i + 1] : zero, vyp = cy < n1 - 1 ? x[i + n0] : zero, vzp = cz < n2 - 1 ? x[i + plane] : zero;
+        if (fx) {
+            const double czm = cz > 0 ? __ldg(fz + i) : 0., cym = cy > 0 ? __ldg(fy + i - n0) : 0., cxm = cx > 0 ? __ldg(fx + i - 1) : 0.;
+            const double cxp = cx < n0 - 1 ? __ldg(fx + i) : 0., cyp = cy < n1 - 1 ? __ldg(fy + i) : 0., czp = cz < n2 - 1 ? __ldg(fz + i + plane) : 0.;
+            vzm = cmake(czm * vzm.x, czm * vzm.y); vym = cmake(cym * vym.x, cym * vym.y); vxm = cmake(cxm * vxm.x, cxm * vxm.y);
+            vxp = cmake(cxp * vxp.x, cxp * vxp.y); vyp = cmake(cyp * vyp.x, cyp * vyp.y); vzp = cmake(czp * vzp.x, czp * vzp.y);
+        }
+        c128 s = cadd(vzm, vym);
+        s = cadd(s, vxm);
+        s = cadd(s, vxp);
+        s = cadd(s, vyp);
+        s = cadd(s, vzp);
         if (dirac) {
             c128 xr = x[i];
             if (diag) { double d = __ldg(diag + i); xr = cmake(d * xr.x, d * xr.y); }
@@ -122,7 +139,8 @@ static inline bool with_rows(mgcr_op* A, F&& f, int* status, bool allow_dist = f
         HoppingOp* h = static_cast<HoppingOp*>(A);
         if (h->distributed && !allow_dist) return false;
         const int lo = h->distributed && h->ctx->rank > 0, hi = h->distributed && h->ctx->rank + 1 < h->ctx->nranks;
-        *status = f(HopRows{h->n2_local, h->gdims[1], h->gdims[2], dirac, k, diag, lo, hi, lo ? h->gdims[1] * h->gdims[2] : 0});
+        *status = f(HopRows{h->n2_local, h->gdims[1], h->gdims[2], dirac, k, diag, lo, hi, lo ? h->gdims[1] * h->gdims[2] : 0,
+                             h->var ? h->d_face[0] : nullptr, h->var ? h->d_face[1] : nullptr, h->var ? h->d_face[2] : nullptr});
         return true;
     }
     if (A->kind == OP_BLOCKCSR && !dirac) {

@@ -282,25 +282,45 @@ class Sparse(Operator):
         self.nnz = int(row[-1])
 
 
-class Hopping(Operator):
-    """Matrix-free unit-hopping operator of a Dirichlet lattice (what make_hopping + Sparse give, never stored)."""
+def _ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    return arr
 
-    def __init__(self, ctx, dims):
+
+class Hopping(Operator):
+    """Matrix-free hopping operator of a Dirichlet lattice (what make_hopping + Sparse give, never stored).
+    faces: optional list of len(dims) host arrays of n_local doubles, faces[d][i] = coefficient of the bond between site i
+    and its +1 neighbour in dim d (unit hopping when omitted).  faces_dev: the same as DEVICE pointers (ints)."""
+
+    def __init__(self, ctx, dims, faces=None, faces_dev=None):
         dims = capi.i64(dims)
         h = C.c_void_p()
-        check(ctx.lib.mgcr_hopping_create(ctx.h, len(dims), dims.ctypes.data_as(C.POINTER(C.c_int64)), None, C.byref(h)))
+        pd = dims.ctypes.data_as(C.POINTER(C.c_int64))
+        if faces_dev is not None:
+            assert len(faces_dev) == len(dims)
+            check(ctx.lib.mgcr_hopping_create_dev(ctx.h, len(dims), pd, _ptr_array([int(p) for p in faces_dev]), C.byref(h)))
+        elif faces is not None:
+            assert len(faces) == len(dims)
+            fs = [np.ascontiguousarray(f, dtype=np.float64).reshape(-1) for f in faces]
+            check(ctx.lib.mgcr_hopping_create(ctx.h, len(dims), pd, _ptr_array([f.ctypes.data for f in fs]), C.byref(h)))
+        else:
+            check(ctx.lib.mgcr_hopping_create(ctx.h, len(dims), pd, None, C.byref(h)))
         super().__init__(ctx, h)
         self.dims = [int(d) for d in dims]
 
 
 class DiracOp(Operator):
-    """DiracOp<num_type>(D, k) = 1 - k D (src/Operator.h:105-122)."""
+    """DiracOp<num_type>(D, k) = 1 - k D (src/Operator.h:105-122); diag (host array) / diag_dev (device pointer) generalise
+    the identity to a real diagonal."""
 
-    def __init__(self, ctx, D, k, diag=None):
+    def __init__(self, ctx, D, k, diag=None, diag_dev=None):
         k = complex(k)
         h = C.c_void_p()
-        d = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
-        check(ctx.lib.mgcr_dirac_create(ctx.h, D.h, k.real, k.imag, capi.ptr(d), C.byref(h)))
+        if diag_dev is not None:
+            check(ctx.lib.mgcr_dirac_create_dev(ctx.h, D.h, k.real, k.imag, C.c_void_p(int(diag_dev)), C.byref(h)))
+        else:
+            d = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
+            check(ctx.lib.mgcr_dirac_create(ctx.h, D.h, k.real, k.imag, capi.ptr(d), C.byref(h)))
         super().__init__(ctx, h, keep=(D,))
 
     def set_k(self, k):
@@ -461,27 +481,96 @@ class MG(Operator):
         self.mg = None
 
 
-def hopping_csr(dims):
-    """Host CSR of the unit-hopping matrix of a Dirichlet lattice in the reference's layout (ascending columns):
-    the synthetic operator of SURVEY.md 8(d), for feeding Sparse(...) exactly as a user of the reference would."""
+def hopping_csr(dims, faces=None):
+    """Host CSR of the hopping matrix of a Dirichlet lattice in the reference's layout (ascending columns): the synthetic
+    operator of SURVEY.md 8(d), for feeding Sparse(...) exactly as a user of the reference would.  faces (optional): per-dim
+    bond coefficients as in Hopping(...); unit hopping when omitted."""
     dims = [int(d) for d in dims]
     nd = len(dims)
     V = int(np.prod(dims))
     idx = np.arange(V, dtype=np.int64)
     stride = [int(np.prod(dims[d + 1:])) for d in range(nd)]
     coords = [(idx // stride[d]) % dims[d] for d in range(nd)]
-    cols, mask = [], []
+    cols, mask, vals = [], [], []
     for d in range(nd):
         cols.append(idx - stride[d])
         mask.append(coords[d] > 0)
+        if faces is not None:   # bond between (i - stride) and i lives with the lower site
+            vals.append(np.asarray(faces[d], dtype=np.float64).reshape(-1)[np.maximum(idx - stride[d], 0)])
     for d in range(nd - 1, -1, -1):
         cols.append(idx + stride[d])
         mask.append(coords[d] < dims[d] - 1)
+        if faces is not None:
+            vals.append(np.asarray(faces[d], dtype=np.float64).reshape(-1))
     cols = np.stack(cols, axis=1)
     mask = np.stack(mask, axis=1)
     counts = mask.sum(axis=1)
     row = np.zeros(V + 1, dtype=np.int64)
     np.cumsum(counts, out=row[1:])
     col = cols[mask]
-    val = np.ones(col.size, dtype=np.complex128)
+    if faces is None:
+        val = np.ones(col.size, dtype=np.complex128)
+    else:
+        val = np.stack(vals, axis=1)[mask].astype(np.complex128)
     return row, col.astype(np.int64), val
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Synthetic anisotropic variable-coefficient operator of BASELINE.json configs[4] (SURVEY.md 8d, C5):
+#   a_d(site) = exp(sigma * g_d(site)), g_d in [-1, 1) from a counter-based hash of (global site, d, seed) -- no rand()
+#   stream, so any slab of the lattice can be generated independently on the host or on the device;
+#   bond between site i and i+e_d: eps_d * (a_d(i) + a_d(i+e_d)) / 2; diagonal: sum of the bonds of the site + m2;
+#   A = diag - H  (DiracOp(H, 1, diag)), symmetric positive definite.
+# ----------------------------------------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def hash_unit(site, d, seed):
+    """splitmix64 finaliser of (3*site + d) + seed*golden -> double in [-1, 1).  site: int64/uint64 numpy array."""
+    with np.errstate(over="ignore"):
+        z = site.astype(np.uint64) * np.uint64(3) + np.uint64(d) + np.uint64((seed * 0x9E3779B97F4A7C15) & _M64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
+
+
+def synthetic_bonds(dims, eps=(1e-4, 1e-2, 1.0), sigma=0.5, m2=0.01, seed=12345, z_range=None):
+    """Bond arrays (dims order: slowest first) and diagonal of the C5 operator for planes z_range of the slowest dim.
+    eps is in dims order (the fastest dim carries the strong coupling).  Returns (faces[3], diag), each (nz, ny, nx)."""
+    nzg, ny, nx = [int(d) for d in dims]
+    z0, z1 = (0, nzg) if z_range is None else z_range
+    # planes z0-1 .. z1 (clamped) so that the bonds to the neighbour slabs are known
+    za, zb = max(z0 - 1, 0), min(z1 + 1, nzg)
+    zz = np.arange(za, zb, dtype=np.int64)[:, None, None]
+    site = (zz * ny + np.arange(ny, dtype=np.int64)[None, :, None]) * nx + np.arange(nx, dtype=np.int64)[None, None, :]
+    stride = (ny * nx, nx, 1)
+    faces_ext = []
+    for d in range(3):
+        a = np.exp(sigma * hash_unit(site, d, seed))
+        # coefficient at the +1 neighbour: recompute from the hash (the neighbour may lie outside the generated planes)
+        an = np.exp(sigma * hash_unit(site + stride[d], d, seed))
+        f = eps[d] * ((a + an) * 0.5)
+        # no bond leaves the lattice
+        if d == 0:
+            f[zz[:, 0, 0] == nzg - 1, :, :] = 0.0
+        elif d == 1:
+            f[:, ny - 1, :] = 0.0
+        else:
+            f[:, :, nx - 1] = 0.0
+        faces_ext.append(f)
+    lo = z0 - za
+    n = z1 - z0
+    diag = np.full((n, ny, nx), m2, dtype=np.float64)
+    fz, fy, fx = faces_ext
+    diag += fz[lo:lo + n]
+    if z0 > 0:
+        diag += fz[lo - 1:lo - 1 + n]
+    else:
+        diag[1:] += fz[lo:lo + n - 1]
+    diag += fy[lo:lo + n]
+    diag[:, 1:, :] += fy[lo:lo + n, :-1, :]
+    diag += fx[lo:lo + n]
+    diag[:, :, 1:] += fx[lo:lo + n, :, :-1]
+    faces = [np.ascontiguousarray(f[lo:lo + n]) for f in faces_ext]
+    return faces, diag

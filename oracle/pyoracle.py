@@ -53,6 +53,10 @@ def lib():
         L.orc_dirac_new.restype = C.c_void_p
         L.orc_hopping_new.argtypes = [C.c_int, _lp]
         L.orc_hopping_new.restype = C.c_void_p
+        L.orc_dirac_diag_new.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.orc_dirac_diag_new.restype = C.c_void_p
+        L.orc_hopping_var_new.argtypes = [C.c_int, _lp, C.c_void_p]
+        L.orc_hopping_var_new.restype = C.c_void_p
         L.orc_csr_nnz.argtypes = [C.c_void_p]
         L.orc_csr_nnz.restype = C.c_long
         L.orc_csr_export.argtypes = [C.c_void_p, _lp, _lp, _cp]
@@ -151,12 +155,19 @@ def csr(nrow, ncol, row, col, val):
     return Op(lib().orc_csr_new(nrow, ncol, _l(row), _l(col), _c(val)))
 
 
-def dirac(D, k):
+def dirac(D, k, diag=None):
     k = complex(k)
+    if diag is not None:
+        d = np.ascontiguousarray(diag, dtype=np.float64).reshape(-1)
+        return Op(lib().orc_dirac_diag_new(D.h, k.real, k.imag, d.ctypes.data_as(C.c_void_p)), keep=(D,))
     return Op(lib().orc_dirac_new(D.h, k.real, k.imag), keep=(D,))
 
 
-def hopping(dims):
+def hopping(dims, faces=None):
+    if faces is not None:
+        fs = [np.ascontiguousarray(f, dtype=np.float64).reshape(-1) for f in faces]
+        arr = (C.c_void_p * len(fs))(*[f.ctypes.data for f in fs])
+        return Op(lib().orc_hopping_var_new(len(dims), _l(dims), arr))
     return Op(lib().orc_hopping_new(len(dims), _l(dims)))
 
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(rank, world, port, gather_dofs):
+def main(rank, world, port, gather_dofs, mode="unit"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch
@@ -37,8 +37,15 @@ def main(rank, world, port, gather_dofs):
     sl = slice(b * plane, e * plane)
     out = {}
 
-    A = host.DiracOp(ctx, host.Hopping(ctx, dims), k)
-    A1 = host.DiracOp(single, host.Hopping(single, dims), k)
+    def make(c, m2, z_range=None):
+        """the operator of the run: I - k H (unit hopping), or the anisotropic variable-coefficient diag - H of configs[4]"""
+        if mode == "var":
+            faces, diag = host.synthetic_bonds(dims, m2=m2, z_range=z_range)
+            return host.DiracOp(c, host.Hopping(c, dims, faces=faces), 1.0, diag=diag)
+        return host.DiracOp(c, host.Hopping(c, dims), k if m2 == 0.01 else 0.12)
+
+    A = make(ctx, 0.01, (b, e))
+    A1 = make(single, 0.01)
     assert A.get_dim() == (e - b) * plane and A.global_dim() == V
     # operator apply with halo exchange
     f = single.init_rand(1, V)
@@ -56,8 +63,8 @@ def main(rank, world, port, gather_dofs):
     rhsl = ctx.init_rand(0, A.get_dim(), skip=b * plane)
     x1 = single.field(V).set_zero()
     it1, _ = host.GCR(single, A1, p).solve(rhs, x1)
-    Aw = host.DiracOp(ctx, host.Hopping(ctx, dims), 0.12)
-    Aw1 = host.DiracOp(single, host.Hopping(single, dims), 0.12)
+    Aw = make(ctx, 0.5, (b, e))
+    Aw1 = make(single, 0.5)
     x1.set_zero()
     itw1, h1 = host.GCR(single, Aw1, p).solve(rhs, x1)
     xl = ctx.field(A.get_dim()).set_zero()
@@ -67,8 +74,13 @@ def main(rank, world, port, gather_dofs):
     out["gcr_hist_rel"] = float(np.max(np.abs(hd[:m] - h1[:m]) / h1[:m]))
     out["gcr_x_rel"] = float(np.linalg.norm(xl.numpy() - x1.numpy()[sl]) / np.linalg.norm(x1.numpy()[sl]))
     # multigrid: two coarse grids, 4^3 aggregates
-    lv = [dict(site_dims=[1] + dims, sub=[1, 4, 4, 4], n_spin=1, n_col=1, n_eigen=4),
-          dict(site_dims=[1] + [d // 4 for d in dims], sub=[1, 4, 2, 2], n_spin=1, n_col=4, n_eigen=4)]
+    if mode == "var":   # line aggregates along the strongly coupled (fastest) direction first, as in bench.py's mg3d_aniso
+        lv = [dict(site_dims=[1] + dims, sub=[1, 1, 1, 8], n_spin=1, n_col=1, n_eigen=2),
+              dict(site_dims=[1, dims[0], dims[1], dims[2] // 8], sub=[1, 4, 2, 3], n_spin=1, n_col=2, n_eigen=4),
+              dict(site_dims=[1, dims[0] // 4, dims[1] // 2, 1], sub=[1, 4, 4, 1], n_spin=1, n_col=4, n_eigen=4)]
+    else:
+        lv = [dict(site_dims=[1] + dims, sub=[1, 4, 4, 4], n_spin=1, n_col=1, n_eigen=4),
+              dict(site_dims=[1] + [d // 4 for d in dims], sub=[1, 4, 2, 2], n_spin=1, n_col=4, n_eigen=4)]
     eig, coarse, smooth = host.GCR_Param(0, 10, 10, 1e-8), host.GCR_Param(0, 10, 8, 1e-2), host.GCR_Param(0, 4, 3, 1e-8)
     mg = host.MG(ctx, A, lv, eig, coarse, smooth)
     mg1 = host.MG(single, A1, lv, eig, coarse, smooth)
@@ -102,4 +114,5 @@ def main(rank, world, port, gather_dofs):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), None if sys.argv[4] == "default" else int(sys.argv[4]))
+    main(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), None if sys.argv[4] == "default" else int(sys.argv[4]),
+         sys.argv[5] if len(sys.argv) > 5 else "unit")

@@ -19,9 +19,9 @@ def ngpus():
         return 0
 
 
-def run_world(world, gather):
+def run_world(world, gather, mode="unit"):
     port = 29500 + (os.getpid() % 1000)
-    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(r), str(world), str(port), gather],
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(r), str(world), str(port), gather, mode],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     outs = [p.communicate(timeout=900)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(o[-3000:] for o in outs)
@@ -30,12 +30,13 @@ def run_world(world, gather):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["unit", "var"])   # unit hopping (configs[3]) / anisotropic variable coefficients (configs[4])
 @pytest.mark.parametrize("gather", ["default", "0"])   # default: coarse level replicated at once; 0: hierarchy stays distributed as deep as it can
 @pytest.mark.parametrize("world", [2, 4])
-def test_distributed_against_single_gpu(world, gather):
+def test_distributed_against_single_gpu(world, gather, mode):
     if ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
-    for o in run_world(world, gather):
+    for o in run_world(world, gather, mode):
         assert o["apply_exact"]                                   # halo exchange: bit-identical to the one-GPU stencil
         assert o["dot_rel"] < 1e-14
         assert abs(o["gcr_iters"][0] - o["gcr_iters"][1]) <= 1 and o["gcr_hist_rel"] < 1e-10 and o["gcr_x_rel"] < 1e-8

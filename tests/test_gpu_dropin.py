@@ -115,3 +115,15 @@ def test_reference_driver_flow(data_dir, tmp_path):
     assert float(plain.split()[-1]) < 2e-13
     mg = [ln for ln in out.splitlines() if ln.startswith("MG-GCR")][0]
     assert int(mg.split()[1]) < int(conv[0].split()[3]) and float(mg.split()[-1]) < 2e-13
+
+
+@pytest.mark.gpu
+def test_stencil_operator_through_the_cpp_classes(data_dir, tmp_path):
+    """include/mgcr/Stencil.h (matrix-free variable-coefficient operator) against the same entries held as a Sparse"""
+    out = run(os.path.join(ROOT, "examples", "_build", "stencil_gcr"), data_dir, str(tmp_path))
+    kv = {ln.split()[0]: ln.split()[1:] for ln in out.splitlines() if ln.strip()}
+    assert "DONE" in kv
+    assert float(kv["APPLY_REL"][0]) < 1e-15
+    d, off_x, off_y = (float(v) for v in kv["VAL_AT"])
+    assert d > 0.5 and -1.4 < off_x < -0.6 and -0.014 < off_y < -0.006
+    assert float(kv["TRUE_RESIDUAL"][0]) < 1.2e-10
