@@ -101,7 +101,9 @@ struct mgcr_ctx {
     int64_t small_gcr_rows = (int64_t)1 << 19;   // operators up to this many rows: whole GCR solve in one persistent kernel
     int64_t gather_dofs = (int64_t)1 << 18;      // distributed coarse systems up to this size are replicated on every rank
     int dot_tma = 1;                              // TMA-staged batched inner products for long vectors
-    int hopping_kernel = 1;                       // matrix-free stencil: 1 = register-marching / L1 form, 0 = shared-memory tile form
+    int hopping_kernel = 2;                       // matrix-free stencil: 2 = TMA-staged ring (lattices of >= hopping_tma_rows sites, else form 1),
+                                                  // 1 = register-marching / L1 form, 0 = shared-memory tile form
+    int64_t hopping_tma_rows = (int64_t)1 << 19;
     void* nccl_comm = nullptr;
     void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
     int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,

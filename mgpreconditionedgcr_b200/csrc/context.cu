@@ -105,6 +105,7 @@ extern "C" int mgcr_ctx_create(int device, mgcr_ctx** out) {
     if (getenv("MGCR_GATHER_DOFS")) c->gather_dofs = atoll(getenv("MGCR_GATHER_DOFS"));
     if (getenv("MGCR_DOT_TMA")) c->dot_tma = atoi(getenv("MGCR_DOT_TMA"));
     if (getenv("MGCR_HOPPING_KERNEL")) c->hopping_kernel = atoi(getenv("MGCR_HOPPING_KERNEL"));
+    if (getenv("MGCR_HOPPING_TMA_ROWS")) c->hopping_tma_rows = atoll(getenv("MGCR_HOPPING_TMA_ROWS"));
     if (getenv("MGCR_HALO_OVERLAP")) c->halo_overlap = atoi(getenv("MGCR_HALO_OVERLAP"));
     *out = c;
     return MGCR_OK;
@@ -116,6 +117,7 @@ extern "C" int mgcr_ctx_set_option(mgcr_ctx* c, const char* key, int64_t value) 
     else if (!strcmp(key, "gather_dofs")) c->gather_dofs = value;
     else if (!strcmp(key, "dot_tma")) c->dot_tma = (int)value;
     else if (!strcmp(key, "hopping_kernel")) c->hopping_kernel = (int)value;
+    else if (!strcmp(key, "hopping_tma_rows")) c->hopping_tma_rows = value;
     else if (!strcmp(key, "halo_overlap")) c->halo_overlap = (int)value;
     else { mgcr_set_error("mgcr_ctx_set_option: unknown option '%s'", key); return MGCR_ERR_ARG; }
     return MGCR_OK;

@@ -293,13 +293,22 @@ __global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx)
 // on a block-wide barrier, and the bytes in flight per SM are stages x tile, independent of the compiler's load scheduling
 // (the register-marching form has one HBM-bound load per thread in flight and sits at 0.63 of the copy peak).
 // The operand is described as doubles (2 per element) because the tensor-map element types stop at 8 bytes.
-template <int TX, int TY>
+template <int TX, int TY, bool VAR>
 struct HopTmaCfg {
     static constexpr int CONSUMERS = TX * TY;
     static constexpr int THREADS = CONSUMERS + 32;
     static constexpr int ROW = TX + 2;
-    static constexpr int TILE = ROW * (TY + 2);                       // c128 per stage
-    static constexpr int STAGE_BYTES = ((TILE * 16 + 127) / 128) * 128;
+    static constexpr int TILE = ROW * (TY + 2);                       // c128 of the operand per stage
+    static constexpr int X_BYTES = ((TILE * 16 + 127) / 128) * 128;
+    // variable coefficients: the stage also carries the plane's bonds and diagonal (doubles)
+    static constexpr int FZ_OFF = X_BYTES;                            // TX x TY       bond to the plane below
+    static constexpr int FY_OFF = FZ_OFF + TX * TY * 8;               // TX x (TY+1)   rows y0-1 .. y0+TY-1
+    static constexpr int FXW = TX + 4;                                // columns x0-2 .. x0+TX+1: the box starts on a 16-byte boundary and its rows
+                                                                      // are a multiple of 32 bytes (a 66-double box starting at x0-1 traps on B200)
+    static constexpr int FX_OFF = FY_OFF + TX * (TY + 1) * 8;         // FXW x TY
+    static constexpr int DG_OFF = FX_OFF + FXW * TY * 8;              // TX x TY       diagonal
+    static constexpr int STAGE_BYTES = VAR ? DG_OFF + TX * TY * 8 : X_BYTES;
+    static_assert(!VAR || (FY_OFF % 128 == 0 && FX_OFF % 128 == 0 && DG_OFF % 128 == 0 && STAGE_BYTES % 128 == 0), "TMA destinations are 128-byte aligned");
 };
 enum { HOP_TMA_MAX_STAGES = 12 };
 
@@ -311,10 +320,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int TX, int TY>
-__global__ void __launch_bounds__(HopTmaCfg<TX, TY>::THREADS, 2) k_hopping_tma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_lo,
-                                                                              const __grid_constant__ CUtensorMap map_hi, HopArgs a, int stages) {
-    typedef HopTmaCfg<TX, TY> C;
+struct HopMaps { CUtensorMap x, lo, hi, fz, fy, fx, dg; };
+
+template <int TX, int TY, bool VAR>
+__global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_tma(const __grid_constant__ HopMaps maps, HopArgs a, int stages, int dbg_skip) {
+    typedef HopTmaCfg<TX, TY, VAR> C;
     extern __shared__ unsigned char hop_smem_raw[];
     __shared__ __align__(8) uint64_t full[HOP_TMA_MAX_STAGES], empty[HOP_TMA_MAX_STAGES];
     unsigned char* ring = (unsigned char*)(((uintptr_t)hop_smem_raw + 127) & ~(uintptr_t)127);
@@ -322,6 +332,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY>::THREADS, 2) k_hopping_tma(c
     const int64_t zs = a.z_lo + (int64_t)blockIdx.z * a.zc;
     const int64_t ze = min(zs + a.zc, a.z_hi);
     const int nplanes = (int)(ze - zs) + 2;                            // planes zs-1 .. ze
+    const bool use_diag = VAR && a.dirac && a.diag;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], C::CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -330,16 +341,31 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY>::THREADS, 2) k_hopping_tma(c
     if (threadIdx.x >= C::CONSUMERS) {
         // ---- producer: one elected thread of the last warp ----
         if (threadIdx.x == C::CONSUMERS) {
+            uint32_t tx_bytes = (uint32_t)(C::TILE * 16) + (VAR ? (uint32_t)(C::DG_OFF - C::FZ_OFF) + (use_diag ? (uint32_t)(TX * TY * 8) : 0u) : 0u);
+            if (VAR && (dbg_skip & 1)) tx_bytes -= TX * TY * 8;
+            if (VAR && (dbg_skip & 2)) tx_bytes -= TX * (TY + 1) * 8;
+            if (VAR && (dbg_skip & 4)) tx_bytes -= C::FXW * TY * 8;
+            if (use_diag && (dbg_skip & 8)) tx_bytes -= TX * TY * 8;
             for (int p = 0; p < nplanes; p++) {
                 const int s = p % stages;
                 if (p >= stages) mbar_wait(&empty[s], (uint32_t)((p / stages - 1) & 1));
                 const int64_t z = zs - 1 + p;
-                const CUtensorMap* m = &map_x;
+                const CUtensorMap* m = &maps.x;
                 int zc = (int)z;                                       // z = -1 / n2 without a slab neighbour: out of range, zero-filled
-                if (z < 0 && a.halo_lo) { m = &map_lo; zc = 0; }
-                else if (z >= a.n2 && a.halo_hi) { m = &map_hi; zc = 0; }
-                mbar_expect_tx(&full[s], (uint32_t)(C::TILE * 16));
-                tma_load_3d(ring + (size_t)s * C::STAGE_BYTES, m, (int)(2 * (x0 - 1)), (int)(y0 - 1), zc, &full[s]);
+                if (z < 0 && a.halo_lo) { m = &maps.lo; zc = 0; }
+                else if (z >= a.n2 && a.halo_hi) { m = &maps.hi; zc = 0; }
+                unsigned char* st = ring + (size_t)s * C::STAGE_BYTES;
+                mbar_expect_tx(&full[s], tx_bytes);
+                tma_load_3d(st, m, (int)(2 * (x0 - 1)), (int)(y0 - 1), zc, &full[s]);
+                if (VAR) {
+                    // bonds below the plane exist for z = 0 .. n2 (n2+1 planes); in-plane bonds and the diagonal only for the
+                    // planes that are computed -- neighbour planes get an out-of-range coordinate (zero fill, no traffic)
+                    const int zin = (z >= 0 && z < a.n2) ? (int)z : -1;
+                    if (!(dbg_skip & 1)) tma_load_3d(st + C::FZ_OFF, &maps.fz, (int)x0, (int)y0, (int)z, &full[s]);
+                    if (!(dbg_skip & 2)) tma_load_3d(st + C::FY_OFF, &maps.fy, (int)x0, (int)(y0 - 1), zin, &full[s]);
+                    if (!(dbg_skip & 4)) tma_load_3d(st + C::FX_OFF, &maps.fx, (int)(x0 - 2), (int)y0, zin, &full[s]);
+                    if (use_diag && !(dbg_skip & 8)) tma_load_3d(st + C::DG_OFF, &maps.dg, (int)x0, (int)y0, zin, &full[s]);
+                }
             }
         }
         return;
@@ -348,38 +374,62 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY>::THREADS, 2) k_hopping_tma(c
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, lane = threadIdx.x & 31;
     const int64_t gx = x0 + tx, gy = y0 + ty;
     const bool inb = gx < a.n0 && gy < a.n1;
+    const bool xp = gx + 1 < a.n0, yp = gy + 1 < a.n1;
     const int64_t plane = a.n1 * a.n0;
     const int64_t c_off = gy * a.n0 + gx;
     const int ctr = (ty + 1) * C::ROW + tx + 1;
-    auto tile = [&](int p) -> const c128* { return (const c128*)(ring + (size_t)(p % stages) * C::STAGE_BYTES); };
+    auto stage = [&](int p) -> const unsigned char* { return ring + (size_t)(p % stages) * C::STAGE_BYTES; };
     mbar_wait(&full[0], 0);
-    c128 prev = tile(0)[ctr];
+    c128 prev = ((const c128*)stage(0))[ctr];
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[0]);
     mbar_wait(&full[1 % stages], (uint32_t)((1 / stages) & 1));
-    c128 cur = tile(1)[ctr];
+    c128 cur = ((const c128*)stage(1))[ctr];
+    double fzm = 0.;
+    if (VAR) fzm = ((const double*)(stage(1) + C::FZ_OFF))[ty * TX + tx];
     for (int p = 1; p + 1 < nplanes; p++) {
         const int64_t z = zs - 1 + p;
         mbar_wait(&full[(p + 1) % stages], (uint32_t)(((p + 1) / stages) & 1));
-        const c128 next = tile(p + 1)[ctr];
-        const c128* t = tile(p);
-        c128 s = cadd(prev, t[ctr - C::ROW]);
-        s = cadd(s, t[ctr - 1]);
-        s = cadd(s, t[ctr + 1]);
-        s = cadd(s, t[ctr + C::ROW]);
-        s = cadd(s, next);
+        const unsigned char* sn = stage(p + 1);
+        const unsigned char* sc = stage(p);
+        const c128 next = ((const c128*)sn)[ctr];
+        const c128* t = (const c128*)sc;
+        c128 vzm = prev, vym = t[ctr - C::ROW], vxm = t[ctr - 1], vxp = t[ctr + 1], vyp = t[ctr + C::ROW], vzp = next;
+        double fzp = 0., dg = 1.;
+        if (VAR) {
+            const double* fy = (const double*)(sc + C::FY_OFF);
+            const double* fx = (const double*)(sc + C::FX_OFF);
+            fzp = ((const double*)(sn + C::FZ_OFF))[ty * TX + tx];
+            const double cym = fy[ty * TX + tx];                      // row y-1 (zero-filled below the lattice)
+            const double cyp = yp ? fy[(ty + 1) * TX + tx] : 0.;
+            const double cxm = fx[ty * C::FXW + tx + 1];              // column x-1 (zero-filled left of the lattice)
+            const double cxp = xp ? fx[ty * C::FXW + tx + 2] : 0.;
+            if (use_diag) dg = ((const double*)(sc + C::DG_OFF))[ty * TX + tx];
+            vzm = cmake(fzm * vzm.x, fzm * vzm.y);
+            vym = cmake(cym * vym.x, cym * vym.y);
+            vxm = cmake(cxm * vxm.x, cxm * vxm.y);
+            vxp = cmake(cxp * vxp.x, cxp * vxp.y);
+            vyp = cmake(cyp * vyp.x, cyp * vyp.y);
+            vzp = cmake(fzp * vzp.x, fzp * vzp.y);
+        }
+        c128 s = cadd(vzm, vym);
+        s = cadd(s, vxm);
+        s = cadd(s, vxp);
+        s = cadd(s, vyp);
+        s = cadd(s, vzp);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[p % stages]);               // this warp is done with plane z's stage
         if (inb) {
             if (a.dirac) {
                 c128 xr = cur;
-                if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
+                if (VAR) { if (use_diag) xr = cmake(dg * xr.x, dg * xr.y); }
+                else if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
                 s = csub(xr, cmul(a.k, s));
             }
             if (a.bsub) s = csub(__ldg(a.bsub + z * plane + c_off), s);
             st_stream(a.y + z * plane + c_off, s);
         }
-        prev = cur; cur = next;
+        prev = cur; cur = next; fzm = fzp;
     }
 }
 
@@ -394,48 +444,58 @@ static tensor_map_encode_fn tensor_map_encoder() {
     }();
     return fn;
 }
-// tensor map of `planes` planes of n1 x n0 c128 at `base`, box (tx+2) x (ty+2) x 1, out-of-range elements read as zero
-static int hop_tensor_map(CUtensorMap* m, const c128* base, int64_t n0, int64_t n1, int64_t planes, int tx, int ty) {
+// tensor map over `planes` planes of n1 rows of `inner` doubles at `base`, box box0 x box1 x 1, out-of-range elements read as zero
+static int hop_tensor_map(CUtensorMap* m, const void* base, int64_t inner, int64_t n1, int64_t planes, int box0, int box1) {
     tensor_map_encode_fn enc = tensor_map_encoder();
     if (!enc) { mgcr_set_error("cuTensorMapEncodeTiled is not available from this driver"); return MGCR_ERR_CUDA; }
-    const cuuint64_t gdim[3] = {(cuuint64_t)(2 * n0), (cuuint64_t)n1, (cuuint64_t)planes};
-    const cuuint64_t gstride[2] = {(cuuint64_t)(16 * n0), (cuuint64_t)(16 * n0 * n1)};
-    const cuuint32_t box[3] = {(cuuint32_t)(2 * (tx + 2)), (cuuint32_t)(ty + 2), 1};
+    const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)n1, (cuuint64_t)planes};
+    const cuuint64_t gstride[2] = {(cuuint64_t)(8 * inner), (cuuint64_t)(8 * inner * n1)};
+    const cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
     const cuuint32_t estride[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { mgcr_set_error("cuTensorMapEncodeTiled failed (%d) for a %lld x %lld x %lld lattice", (int)r, (long long)planes, (long long)n1, (long long)n0); return MGCR_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { mgcr_set_error("cuTensorMapEncodeTiled failed (%d) for %lld planes of %lld x %lld doubles", (int)r, (long long)planes, (long long)n1, (long long)inner); return MGCR_ERR_CUDA; }
     return MGCR_OK;
 }
 
-template <int TX, int TY>
+template <int TX, int TY, bool VAR>
 static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_t z_hi, const char* name, double bytes) {
-    typedef HopTmaCfg<TX, TY> C;
+    typedef HopTmaCfg<TX, TY, VAR> C;
     HopArgs a = a0;
     static const int stages_env = getenv("MGCR_HOP_STAGES") ? atoi(getenv("MGCR_HOP_STAGES")) : 0;   // experiment knobs
     static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;
-    const int stages = std::max(3, std::min((int)HOP_TMA_MAX_STAGES, stages_env > 0 ? stages_env : 6));
+    static const int dbg_skip = getenv("MGCR_HOP_SKIP") ? atoi(getenv("MGCR_HOP_SKIP")) : 0;   // debugging: leave bond tiles out
+    // two CTAs per SM (registers); the ring takes what shared memory allows: 8 planes of the operand tile in flight per CTA
+    // saturate HBM (profiles/r01_stencil_tma_sweep.txt), 4 with the bond / diagonal tiles riding along
+    const int stages_max = std::min((int)HOP_TMA_MAX_STAGES, (int)((111 * 1024 - 128) / C::STAGE_BYTES));
+    const int stages = std::max(3, std::min(stages_max, stages_env > 0 ? stages_env : 8));
     const size_t smem = (size_t)stages * C::STAGE_BYTES + 128;
-    CUtensorMap mx, mlo, mhi;
-    MGCR_TRY(hop_tensor_map(&mx, a.x, a.n0, a.n1, a.n2, TX, TY));
-    mlo = mx; mhi = mx;
-    if (a.halo_lo) MGCR_TRY(hop_tensor_map(&mlo, a.halo_lo, a.n0, a.n1, 1, TX, TY));
-    if (a.halo_hi) MGCR_TRY(hop_tensor_map(&mhi, a.halo_hi, a.n0, a.n1, 1, TX, TY));
+    HopMaps maps;
+    MGCR_TRY(hop_tensor_map(&maps.x, a.x, 2 * a.n0, a.n1, a.n2, 2 * (TX + 2), TY + 2));
+    maps.lo = maps.x; maps.hi = maps.x; maps.fz = maps.x; maps.fy = maps.x; maps.fx = maps.x; maps.dg = maps.x;
+    if (a.halo_lo) MGCR_TRY(hop_tensor_map(&maps.lo, a.halo_lo, 2 * a.n0, a.n1, 1, 2 * (TX + 2), TY + 2));
+    if (a.halo_hi) MGCR_TRY(hop_tensor_map(&maps.hi, a.halo_hi, 2 * a.n0, a.n1, 1, 2 * (TX + 2), TY + 2));
+    if (VAR) {
+        MGCR_TRY(hop_tensor_map(&maps.fz, a.fz, a.n0, a.n1, a.n2 + 1, TX, TY));
+        MGCR_TRY(hop_tensor_map(&maps.fy, a.fy, a.n0, a.n1, a.n2, TX, TY + 1));
+        MGCR_TRY(hop_tensor_map(&maps.fx, a.fx, a.n0, a.n1, a.n2, C::FXW, TY));
+        if (a.dirac && a.diag) MGCR_TRY(hop_tensor_map(&maps.dg, a.diag, a.n0, a.n1, a.n2, TX, TY));
+    }
     static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_hopping_tma<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HOP_TMA_MAX_STAGES * C::STAGE_BYTES + 128))); attr_set = true; }
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_hopping_tma<TX, TY, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024)); attr_set = true; }
     const int64_t nz = z_hi - z_lo;
     dim3 grid((unsigned)((a.n0 + TX - 1) / TX), (unsigned)((a.n1 + TY - 1) / TY), 1);
     // chunks of planes: enough CTAs for ~8 waves of the resident set (the last, partial wave is the tail), but chunks of
     // at least 16 planes (each chunk re-reads its two boundary planes)
     const int64_t tiles = (int64_t)grid.x * grid.y;
-    const int64_t resident = (int64_t)ctx->num_sms * std::max<int64_t>(1, std::min<int64_t>(2, (int64_t)(220 * 1024) / (int64_t)smem));   // 2 CTAs per SM by registers
+    const int64_t resident = (int64_t)ctx->num_sms * 2;
     int64_t nchunks = std::max<int64_t>(1, (8 * resident + tiles - 1) / tiles);
     a.zc = std::max<int64_t>((nz + nchunks - 1) / nchunks, std::min<int64_t>(16, nz));
     if (zc_env > 0) a.zc = std::min<int64_t>(zc_env, nz);
     grid.z = (unsigned)((nz + a.zc - 1) / a.zc);
     ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
     a.z_lo = z_lo; a.z_hi = z_hi;
-    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY><<<grid, C::THREADS, smem, ctx->stream>>>(mx, mlo, mhi, a, stages)));
+    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY, VAR><<<grid, C::THREADS, smem, ctx->stream>>>(maps, a, stages, dbg_skip)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -473,23 +533,25 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
         MGCR_TRY(dist_halo_end(ctx));
     }
     if (n_local == 0) return dist_halo_wait(ctx);
-    const bool l1_form = ctx->hopping_kernel == 1 || var;   // the tile kernel is unit-hopping only
+    const bool l1_form = ctx->hopping_kernel != 0 || var;   // the tile kernel is unit-hopping only
     int hl_tx = 32;
     static const int hl_tx_max = getenv("MGCR_HL_TX") ? std::min(atoi(getenv("MGCR_HL_TX")), (int)HL_THREADS) : (int)HL_THREADS;   // experiment knob
     while (hl_tx < hl_tx_max && hl_tx * 2 <= a.n0) hl_tx *= 2;
     const int tx = l1_form ? hl_tx : (int)HOP_TX, ty = l1_form ? HL_THREADS / hl_tx : (int)HOP_TY;
     static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;   // experiment knob
     const double bytes_per_plane = (apply_bytes() + (diag ? 8. * n_local : 0.) + (bsub ? 16. * n_local : 0.)) / (double)a.n2;
-    // TMA-staged form: unit hopping on lattices at least one tile wide (narrower ones are latency-bound anyway)
+    // TMA-staged form on lattices at least one tile wide with enough sites to fill the machine (small ones are latency-bound
+    // and the register-marching form starts faster: 11 us against 13 us at 40 x 33 x 130)
     static const int tma_tile_env = getenv("MGCR_HOP_TILE") ? atoi(getenv("MGCR_HOP_TILE")) : 0;   // experiment knob: 1 = 32 x 16 tile
-    const bool tma_form = ctx->hopping_kernel == 2 && !var && a.n0 >= 64 && a.n1 >= 8;
+    const bool tma_form = ctx->hopping_kernel == 2 && a.n0 >= 64 && a.n1 >= 8 && (!var || d_face[1]) && n_local >= ctx->hopping_tma_rows;
     auto launch = [&](int64_t z_lo, int64_t z_hi) -> int {   // planes [z_lo, z_hi)
         if (z_hi <= z_lo) return MGCR_OK;
         const int64_t nz = z_hi - z_lo;
         if (tma_form) {
+            if (var) return hop_tma_launch<64, 8, true>(ctx, a, z_lo, z_hi, dirac ? "hopping_var_dirac" : "hopping_var", bytes_per_plane * nz);
             const char* nm = dirac ? "hopping_dirac" : "hopping";
-            return tma_tile_env == 1 ? hop_tma_launch<32, 16>(ctx, a, z_lo, z_hi, nm, bytes_per_plane * nz)
-                                     : hop_tma_launch<64, 8>(ctx, a, z_lo, z_hi, nm, bytes_per_plane * nz);
+            return tma_tile_env == 1 ? hop_tma_launch<32, 16, false>(ctx, a, z_lo, z_hi, nm, bytes_per_plane * nz)
+                                     : hop_tma_launch<64, 8, false>(ctx, a, z_lo, z_hi, nm, bytes_per_plane * nz);
         }
         dim3 grid((unsigned)((a.n0 + tx - 1) / tx), (unsigned)((a.n1 + ty - 1) / ty), 1);
         int64_t tiles = (int64_t)grid.x * grid.y;

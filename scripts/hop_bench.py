@@ -12,12 +12,18 @@ from mgpreconditionedgcr_b200 import host  # noqa: E402
 kernel = int(sys.argv[1])
 lattices = [[int(v) for v in a.split("x")] for a in sys.argv[2:]] or [[256, 256, 256]]
 ctx = host.Context(0)
-tag = "kernel=%d stages=%s zc=%s tile=%s" % (kernel, os.environ.get("MGCR_HOP_STAGES", "-"), os.environ.get("MGCR_HOP_ZC", "-"), os.environ.get("MGCR_HOP_TILE", "-"))
+tag = ("var " if os.environ.get("HOP_VAR") else "") + "kernel=%d stages=%s zc=%s tile=%s" % (kernel, os.environ.get("MGCR_HOP_STAGES", "-"), os.environ.get("MGCR_HOP_ZC", "-"), os.environ.get("MGCR_HOP_TILE", "-"))
 for dims in lattices:
     V = int(np.prod(dims))
     x = ctx.init_rand(1, V)
     ctx.set_option("hopping_kernel", kernel)
-    A = host.DiracOp(ctx, host.Hopping(ctx, dims), 1.0 / 6.01)
+    cls = "hopping_dirac"
+    if os.environ.get("HOP_VAR"):   # variable bonds + diagonal (random values: only the traffic matters here)
+        rng = np.random.default_rng(1)
+        A = host.DiracOp(ctx, host.Hopping(ctx, dims, faces=[0.5 + rng.random(V) for _ in dims]), 1.0, diag=6.0 + rng.random(V))
+        cls = "hopping_var_dirac"
+    else:
+        A = host.DiracOp(ctx, host.Hopping(ctx, dims), 1.0 / 6.01)
     y = ctx.field(V)
     for _ in range(3):
         A(x, out=y)
@@ -28,7 +34,7 @@ for dims in lattices:
     ctx.sync()
     prof = ctx.profile()
     ctx.set_profile(False)
-    p = prof["hopping_dirac"]
+    p = prof[cls]
     line = "%s %s: %.1f us %.0f GB/s" % (tag, "x".join(map(str, dims)), 1e3 * p["ms"] / p["calls"], p["bytes"] / (p["ms"] * 1e-3) / 1e9)
     if kernel != 1 and V <= 2 ** 25:
         ctx.set_option("hopping_kernel", 1)

@@ -52,6 +52,23 @@ def main(rank, world, port, gather_dofs, mode="unit"):
     fl = ctx.init_rand(1, A.get_dim(), skip=b * plane)
     assert np.array_equal(fl.numpy(), f.numpy()[sl])
     out["apply_exact"] = bool(np.array_equal(A(fl).numpy(), A1(f).numpy()[sl]))
+    # the TMA-staged stencil form with the neighbour planes coming from the halo buffers (lattice wide enough for its tiles)
+    dims_w = [16 * world, 24, 72]
+    pw = dims_w[1] * dims_w[2]
+    for c in (ctx, single):
+        c.set_option("hopping_tma_rows", 0)
+    if mode == "var":
+        fw, dw = host.synthetic_bonds(dims_w, m2=0.3)
+        Aw_t = host.DiracOp(ctx, host.Hopping(ctx, dims_w, faces=[q[b // 2:e // 2] for q in fw]), 1.0, diag=dw[b // 2:e // 2])
+        Aw_1 = host.DiracOp(single, host.Hopping(single, dims_w, faces=fw), 1.0, diag=dw)
+    else:
+        Aw_t = host.DiracOp(ctx, host.Hopping(ctx, dims_w), k)
+        Aw_1 = host.DiracOp(single, host.Hopping(single, dims_w), k)
+    fw1 = single.init_rand(7, int(np.prod(dims_w)))
+    fwl = ctx.init_rand(7, Aw_t.get_dim(), skip=(b // 2) * pw)
+    out["apply_tma_exact"] = bool(np.array_equal(Aw_t(fwl).numpy(), Aw_1(fw1).numpy()[(b // 2) * pw:(e // 2) * pw]))
+    for c in (ctx, single):
+        c.set_option("hopping_tma_rows", 1 << 19)
     # all-reduced inner products
     g = single.init_rand(3, V)
     gl = ctx.init_rand(3, A.get_dim(), skip=b * plane)

@@ -37,7 +37,7 @@ def test_distributed_against_single_gpu(world, gather, mode):
     if ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     for o in run_world(world, gather, mode):
-        assert o["apply_exact"]                                   # halo exchange: bit-identical to the one-GPU stencil
+        assert o["apply_exact"] and o["apply_tma_exact"]          # halo exchange: bit-identical to the one-GPU stencil (both kernel forms)
         assert o["dot_rel"] < 1e-14
         assert abs(o["gcr_iters"][0] - o["gcr_iters"][1]) <= 1 and o["gcr_hist_rel"] < 1e-10 and o["gcr_x_rel"] < 1e-8
         assert o["nblocks"][0] * world == o["nblocks"][1]

@@ -181,6 +181,7 @@ def test_tma_staged_stencil_is_bit_exact(ctx, host, orc, dims):
     x = orc.init_rand(3, n)
     Ho = orc.hopping(dims)
     ctx.set_option("hopping_kernel", 2)
+    ctx.set_option("hopping_tma_rows", 0)
     try:
         H = host.Hopping(ctx, dims)
         assert np.array_equal(H(x), Ho(x))
@@ -188,8 +189,18 @@ def test_tma_staged_stencil_is_bit_exact(ctx, host, orc, dims):
         assert np.array_equal(host.DiracOp(ctx, H, k)(x), orc.dirac(Ho, k)(x))
         diag = 1.0 + np.random.default_rng(8).random(n)
         assert np.array_equal(host.DiracOp(ctx, H, 0.2, diag=diag)(x), orc.dirac(Ho, 0.2, diag)(x))
-    finally:
+        # variable bonds + diagonal ride along in the same ring
+        faces = [0.25 + np.random.default_rng(9 + d).random(n) for d in range(3)]
+        Hv, Hvo = host.Hopping(ctx, dims, faces=faces), orc.hopping(dims, faces)
+        assert np.array_equal(Hv(x), Hvo(x))
+        assert np.array_equal(host.DiracOp(ctx, Hv, 1.0, diag=diag)(x), orc.dirac(Hvo, 1.0, diag)(x))
+        assert np.array_equal(host.DiracOp(ctx, Hv, k)(x), orc.dirac(Hvo, k)(x))
+        # and it agrees with the register-marching form it replaces
         ctx.set_option("hopping_kernel", 1)
+        assert np.array_equal(host.DiracOp(ctx, Hv, 1.0, diag=diag)(x), orc.dirac(Hvo, 1.0, diag)(x))
+    finally:
+        ctx.set_option("hopping_kernel", 2)
+        ctx.set_option("hopping_tma_rows", 1 << 19)
 
 
 def test_dirac_with_diagonal(ctx, host, orc):
