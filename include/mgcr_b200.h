@@ -67,7 +67,8 @@ int mgcr_ctx_get_profile(mgcr_ctx* ctx, int cap, const char** names, double* ms,
  * "gather_dofs" (distributed coarse systems up to this size are replicated on every rank, default 2^18),
  * "dot_tma" (1 = TMA-staged batched inner products on long vectors, default 1), "hopping_kernel" (2 = planes staged through
  * shared memory by TMA tensor copies for lattices of at least "hopping_tma_rows" sites (default 2^19), 1 = register-marching
- * stencil kernel, 0 = shared-memory tile kernel), "halo_overlap" (1 = halo exchange on a second stream / communicator while
+ * stencil kernel, 0 = shared-memory tile kernel), "blockcsr_ring_rows" (block-CSR operators with ne = 2, 4, 8 and at least
+ * this many rows are applied from their sliced image streamed through a shared-memory ring of bulk copies, default 2^18), "halo_overlap" (1 = halo exchange on a second stream / communicator while
  * interior rows are computed, default 0: measured no gain) */
 int mgcr_ctx_set_option(mgcr_ctx* ctx, const char* key, int64_t value);
 

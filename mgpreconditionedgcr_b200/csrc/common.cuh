@@ -104,6 +104,7 @@ struct mgcr_ctx {
     int hopping_kernel = 2;                       // matrix-free stencil: 2 = TMA-staged ring (lattices of >= hopping_tma_rows sites, else form 1),
                                                   // 1 = register-marching / L1 form, 0 = shared-memory tile form
     int64_t hopping_tma_rows = (int64_t)1 << 19;
+    int64_t blockcsr_ring_rows = (int64_t)1 << 18;   // block-CSR operators (ne = 2, 4, 8) of at least this many rows stream through the bulk-copy ring
     void* nccl_comm = nullptr;
     void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
     int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,

@@ -118,6 +118,7 @@ extern "C" int mgcr_ctx_set_option(mgcr_ctx* c, const char* key, int64_t value) 
     else if (!strcmp(key, "dot_tma")) c->dot_tma = (int)value;
     else if (!strcmp(key, "hopping_kernel")) c->hopping_kernel = (int)value;
     else if (!strcmp(key, "hopping_tma_rows")) c->hopping_tma_rows = value;
+    else if (!strcmp(key, "blockcsr_ring_rows")) c->blockcsr_ring_rows = value;
     else if (!strcmp(key, "halo_overlap")) c->halo_overlap = (int)value;
     else { mgcr_set_error("mgcr_ctx_set_option: unknown option '%s'", key); return MGCR_ERR_ARG; }
     return MGCR_OK;

@@ -803,8 +803,211 @@ __global__ void __launch_bounds__(256) k_blockcsr_apply_ne(int64_t nb, const int
     st_stream(y + t, value);
 }
 
+// Sliced streaming image (see BlockCsrOp) applied by a persistent kernel: one CTA per SM, warp i of the CTA owns ring stage i; slices
+// are dealt round-robin over all warps of the grid.  A slice (a contiguous blob: per block slot NE*32
+// values + 32/NE columns) is fetched into the stage by ONE 1-D bulk copy (cp.async.bulk completing on the stage's
+// mbarrier) that the warp issues itself as soon as it has finished with the previous blob.  While the copy is in flight
+// the warp gathers the x blocks of that slice through L1/L2 -- the column indices were read one slice ahead -- so the
+// DRAM latency of the matrix stream and the L2 latency of the gathers overlap instead of adding up (the first ring
+// version, with a producer thread and gathers after the arrival, spent 53 % of its stall samples waiting for refills:
+// profiles/r01_ncu_blockcsr_ring.md).  The DRAM stream is as deep as the ring: nst blobs per SM.
+// Accumulation order per row is that of k_blockcsr_apply_ne; the padding blocks add exact zeros.
+template <int NE> struct RingCfg {
+    static constexpr int PRE = NE == 8 ? 2 : 4;                         // block slots whose x gathers are issued before the blob arrives
+    static constexpr int MAX_STAGES = NE == 2 ? 26 : 14;                 // = warps per CTA (ne = 2: 7.6 KB blobs, more of them in flight)
+    static constexpr int MAX_THREADS = 32 * MAX_STAGES;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int NE>
+__global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(int64_t nb, int64_t nslices, const int64_t* __restrict__ sl_ptr,
+                                                                                const unsigned char* __restrict__ blob, const c128* __restrict__ x,
+                                                                                const c128* __restrict__ ghost, int64_t nb_local_cols,
+                                                                                const c128* __restrict__ bsub, c128* __restrict__ y, int nst, int stage_bytes) {
+    constexpr int S = 32 / NE;
+    constexpr int SLOT = NE * 512 + S * 4;                 // bytes per block slot: NE columns x 32 lanes of c128, then S int32 columns
+    constexpr int PRE = RingCfg<NE>::PRE;
+    extern __shared__ unsigned char ring_raw[];
+    __shared__ __align__(8) uint64_t full[RingCfg<NE>::MAX_STAGES];
+    unsigned char* ring = (unsigned char*)(((uintptr_t)ring_raw + 127) & ~(uintptr_t)127);
+    // slices are dealt round-robin over (CTA, warp): at any time the whole machine streams one window of gridDim.x * nst
+    // consecutive slices (148 distant sequential streams, one per CTA, reached only 5.6 TB/s)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t s_end = nslices, stride = (int64_t)gridDim.x * nst;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nst; i++) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int rin = lane / NE;
+    unsigned char* stage = ring + (size_t)warp * stage_bytes;
+    auto fetch = [&](int64_t base, int w) {                // lane 0: start the copy of a slice into this warp's stage
+        mbar_expect_tx(&full[warp], (uint32_t)w * SLOT);
+        if (w) tma_load_1d(stage, blob + base * SLOT, (uint32_t)w * SLOT, &full[warp]);
+    };
+    auto load_cols = [&](int64_t base, int w, int32_t (&col)[PRE]) {
+#pragma unroll
+        for (int i = 0; i < PRE; i++) col[i] = i < w ? __ldg((const int32_t*)(blob + (base + i) * SLOT + NE * 512) + rin) : 0;
+    };
+    int64_t s = (int64_t)blockIdx.x * nst + warp;
+    int64_t base = 0; int w = 0;
+    int32_t col[PRE];
+    if (s < s_end) {
+        base = __ldg(sl_ptr + s);
+        w = (int)(__ldg(sl_ptr + s + 1) - base);
+        if (lane == 0) fetch(base, w);
+    }
+    load_cols(base, w, col);
+    uint32_t parity = 0;
+    for (; s < s_end; s += stride) {
+        // x blocks of the first PRE slots: in flight together with the blob
+        c128 xv[PRE][NE];
+#pragma unroll
+        for (int i = 0; i < PRE; i++) {
+            if (i < w) {
+                const int64_t bc = col[i];
+                const c128* xb = bc < nb_local_cols ? x + bc * NE : ghost + (bc - nb_local_cols) * NE;
+#pragma unroll
+                for (int c = 0; c < NE; c++) xv[i][c] = __ldg(xb + c);
+            }
+        }
+        // the slice after this one: offsets and column indices (consumed by the next trip)
+        const int64_t sn = s + stride;
+        int64_t basen = 0; int wn = 0;
+        if (sn < s_end) { basen = __ldg(sl_ptr + sn); wn = (int)(__ldg(sl_ptr + sn + 1) - basen); }
+        int32_t coln[PRE];
+        load_cols(basen, wn, coln);
+        mbar_wait(&full[warp], parity);
+        parity ^= 1;
+        c128 value = cmake(0., 0.);
+#pragma unroll
+        for (int i = 0; i < PRE; i++) {
+            if (i < w) {
+                const c128* m = (const c128*)(stage + (size_t)i * SLOT) + lane;
+                c128 o = cmake(0., 0.);
+#pragma unroll
+                for (int c = 0; c < NE; c++) o = cadd(o, cmul(m[c * 32], xv[i][c]));
+                value = cadd(value, o);
+            }
+        }
+        for (int l0 = PRE; l0 < w; l0 += PRE) {            // the remaining slots in batches, columns from shared memory
+#pragma unroll
+            for (int i = 0; i < PRE; i++) {
+                if (l0 + i < w) {
+                    const int64_t bc = ((const int32_t*)(stage + (size_t)(l0 + i) * SLOT + NE * 512))[rin];
+                    const c128* xb = bc < nb_local_cols ? x + bc * NE : ghost + (bc - nb_local_cols) * NE;
+#pragma unroll
+                    for (int c = 0; c < NE; c++) xv[i][c] = __ldg(xb + c);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PRE; i++) {
+                if (l0 + i < w) {
+                    const c128* m = (const c128*)(stage + (size_t)(l0 + i) * SLOT) + lane;
+                    c128 o = cmake(0., 0.);
+#pragma unroll
+                    for (int c = 0; c < NE; c++) o = cadd(o, cmul(m[c * 32], xv[i][c]));
+                    value = cadd(value, o);
+                }
+            }
+        }
+        __syncwarp();                                      // every lane is done with the stage
+        if (lane == 0 && sn < s_end) { fence_proxy_async_smem(); fetch(basen, wn); }
+        const int64_t t = s * 32 + lane;
+        if (t < nb * NE) {
+            if (bsub) value = csub(__ldg(bsub + t), value);
+            st_stream(y + t, value);
+        }
+        base = basen; w = wn;
+#pragma unroll
+        for (int i = 0; i < PRE; i++) col[i] = coln[i];
+    }
+}
+
+static __global__ void __launch_bounds__(256) k_slice_width(int64_t nb, int64_t nslices, int S, const int32_t* __restrict__ brow, int64_t* __restrict__ width) {
+    GRID_STRIDE(s, nslices) {
+        int w = 0;
+        for (int q = 0; q < S; q++) {
+            const int64_t R = s * S + q;
+            if (R < nb) w = max(w, brow[R + 1] - brow[R]);
+        }
+        width[s] = w;
+    }
+}
+// one warp per slice copies its rows from the assembly layout [l][c][r] into the slice's blob; padding = zero blocks
+// whose column is the row's own block (always addressable)
+static __global__ void __launch_bounds__(256) k_slice_fill(int64_t nb, int64_t nslices, int ne, const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+                                                           const c128* __restrict__ bval, const int64_t* __restrict__ sl_ptr, unsigned char* __restrict__ blob) {
+    const int S = 32 / ne;
+    const int slot = ne * 512 + S * 4;
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslices) return;
+    const int lane = threadIdx.x & 31, rin = lane / ne, r = lane - rin * ne;
+    const int64_t R = s * S + rin;
+    const int64_t base = sl_ptr[s];
+    const int w = (int)(sl_ptr[s + 1] - base);
+    const int first = R < nb ? brow[R] : 0, cnt = R < nb ? brow[R + 1] - brow[R] : 0;
+    for (int l = 0; l < w; l++) {
+        const bool on = l < cnt;
+        unsigned char* p = blob + (base + l) * slot;
+        if (r == 0) ((int32_t*)(p + ne * 512))[rin] = on ? bcol[first + l] : (int32_t)min(R, nb - 1);
+        for (int c = 0; c < ne; c++)
+            ((c128*)p)[c * 32 + lane] = on ? bval[((int64_t)(first + l) * ne + c) * ne + r] : cmake(0., 0.);
+    }
+}
+
+int BlockCsrOp::build_sliced() {
+    sliced = -1;
+    static const int enabled = getenv("MGCR_BLOCKCSR_SLICED") ? atoi(getenv("MGCR_BLOCKCSR_SLICED")) : 1;   // experiment knob
+    if (!enabled || !(ne == 2 || ne == 4 || ne == 8) || nb * ne < ctx->blockcsr_ring_rows) return MGCR_OK;   // small operators are latency-bound anyway
+    const int S = 32 / ne;
+    const int slot = ne * 512 + S * 4;
+    nslices = (nb + S - 1) / S;
+    int64_t* d_w = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)nslices, &d_w));
+    k_slice_width<<<stream_grid(ctx, nslices, 8), RED_THREADS, 0, ctx->stream>>>(nb, nslices, S, d_brow, d_w);
+    CHECK_LAUNCH();
+    std::vector<int64_t> w((size_t)nslices), ptr((size_t)nslices + 1, 0);
+    CUDA_TRY(cudaMemcpyAsync(w.data(), d_w, sizeof(int64_t) * (size_t)nslices, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, d_w);
+    int64_t wmax = 0;
+    for (int64_t s = 0; s < nslices; s++) { ptr[(size_t)s + 1] = ptr[(size_t)s] + w[(size_t)s]; wmax = std::max(wmax, w[(size_t)s]); }
+    sl_slots = ptr[(size_t)nslices];
+    // ring: one stage (= the widest slice) per consumer warp, as many as fit 200 KB, at most 14 (26 for ne = 2)
+    sl_stage_bytes = (int)(((wmax * slot + 127) / 128) * 128);
+    static const int nst_env = getenv("MGCR_BLOCKCSR_STAGES") ? atoi(getenv("MGCR_BLOCKCSR_STAGES")) : 0;   // experiment knob
+    const int max_stages = ne == 2 ? RingCfg<2>::MAX_STAGES : RingCfg<4>::MAX_STAGES;
+    sl_stages = sl_stage_bytes ? (int)std::min<int64_t>(nst_env > 0 ? std::min(nst_env, max_stages) : max_stages, (200 * 1024) / sl_stage_bytes) : 0;
+    // very ragged rows (> 25 % padding) or blobs too large for a useful ring: the assembly layout serves better
+    if ((double)sl_slots * S > 1.25 * (double)nnzb || sl_stages < 4) return MGCR_OK;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)nslices + 1, &d_sl_ptr));
+    MGCR_TRY(dev_alloc(ctx, (size_t)std::max<int64_t>(sl_slots, 1) * slot, (void**)&d_sl_blob));
+    CUDA_TRY(cudaMemcpyAsync(d_sl_ptr, ptr.data(), sizeof(int64_t) * ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+    k_slice_fill<<<(unsigned)((nslices * 32 + 255) / 256), 256, 0, ctx->stream>>>(nb, nslices, ne, d_brow, d_bcol, d_bval, d_sl_ptr, d_sl_blob);
+    CHECK_LAUNCH();
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // ptr (host vector) must outlive the copy
+    sliced = 1;
+    return MGCR_OK;
+}
+
+template <int NE>
+static int blockcsr_ring_launch(BlockCsrOp* op, const c128* x, const c128* ghost, const c128* bsub, c128* y) {
+    mgcr_ctx* ctx = op->ctx;
+    const size_t smem = (size_t)op->sl_stages * op->sl_stage_bytes + 128;
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_blockcsr_ring<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024)); attr_set = true; }
+    const int threads = 32 * op->sl_stages;
+    const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms, (op->nslices + op->sl_stages - 1) / op->sl_stages);
+    k_blockcsr_ring<NE><<<grid, threads, smem, ctx->stream>>>(op->nb, op->nslices, op->d_sl_ptr, op->d_sl_blob, x, ghost, op->n_local / op->ne, bsub, y,
+                                                             op->sl_stages, op->sl_stage_bytes);
+    return MGCR_OK;
+}
+
 BlockCsrOp::~BlockCsrOp() {
     dev_free(ctx, d_brow); dev_free(ctx, d_bcol); dev_free(ctx, d_bval);
+    dev_free(ctx, d_sl_ptr); dev_free(ctx, d_sl_blob);
     halo_free(ctx, halo);
 }
 
@@ -819,7 +1022,19 @@ int BlockCsrOp::run(const c128* x, c128* y, const c128* bsub) {
     const c128* ghost = nullptr;
     if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x)); ghost = halo->d_ghost; }
     if (nb == 0) return dist_halo_wait(ctx);
+    if (sliced == 0) MGCR_TRY(build_sliced());
     const double bytes_per_row = (apply_bytes() + (bsub ? 16. * n_local : 0.)) / (double)nb;
+    if (sliced == 1 && !(halo && dist_halo_overlap(ctx))) {
+        MGCR_TRY(dist_halo_wait(ctx));
+        ProfScope ps_(ctx, "blockcsr_apply", bytes_per_row * nb);
+        switch (ne) {
+            case 2: MGCR_TRY(blockcsr_ring_launch<2>(this, x, ghost, bsub, y)); break;
+            case 4: MGCR_TRY(blockcsr_ring_launch<4>(this, x, ghost, bsub, y)); break;
+            default: MGCR_TRY(blockcsr_ring_launch<8>(this, x, ghost, bsub, y)); break;
+        }
+        CHECK_LAUNCH();
+        return MGCR_OK;
+    }
     auto launch = [&](int64_t r0, int64_t r1) -> int {   // block rows [r0, r1)
         if (r1 <= r0) return MGCR_OK;
         const int grid = (int)(((r1 - r0) * ne + 255) / 256);

@@ -87,6 +87,17 @@ struct BlockCsrOp : mgcr_op {
     c128* d_bval = nullptr;      // [nnzb][ne(col)][ne(row)]
     HaloPlan* halo = nullptr;
     int64_t halo_rows_lo = 0, halo_rows_hi = 0;   // leading / trailing block rows that reference ghost columns
+    // Streaming image for the apply (ne = 2, 4, 8; built on the first apply): slices of 32/ne block rows = one warp, every
+    // row of a slice padded with zero blocks to the slice's widest.  A slice is one contiguous blob of block slots, slot l =
+    // [ne columns][32 lanes] c128 (lane = (row in slice) * ne + r) followed by the 32/ne column indices of the slot, so that a
+    // slice is fetched by ONE bulk copy into shared memory (k_blockcsr_ring); the assembly layout above stays for the
+    // Galerkin product of the next level, the persistent small-level solver and the exports.
+    int64_t nslices = 0, sl_slots = 0;
+    int64_t* d_sl_ptr = nullptr;          // [nslices+1] first block slot of each slice
+    unsigned char* d_sl_blob = nullptr;   // [sl_slots] slots of ne*512 + (32/ne)*4 bytes
+    int sl_stages = 0, sl_stage_bytes = 0;   // ring geometry: one stage (the widest slice) per consumer warp
+    int sliced = 0;                       // 0 = not tried yet, 1 = built, -1 = not applicable
+    int build_sliced();
     ~BlockCsrOp() override;
     int apply(const c128* x, c128* y) override;
     int apply_residual(const c128* x, const c128* b, c128* r) override;
