@@ -106,6 +106,7 @@ struct mgcr_ctx {
     int64_t hopping_tma_rows = (int64_t)1 << 19;
     int64_t blockcsr_ring_rows = (int64_t)1 << 18;   // block-CSR operators (ne = 2, 4, 8) of at least this many rows stream through the bulk-copy ring
     void* nccl_comm = nullptr;
+    void* p2p = nullptr;                    // peer-memory state (p2p.cu): mapped heaps of all ranks, NULL = NCCL for everything
     void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
     int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,
                                             // the exchanges are latency- and skew-bound; profiles/r01_halo_overlap_n8.txt)
@@ -165,6 +166,15 @@ int dev_free(mgcr_ctx* ctx, void* p);
 template <typename T> static inline int dev_alloc_t(mgcr_ctx* ctx, size_t count, T** out) {
     return dev_alloc(ctx, count * sizeof(T), (void**)out);
 }
+
+// peer-memory exchanges (p2p.cu)
+struct PeerHalo { bool on = false; size_t buf_off[2] = {0, 0}; size_t flag_off = 0; int64_t n = 0; uint32_t seq = 0; };
+int p2p_init(mgcr_ctx* ctx);
+void p2p_destroy(mgcr_ctx* ctx);
+bool p2p_enabled(mgcr_ctx* ctx);
+int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
+int p2p_halo_create(mgcr_ctx* ctx, int64_t n, PeerHalo* h);
+int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi);
 
 // distributed helpers (dist.cu)
 void dist_destroy(mgcr_ctx* ctx);

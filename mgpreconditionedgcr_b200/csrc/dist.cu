@@ -94,7 +94,8 @@ extern "C" int mgcr_ctx_init_dist(mgcr_ctx* ctx, int rank, int nranks, const voi
         ncclComm_t halo = nullptr;
         if (g_nccl.CommSplit(comm, 0, rank, &halo, nullptr) == ncclSuccess_) ctx->nccl_comm_halo = halo;
     }
-    return MGCR_OK;
+    // halo exchange and short all-reduces over NVLink peer memory (p2p.cu); NCCL remains the fallback and the bootstrap
+    return p2p_init(ctx);
 }
 
 extern "C" int mgcr_ctx_set_slab_align(mgcr_ctx* ctx, int64_t align) {
@@ -104,6 +105,7 @@ extern "C" int mgcr_ctx_set_slab_align(mgcr_ctx* ctx, int64_t align) {
 }
 
 void dist_destroy(mgcr_ctx* ctx) {
+    p2p_destroy(ctx);
     if (ctx->nccl_comm_halo && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm_halo);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr; ctx->nccl_comm_halo = nullptr;
@@ -118,6 +120,10 @@ extern "C" int mgcr_ctx_rank(mgcr_ctx* ctx, int* rank, int* nranks) {
 
 int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
     if (ctx->nranks == 1) return MGCR_OK;
+    {
+        const int st = p2p_allreduce_sum(ctx, d_buf, n);
+        if (st != MGCR_ERR_UNSUPPORTED) return st;
+    }
     ProfScope ps_(ctx, "nccl_allreduce", 8. * n);
     NCCL_TRY(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat64_, ncclSum_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return MGCR_OK;

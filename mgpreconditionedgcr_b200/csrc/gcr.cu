@@ -150,8 +150,11 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     GTRY(dev_alloc_t(ctx, (size_t)n, &r));
     GTRY(dev_alloc_t(ctx, (size_t)n, &Ar));
     if (right) GTRY(dev_alloc_t(ctx, (size_t)n, &z));
-    GTRY(dev_alloc_t(ctx, (size_t)stride * storage, &ps));
-    GTRY(dev_alloc_t(ctx, (size_t)stride * storage, &Aps));
+    // a solve of max_iter iterations stores at most max_iter + 1 directions (slot indices stay below that): short smoother /
+    // coarse solves with a long nominal restart do not hold the unused ring slots (15 GB per cycle on the 1024x512x512 lattice)
+    const int slots_alloc = std::min(storage, prm->max_iter + 1);
+    GTRY(dev_alloc_t(ctx, (size_t)stride * slots_alloc, &ps));
+    GTRY(dev_alloc_t(ctx, (size_t)stride * slots_alloc, &Aps));
     if (storage > GCR_CHUNK) { GTRY(dev_alloc_t(ctx, (size_t)n, &acc_p)); GTRY(dev_alloc_t(ctx, (size_t)n, &acc_Ap)); }
     GTRY(dev_alloc_t(ctx, (size_t)nscal, &scal));
     GCUDA(cudaMemsetAsync(scal, 0, sizeof(double) * nscal, ctx->stream));

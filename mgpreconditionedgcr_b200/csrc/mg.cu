@@ -705,6 +705,7 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
         Ac->halo = h;
         Ac->halo_rows_lo = lo_blocks; Ac->halo_rows_hi = hi_blocks;
         MGCR_TRY(dev_alloc_t(ctx, (size_t)std::max<int64_t>(1, h->n_ghost * ne), &h->d_ghost));
+        MGCR_TRY(p2p_halo_create(ctx, g.plane_blocks * ne, &h->ph));   // same size and order on every rank
         // gather here?  yes when the next level cannot keep the slab partition (a rank's aggregates no longer divide) or
         // the coarse system is small enough that communication latency dominates (option gather_dofs, default 2^18)
         bool gather = L.nc_global <= ctx->gather_dofs;
@@ -776,6 +777,13 @@ extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr
         op->n_local = mg->lv[l + 1].n; op->n_global = mg->lv[l + 1].A->n_global; op->distributed = mg->lv[l + 1].A->distributed;
         mg->lv[l].deeper = op;
     }
+    // the hierarchy is complete: large coarse operators keep only their streaming image (ops.cu, BlockCsrOp::build_sliced)
+    for (int l = 0; l < n_level; l++) {
+        BlockCsrOp* used = mg->lv[l].gather ? mg->lv[l].Ac_full : mg->lv[l].Ac;
+        if (!used) continue;
+        if (used->sliced == 0) { int st = used->build_sliced(); if (st != MGCR_OK) { mgcr_mg_destroy(mg); return st; } }
+        used->drop_assembly_values();
+    }
     *out = mg;
     return MGCR_OK;
 }
@@ -819,6 +827,7 @@ extern "C" int mgcr_mg_export_coarse(mgcr_mg* mg, int level, int64_t* h_brow, in
     const MgLevel& L = mg->lv[level];
     const LevelGeom& g = L.g;
     ARG_CHECK(!g.dist, "mgcr_mg_export_coarse: the reference-pattern export is single-GPU (level %d is slab-partitioned)", level);
+    ARG_CHECK(L.Ac->d_bval, "mgcr_mg_export_coarse: level %d keeps only its streaming image (operators above small_gcr_rows rows drop the assembly copy)", level);
     const int ne = g.ne;
     const size_t bsz = (size_t)ne * ne;
     std::vector<c128> val((size_t)L.Ac->nnzb * bsz);

@@ -52,7 +52,7 @@ static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, c
     mgcr_ctx* ctx = op->ctx;
     ARG_CHECK(x != y, "operator apply: input and output alias");
     const c128* ghost = nullptr;
-    if (op->halo) { MGCR_TRY(halo_exchange(ctx, op->halo, x)); MGCR_TRY(dist_halo_wait(ctx)); ghost = op->halo->d_ghost; }
+    if (op->halo) { MGCR_TRY(halo_exchange(ctx, op->halo, x)); MGCR_TRY(dist_halo_wait(ctx)); ghost = op->halo->ghost_cur; }
     if (op->nrow == 0) return MGCR_OK;
     int grid = (int)((op->nslices * 32 + 255) / 256);
     if (dirac)
@@ -516,7 +516,10 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
     const int64_t plane = a.n1 * a.n0;
     const int lo = ctx->rank - 1, hi = ctx->rank + 1;
     const bool has_lo = distributed && lo >= 0, has_hi = distributed && hi < ctx->nranks;
-    if (distributed) {
+    if (distributed && ph.on) {
+        // one plane to each slab neighbour, stored straight into its receive buffer over NVLink (p2p.cu)
+        MGCR_TRY(p2p_halo_exchange(ctx, &ph, x, x + (n2_local - 1) * plane, &a.halo_lo, &a.halo_hi));
+    } else if (distributed) {
         // one plane to each slab neighbour (NCCL send/recv; on the auxiliary stream when the exchange is overlapped)
         cudaStream_t hs;
         MGCR_TRY(dist_halo_begin(ctx, &hs));
@@ -572,7 +575,7 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
         CHECK_LAUNCH();
         return MGCR_OK;
     };
-    if (distributed && dist_halo_overlap(ctx) && a.n2 >= 4) {
+    if (distributed && !ph.on && dist_halo_overlap(ctx) && a.n2 >= 4) {
         // interior planes need no ghost data: they run while the halo planes are in flight
         const int64_t zi0 = has_lo ? 1 : 0, zi1 = has_hi ? a.n2 - 1 : a.n2;
         MGCR_TRY(launch(zi0, zi1));
@@ -610,6 +613,7 @@ static int hopping_create(mgcr_ctx* ctx, int ndim, const int64_t* dims, const do
         if (st == MGCR_OK && ze <= zb) { mgcr_set_error("mgcr_hopping_create: rank %d owns no plane", ctx->rank); st = MGCR_ERR_ARG; }
         if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_lo);
         if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)plane, &op->d_halo_hi);
+        if (st == MGCR_OK) st = p2p_halo_create(ctx, plane, &op->ph);
         if (st != MGCR_OK) { delete op; return st; }
     }
     op->distributed = ctx->nranks > 1;
@@ -992,6 +996,10 @@ int BlockCsrOp::build_sliced() {
     return MGCR_OK;
 }
 
+void BlockCsrOp::drop_assembly_values() {
+    if (sliced == 1 && d_bval && n_local > ctx->small_gcr_rows) { dev_free(ctx, d_bval); d_bval = nullptr; }
+}
+
 template <int NE>
 static int blockcsr_ring_launch(BlockCsrOp* op, const c128* x, const c128* ghost, const c128* bsub, c128* y) {
     mgcr_ctx* ctx = op->ctx;
@@ -1020,11 +1028,11 @@ int BlockCsrOp::apply_residual(const c128* x, const c128* b, c128* r) {
 int BlockCsrOp::run(const c128* x, c128* y, const c128* bsub) {
     ARG_CHECK(x != y, "operator apply: input and output alias");
     const c128* ghost = nullptr;
-    if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x)); ghost = halo->d_ghost; }
+    if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x)); ghost = halo->ghost_cur; }
     if (nb == 0) return dist_halo_wait(ctx);
     if (sliced == 0) MGCR_TRY(build_sliced());
     const double bytes_per_row = (apply_bytes() + (bsub ? 16. * n_local : 0.)) / (double)nb;
-    if (sliced == 1 && !(halo && dist_halo_overlap(ctx))) {
+    if (sliced == 1 && !(halo && !halo->ph.on && dist_halo_overlap(ctx))) {
         MGCR_TRY(dist_halo_wait(ctx));
         ProfScope ps_(ctx, "blockcsr_apply", bytes_per_row * nb);
         switch (ne) {
@@ -1047,7 +1055,7 @@ int BlockCsrOp::run(const c128* x, c128* y, const c128* bsub) {
         }
         return MGCR_OK;
     };
-    if (halo && dist_halo_overlap(ctx) && nb > halo_rows_lo + halo_rows_hi) {
+    if (halo && !halo->ph.on && dist_halo_overlap(ctx) && nb > halo_rows_lo + halo_rows_hi) {
         // only the first / last plane of aggregates has ghost columns: everything else runs while the halo is in flight
         MGCR_TRY(launch(halo_rows_lo, nb - halo_rows_hi));
         MGCR_TRY(dist_halo_wait(ctx));
@@ -1168,6 +1176,18 @@ __global__ void __launch_bounds__(RED_THREADS) k_pack(int64_t n_items, int elem,
 
 int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x) {
     if (!h || h->npeers == 0) return MGCR_OK;
+    h->ghost_cur = h->d_ghost;
+    if (h->ph.on && !h->d_send_idx) {
+        // slab neighbours, contiguous ranges: stored straight into the neighbours' receive areas over NVLink (p2p.cu)
+        const c128 *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
+        for (int p = 0; p < h->npeers; p++) {
+            if (h->peer[p] == ctx->rank - 1) send_lo = x + h->send_start[p] * h->elem;
+            if (h->peer[p] == ctx->rank + 1) send_hi = x + h->send_start[p] * h->elem;
+        }
+        MGCR_TRY(p2p_halo_exchange(ctx, &h->ph, send_lo, send_hi, &recv_lo, &recv_hi));
+        h->ghost_cur = recv_lo ? recv_lo : recv_hi;   // [lower plane][upper plane] contiguous; without a lower neighbour the upper one comes first
+        return MGCR_OK;
+    }
     int64_t n_send = h->send_off[h->npeers];
     if (h->d_send_idx && n_send > 0) {
         KLAUNCH(ctx, "halo_pack", 36. * n_send * h->elem, (k_pack<<<stream_grid(ctx, n_send * h->elem, 4), RED_THREADS, 0, ctx->stream>>>(n_send, h->elem, h->d_send_idx, x, h->d_send_buf)));

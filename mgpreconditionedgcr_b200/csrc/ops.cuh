@@ -17,6 +17,8 @@ struct HaloPlan {
     c128* d_ghost = nullptr;
     int64_t n_ghost = 0;
     int elem = 1;                     // c128 per exchanged item (ne for block operators)
+    PeerHalo ph;                      // slab neighbours over peer memory (p2p.cu) when available: replaces the NCCL send/recv pair
+    const c128* ghost_cur = nullptr;  // where the ghosts of the latest exchange are (d_ghost, or the peer-memory receive area)
 };
 
 struct mgcr_op {
@@ -57,7 +59,8 @@ struct HoppingOp : mgcr_op {
     // global boundary)
     bool var = false;
     double* d_face[3] = {nullptr, nullptr, nullptr};
-    c128* d_halo_lo = nullptr; c128* d_halo_hi = nullptr;   // neighbour planes (distributed)
+    c128* d_halo_lo = nullptr; c128* d_halo_hi = nullptr;   // neighbour planes (distributed, NCCL path)
+    PeerHalo ph;                                            // neighbour planes over peer memory (p2p.cu) when available
     ~HoppingOp() override;
     int apply(const c128* x, c128* y) override;
     int apply_dirac(const c128* x, c128* y, c128 k, const double* d_diag, const c128* bsub = nullptr);
@@ -98,6 +101,8 @@ struct BlockCsrOp : mgcr_op {
     int sl_stages = 0, sl_stage_bytes = 0;   // ring geometry: one stage (the widest slice) per consumer warp
     int sliced = 0;                       // 0 = not tried yet, 1 = built, -1 = not applicable
     int build_sliced();
+    // after the hierarchy is complete nothing reads the assembly copy of a large operator's values any more: give it back
+    void drop_assembly_values();
     ~BlockCsrOp() override;
     int apply(const c128* x, c128* y) override;
     int apply_residual(const c128* x, const c128* b, c128* r) override;

@@ -1,0 +1,230 @@
+// csrc/p2p.cu -- the two exchanges of the distributed solve written directly over NVLink peer memory instead of NCCL calls:
+//   * slab halo exchange: a kernel STORES this rank's boundary plane into the neighbour's receive buffer (peer pointer from
+//     a CUDA IPC handle), fences, raises a sequence flag in the neighbour's memory and waits for the neighbours' flags -- one
+//     launch per exchange instead of an ncclSend/ncclRecv group (42 us per exchange at 8 GPUs, profiles/r01_bench_mg3d_512_n8.json);
+//   * scalar all-reduce of <= 64 doubles: every rank stores its partial sums into a slot of every peer, each 32-bit half
+//     travelling in one 8-byte store together with the sequence number (flag-in-data, no fence), then sums the slots in rank
+//     order -- identical bits on every rank, one launch instead of an ncclAllReduce (32 us).
+// Each context owns a "heap" (one cudaMalloc) that every peer maps; receive buffers and flags are carved from it by a bump
+// allocator that all ranks call in the same order with the same sizes, so an offset means the same thing on every rank.
+// Buffers are double-buffered by the parity of the sequence number: a neighbour can be at most one exchange ahead (it cannot
+// finish exchange k+1 before this rank has contributed to it, which this rank does only after it has consumed exchange k).
+// NCCL stays for communicator bootstrap, set-up traffic, the coarse-level all-gather and reductions longer than 64 doubles.
+#include "common.cuh"
+
+int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+
+enum { P2P_AR_MAX = 64, P2P_ALIGN = 256 };
+
+struct PeerState {
+    unsigned char* heap = nullptr;
+    size_t bytes = 0, used = 0;
+    std::vector<unsigned char*> peer;      // peer[r] = rank r's heap mapped here (peer[rank] = heap)
+    size_t ar_off = 0;                     // all-reduce area: [2][nranks][2 * P2P_AR_MAX] uint64
+    uint32_t ar_seq = 0;
+    unsigned int* d_ticket = nullptr;      // last-CTA ticket of the halo kernel
+};
+
+static PeerState* state(mgcr_ctx* ctx) { return (PeerState*)ctx->p2p; }
+bool p2p_enabled(mgcr_ctx* ctx) { return ctx->p2p != nullptr; }
+
+int p2p_alloc(mgcr_ctx* ctx, size_t bytes, size_t* off) {
+    PeerState* s = state(ctx);
+    bytes = (bytes + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN;
+    if (!s || s->used + bytes > s->bytes) return MGCR_ERR_OOM;
+    *off = s->used;
+    s->used += bytes;
+    return MGCR_OK;
+}
+unsigned char* p2p_ptr(mgcr_ctx* ctx, int rank, size_t off) { return state(ctx)->peer[(size_t)rank] + off; }
+
+// collective; on any failure the context simply keeps using NCCL for everything
+int p2p_init(mgcr_ctx* ctx) {
+    static const int enabled = getenv("MGCR_P2P") ? atoi(getenv("MGCR_P2P")) : 1;
+    if (!enabled || ctx->nranks == 1) return MGCR_OK;
+    static const size_t heap_mb = getenv("MGCR_P2P_HEAP_MB") ? (size_t)atoll(getenv("MGCR_P2P_HEAP_MB")) : 192;
+    PeerState* s = new PeerState();
+    s->bytes = heap_mb << 20;
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc(&s->heap, s->bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; s->heap = nullptr; }
+    if (ok && cudaMemset(s->heap, 0, s->bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, s->heap) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    // handles (+ a validity byte) go round through NCCL
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    std::vector<unsigned char> all(rec * (size_t)ctx->nranks, 0), one(rec, 0);
+    memcpy(one.data(), &mine, sizeof(mine));
+    one[sizeof(mine)] = (unsigned char)ok;
+    unsigned char* d = nullptr;
+    MGCR_TRY(dev_alloc(ctx, rec * ((size_t)ctx->nranks + 1), (void**)&d));
+    CUDA_TRY(cudaMemcpyAsync(d + rec * (size_t)ctx->nranks, one.data(), rec, cudaMemcpyHostToDevice, ctx->stream));
+    MGCR_TRY(dist_allgather(ctx, d + rec * (size_t)ctx->nranks, d, rec));
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, d);
+    for (int r = 0; r < ctx->nranks; r++) ok = ok && all[rec * (size_t)r + sizeof(mine)];
+    s->peer.assign((size_t)ctx->nranks, nullptr);
+    if (ok) {
+        for (int r = 0; r < ctx->nranks && ok; r++) {
+            if (r == ctx->rank) { s->peer[(size_t)r] = s->heap; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + rec * (size_t)r, sizeof(h));
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+            s->peer[(size_t)r] = (unsigned char*)p;
+        }
+    }
+    // every rank must have mapped every peer, or nobody uses the peer path
+    double* dflag = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, 1, &dflag));
+    double f = ok ? 0. : 1.;
+    CUDA_TRY(cudaMemcpyAsync(dflag, &f, 8, cudaMemcpyHostToDevice, ctx->stream));
+    MGCR_TRY(dist_allreduce_sum(ctx, dflag, 1));
+    CUDA_TRY(cudaMemcpyAsync(&f, dflag, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, dflag);
+    if (f != 0.) {
+        for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && s->peer[(size_t)r]) cudaIpcCloseMemHandle(s->peer[(size_t)r]);
+        if (s->heap) cudaFree(s->heap);
+        delete s;
+        if (getenv("MGCR_VERBOSE")) fprintf(stderr, "mgcr: peer-memory path unavailable on rank %d, using NCCL\n", ctx->rank);
+        return MGCR_OK;
+    }
+    CUDA_TRY(cudaMalloc(&s->d_ticket, 64));
+    CUDA_TRY(cudaMemset(s->d_ticket, 0, 64));
+    ctx->p2p = s;
+    MGCR_TRY(p2p_alloc(ctx, sizeof(uint64_t) * 2 * (size_t)ctx->nranks * 2 * P2P_AR_MAX, &s->ar_off));
+    return MGCR_OK;
+}
+
+void p2p_destroy(mgcr_ctx* ctx) {
+    PeerState* s = state(ctx);
+    if (!s) return;
+    for (int r = 0; r < ctx->nranks; r++) if (r != ctx->rank && s->peer[(size_t)r]) cudaIpcCloseMemHandle(s->peer[(size_t)r]);
+    cudaFree(s->heap); cudaFree(s->d_ticket);
+    delete s;
+    ctx->p2p = nullptr;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// all-reduce
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+struct PeerPtrs { uint64_t* p[16]; };
+
+// slot layout of one parity: [source rank][2 * P2P_AR_MAX] words, word 2i / 2i+1 = {low / high half of element i, seq}
+static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, uint64_t* mine, int rank, int nranks, int n, uint32_t seq, double* buf) {
+    const int words = 2 * n;
+    for (int t = threadIdx.x; t < words * nranks; t += blockDim.x) {
+        const int p = t / words, j = t - p * words;
+        const uint64_t bits = (uint64_t)__double_as_longlong(buf[j >> 1]);
+        const uint32_t half = (j & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+        st_volatile_u64(peers.p[p] + (size_t)rank * (2 * P2P_AR_MAX) + j, ((uint64_t)seq << 32) | half);
+    }
+    __syncthreads();   // buf has been read by every thread before anybody overwrites it
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double sum = 0.;
+        for (int r = 0; r < nranks; r++) {
+            const uint64_t* w = mine + (size_t)r * (2 * P2P_AR_MAX) + 2 * i;
+            uint64_t lo, hi;
+            do { lo = ld_volatile_u64(w); } while ((uint32_t)(lo >> 32) != seq);
+            do { hi = ld_volatile_u64(w + 1); } while ((uint32_t)(hi >> 32) != seq);
+            sum += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+        }
+        buf[i] = sum;
+    }
+}
+
+// returns MGCR_ERR_UNSUPPORTED when the caller has to use NCCL (path off, too many values)
+int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
+    PeerState* s = state(ctx);
+    if (!s || n > P2P_AR_MAX || ctx->nranks > 16) return MGCR_ERR_UNSUPPORTED;
+    if (n <= 0) return MGCR_OK;
+    s->ar_seq++;
+    if (s->ar_seq == 0) s->ar_seq = 1;
+    const size_t par = (size_t)(s->ar_seq & 1) * (size_t)ctx->nranks * 2 * P2P_AR_MAX * sizeof(uint64_t);
+    PeerPtrs pp;
+    for (int r = 0; r < ctx->nranks; r++) pp.p[r] = (uint64_t*)(s->peer[(size_t)r] + s->ar_off + par);
+    KLAUNCH(ctx, "p2p_allreduce", 8. * n, (k_p2p_allreduce<<<1, 256, 0, ctx->stream>>>(pp, (uint64_t*)(s->heap + s->ar_off + par), ctx->rank, ctx->nranks, n, s->ar_seq, d_buf)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// slab halo exchange
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+static __global__ void __launch_bounds__(256) k_p2p_halo(const c128* __restrict__ src_lo, c128* __restrict__ dst_lo, uint32_t* flag_at_lo,
+                                                         const c128* __restrict__ src_hi, c128* __restrict__ dst_hi, uint32_t* flag_at_hi, int64_t n,
+                                                         uint32_t seq, unsigned int* ticket, const uint32_t* my_flag_lo, const uint32_t* my_flag_hi) {
+    __shared__ bool is_last;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (dst_lo) dst_lo[i] = ld_stream(src_lo + i);
+        if (dst_hi) dst_hi[i] = ld_stream(src_hi + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence_system();
+    if (flag_at_lo) st_release_sys_u32(flag_at_lo, seq);
+    if (flag_at_hi) st_release_sys_u32(flag_at_hi, seq);
+    // the kernel ends when the neighbours' planes of the same exchange have landed here
+    if (my_flag_lo) while ((int32_t)(ld_acquire_sys_u32(my_flag_lo) - seq) < 0) {}
+    if (my_flag_hi) while ((int32_t)(ld_acquire_sys_u32(my_flag_hi) - seq) < 0) {}
+}
+
+// receive area per parity: [n c128 from the lower neighbour][n c128 from the upper neighbour]; flags: lo at +0, hi at +128
+int p2p_halo_create(mgcr_ctx* ctx, int64_t n, PeerHalo* h) {
+    h->on = false;
+    if (!p2p_enabled(ctx)) return MGCR_OK;
+    size_t o0, o1, of;
+    // all three or nothing: the decision is the same on every rank (same sizes, same allocation order)
+    PeerState* s = state(ctx);
+    const size_t need = 2 * ((sizeof(c128) * 2 * (size_t)n + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN) + P2P_ALIGN;
+    if (s->used + need > s->bytes) return MGCR_OK;
+    MGCR_TRY(p2p_alloc(ctx, sizeof(c128) * 2 * (size_t)n, &o0));
+    MGCR_TRY(p2p_alloc(ctx, sizeof(c128) * 2 * (size_t)n, &o1));
+    MGCR_TRY(p2p_alloc(ctx, 256, &of));
+    h->buf_off[0] = o0; h->buf_off[1] = o1; h->flag_off = of; h->n = n; h->seq = 0; h->on = true;
+    return MGCR_OK;
+}
+
+// sends n elements starting at send_lo to the lower neighbour and at send_hi to the upper one; *recv_lo / *recv_hi point at
+// what the neighbours sent (valid once the kernel enqueued here has completed, i.e. for everything enqueued after it)
+int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi) {
+    PeerState* s = state(ctx);
+    const bool has_lo = ctx->rank > 0, has_hi = ctx->rank + 1 < ctx->nranks;
+    h->seq++;
+    const size_t buf = h->buf_off[h->seq & 1];
+    c128* mine = (c128*)(s->heap + buf);
+    *recv_lo = has_lo ? mine : nullptr;
+    *recv_hi = has_hi ? mine + h->n : nullptr;
+    if (!has_lo && !has_hi) return MGCR_OK;
+    c128* dst_lo = has_lo ? (c128*)(s->peer[(size_t)ctx->rank - 1] + buf) + h->n : nullptr;       // I am the lower neighbour's upper neighbour
+    c128* dst_hi = has_hi ? (c128*)(s->peer[(size_t)ctx->rank + 1] + buf) : nullptr;
+    uint32_t* flag_at_lo = has_lo ? (uint32_t*)(s->peer[(size_t)ctx->rank - 1] + h->flag_off + 128) : nullptr;
+    uint32_t* flag_at_hi = has_hi ? (uint32_t*)(s->peer[(size_t)ctx->rank + 1] + h->flag_off) : nullptr;
+    const uint32_t* my_lo = has_lo ? (const uint32_t*)(s->heap + h->flag_off) : nullptr;
+    const uint32_t* my_hi = has_hi ? (const uint32_t*)(s->heap + h->flag_off + 128) : nullptr;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(64, (h->n + 255) / 256));
+    KLAUNCH(ctx, "p2p_halo", 32. * h->n * ((has_lo ? 1 : 0) + (has_hi ? 1 : 0)),
+            (k_p2p_halo<<<grid, 256, 0, ctx->stream>>>(send_lo, dst_lo, flag_at_lo, send_hi, dst_hi, flag_at_hi, h->n, h->seq, s->d_ticket, my_lo, my_hi)));
+    CHECK_LAUNCH();
+    return MGCR_OK;
+}

@@ -146,6 +146,7 @@ static inline bool with_rows(mgcr_op* A, F&& f, int* status, bool allow_dist = f
     if (A->kind == OP_BLOCKCSR && !dirac) {
         BlockCsrOp* bo = static_cast<BlockCsrOp*>(A);
         if (bo->halo && !allow_dist) return false;
+        if (!bo->d_bval) return false;   // assembly copy dropped (large operator, streaming image only)
         *status = f(BlockRows{bo->d_brow, bo->d_bcol, bo->d_bval, bo->ne});
         return true;
     }

@@ -24,7 +24,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASS = {"k_sell_spmv<1>": "sell_dirac", "k_sell_spmv<0>": "sell_spmv", "k_hopping": "hopping_dirac", "k_hopping_l1": "hopping_dirac",
          "k_gcr_update_xr": "gcr_update_xr", "k_gcr_dot_hist": "gcr_dot_hist", "k_gcr_dot_hist_tma": "gcr_dot_hist", "k_gcr_update_p": "gcr_update_p",
          "k_gcr_init": "gcr_init", "k_blockcsr_apply": "blockcsr_apply", "k_blockcsr_apply_ne": "blockcsr_apply", "k_restrict": "mg_restrict",
-         "k_restrict_warp": "mg_restrict", "k_prolong": "mg_prolong"}
+         "k_restrict_warp": "mg_restrict", "k_restrict_sub": "mg_restrict", "k_prolong": "mg_prolong", "k_hopping_tma": "hopping_dirac",
+         "k_blockcsr_ring": "blockcsr_apply"}
 
 
 def short(name):
