@@ -190,6 +190,7 @@ int dist_group_end(mgcr_ctx* ctx);
 int dist_send(mgcr_ctx* ctx, const void* d_send, size_t bytes, int peer, cudaStream_t stream);
 int dist_recv(mgcr_ctx* ctx, void* d_recv, size_t bytes, int peer, cudaStream_t stream);
 int dist_allgather_host_i64(mgcr_ctx* ctx, int64_t mine, std::vector<int64_t>& all);
+int dist_allgather_host_bytes(mgcr_ctx* ctx, const void* mine, size_t bytes, std::vector<unsigned char>& all);
 int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
 
 // ----------------------------------------------------------------------------------------------------------

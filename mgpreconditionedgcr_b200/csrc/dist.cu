@@ -212,6 +212,20 @@ int dist_allgather_host_i64(mgcr_ctx* ctx, int64_t mine, std::vector<int64_t>& a
     return dev_free(ctx, d);
 }
 
+// every rank contributes `bytes` bytes, all get the nranks * bytes concatenation (setup-time metadata)
+int dist_allgather_host_bytes(mgcr_ctx* ctx, const void* mine, size_t bytes, std::vector<unsigned char>& all) {
+    all.assign(bytes * (size_t)ctx->nranks, 0);
+    if (bytes == 0) return MGCR_OK;
+    if (ctx->nranks == 1) { memcpy(all.data(), mine, bytes); return MGCR_OK; }
+    unsigned char* d = nullptr;
+    MGCR_TRY(dev_alloc(ctx, bytes * ((size_t)ctx->nranks + 1), (void**)&d));
+    CUDA_TRY(cudaMemcpyAsync(d + bytes * (size_t)ctx->nranks, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(g_nccl.AllGather(d + bytes * (size_t)ctx->nranks, d, bytes, ncclChar_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return dev_free(ctx, d);
+}
+
 // contiguous slabs of [0, n) in units of `align`; the first (n/align) % nranks ranks get one unit more
 extern "C" int mgcr_slab_range(int64_t n, int64_t align, int rank, int nranks, int64_t* begin, int64_t* end) {
     ARG_CHECK(begin && end && nranks >= 1 && rank >= 0 && rank < nranks && align >= 1, "mgcr_slab_range: bad argument");

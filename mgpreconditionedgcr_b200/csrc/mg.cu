@@ -901,7 +901,3 @@ extern "C" int mgcr_mg_op_create(mgcr_ctx* ctx, mgcr_mg* mg, mgcr_op** out) {
 }
 
 // the distributed CSR entry point lives here until the slab-partitioned hierarchy lands
-extern "C" int mgcr_csr_create_dist(mgcr_ctx*, int64_t, int64_t, int64_t, const int64_t*, const int64_t*, const mgcr_c128*, mgcr_op**) {
-    mgcr_set_error("mgcr_csr_create_dist: not available yet");
-    return MGCR_ERR_UNSUPPORTED;
-}

@@ -133,6 +133,98 @@ extern "C" int mgcr_csr_create(mgcr_ctx* ctx, int64_t nrow, int64_t ncol, const 
     return MGCR_OK;
 }
 
+// Row-slab-partitioned CSR: this rank holds rows [row_begin, row_end) with GLOBAL column indices.  Columns
+// inside the slab address the local vector; every other column becomes a ghost: the sorted list of distinct off-slab
+// columns is the ghost buffer's layout (ascending global index = grouped by owner, owners ascending), the lists are
+// all-gathered once, and each rank reads off them which of its elements every other rank wants, in that rank's ghost
+// order (pack list).  An apply packs, exchanges (one send/recv pair per communicating peer in one NCCL group) and runs the
+// same sliced-ELL kernel with columns >= n_local redirected to the ghost buffer.  Collective.
+extern "C" int mgcr_csr_create_dist(mgcr_ctx* ctx, int64_t nrow_global, int64_t row_begin, int64_t row_end, const int64_t* row,
+                                    const int64_t* col, const mgcr_c128* val, mgcr_op** out) {
+    ARG_CHECK(ctx && out && row && row_begin >= 0 && row_end >= row_begin && row_end <= nrow_global, "mgcr_csr_create_dist: bad argument");
+    *out = nullptr;
+    const int64_t nl = row_end - row_begin, nnz = row[nl];
+    ARG_CHECK(nnz == 0 || (col && val), "mgcr_csr_create_dist: NULL col/val");
+    if (ctx->nranks == 1) {
+        ARG_CHECK(row_begin == 0 && row_end == nrow_global, "mgcr_csr_create_dist: one rank must hold every row");
+        return mgcr_csr_create(ctx, nl, nrow_global, row, col, val, out);
+    }
+    std::vector<int64_t> begins, ends;
+    MGCR_TRY(dist_allgather_host_i64(ctx, row_begin, begins));
+    MGCR_TRY(dist_allgather_host_i64(ctx, row_end, ends));
+    for (int r = 0; r < ctx->nranks; r++) {
+        const int64_t expect = r == 0 ? 0 : ends[(size_t)r - 1];
+        ARG_CHECK(begins[(size_t)r] == expect && (r + 1 < ctx->nranks || ends[(size_t)r] == nrow_global),
+                  "mgcr_csr_create_dist: the row ranges of the ranks are not a contiguous ascending partition of [0, %lld)", (long long)nrow_global);
+    }
+    // ghost columns
+    std::vector<int64_t> ghost;
+    int bad = 0;
+    for (int64_t l = 0; l < nnz; l++) {
+        const int64_t c = col[l];
+        if (c < 0 || c >= nrow_global) { bad = 1; continue; }
+        if (c < row_begin || c >= row_end) ghost.push_back(c);
+    }
+    std::sort(ghost.begin(), ghost.end());
+    ghost.erase(std::unique(ghost.begin(), ghost.end()), ghost.end());
+    std::vector<int64_t> bads;
+    MGCR_TRY(dist_allgather_host_i64(ctx, bad, bads));
+    for (int64_t b : bads) ARG_CHECK(b == 0, "mgcr_csr_create_dist: column index out of range (src/Operator.h:332 asserts f.field_size() == dim)");
+    std::vector<int64_t> lcol((size_t)std::max<int64_t>(nnz, 1));
+    for (int64_t l = 0; l < nnz; l++) {
+        const int64_t c = col[l];
+        lcol[(size_t)l] = (c >= row_begin && c < row_end) ? c - row_begin : nl + (std::lower_bound(ghost.begin(), ghost.end(), c) - ghost.begin());
+    }
+    // everybody learns everybody's ghost list
+    std::vector<int64_t> sizes;
+    MGCR_TRY(dist_allgather_host_i64(ctx, (int64_t)ghost.size(), sizes));
+    int64_t maxreq = 0;
+    for (int64_t v : sizes) maxreq = std::max(maxreq, v);
+    std::vector<unsigned char> all;
+    {
+        std::vector<int64_t> padded((size_t)std::max<int64_t>(maxreq, 1), -1);
+        std::copy(ghost.begin(), ghost.end(), padded.begin());
+        MGCR_TRY(dist_allgather_host_bytes(ctx, padded.data(), sizeof(int64_t) * (size_t)maxreq, all));
+    }
+    const int64_t* lists = (const int64_t*)all.data();
+    SellOp* op = new SellOp();
+    op->kind = OP_SELL; op->ctx = ctx; op->ncol = nl + (int64_t)ghost.size(); op->n_local = nl; op->n_global = nrow_global; op->distributed = true;
+    HaloPlan* h = new HaloPlan();
+    op->halo = h;
+    h->elem = 1; h->n_ghost = (int64_t)ghost.size();
+    h->send_off.push_back(0); h->recv_off.push_back(0);
+    std::vector<int32_t> send_idx;
+    for (int r = 0; r < ctx->nranks; r++) {
+        if (r == ctx->rank) continue;
+        // what rank r wants from me, in its ghost order
+        const int64_t* lr = lists + (size_t)r * (size_t)maxreq;
+        const int64_t* lo = std::lower_bound(lr, lr + sizes[(size_t)r], row_begin);
+        const int64_t* hi = std::lower_bound(lr, lr + sizes[(size_t)r], row_end);
+        // what I want from rank r
+        const int64_t g0 = std::lower_bound(ghost.begin(), ghost.end(), begins[(size_t)r]) - ghost.begin();
+        const int64_t g1 = std::lower_bound(ghost.begin(), ghost.end(), ends[(size_t)r]) - ghost.begin();
+        if (hi == lo && g1 == g0) continue;
+        h->peer.push_back(r);
+        for (const int64_t* q = lo; q < hi; q++) send_idx.push_back((int32_t)(*q - row_begin));
+        h->send_off.push_back((int64_t)send_idx.size());
+        h->recv_off.push_back(g1);   // ghosts are sorted by global column: rank r's group ends at g1
+        h->send_start.push_back(0);
+    }
+    h->npeers = (int)h->peer.size();
+    int st = sell_build(ctx, nl, op->ncol, row, lcol.data(), val, op);
+    if (st == MGCR_OK) st = dev_alloc_t(ctx, std::max<size_t>(send_idx.size(), 1), &h->d_send_idx);
+    if (st == MGCR_OK) st = dev_alloc_t(ctx, std::max<size_t>(send_idx.size(), 1), &h->d_send_buf);
+    if (st == MGCR_OK) st = dev_alloc_t(ctx, std::max<size_t>(ghost.size(), 1), &h->d_ghost);
+    if (st == MGCR_OK && !send_idx.empty()) {
+        cudaError_t e = cudaMemcpyAsync(h->d_send_idx, send_idx.data(), sizeof(int32_t) * send_idx.size(), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { mgcr_set_error("mgcr_csr_create_dist: pack-list upload: %s", cudaGetErrorString(e)); st = MGCR_ERR_CUDA; }
+    }
+    if (st != MGCR_OK) { delete op; return st; }
+    *out = op;
+    return MGCR_OK;
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // matrix-free hopping stencil.  A CTA owns a TX x TY tile of the (n1, n0) plane and marches along n2: the plane
 // being processed sits in shared memory (with its one-element halo ring) for the x/y neighbours, the z neighbours

@@ -38,6 +38,9 @@ def test_distributed_against_single_gpu(world, gather, mode):
         pytest.skip("needs %d GPUs" % world)
     for o in run_world(world, gather, mode):
         assert o["apply_exact"] and o["apply_tma_exact"]          # halo exchange: bit-identical to the one-GPU stencil (both kernel forms)
+        if mode == "unit":
+            assert o["csr_apply_exact"] and o["csr_random_exact"]     # distributed CSR: gather-list halo, same sums in the same order
+            assert o["csr_gcr"][1] <= 1e-10
         assert o["dot_rel"] < 1e-14
         assert abs(o["gcr_iters"][0] - o["gcr_iters"][1]) <= 1 and o["gcr_hist_rel"] < 1e-10 and o["gcr_x_rel"] < 1e-8
         assert o["nblocks"][0] * world == o["nblocks"][1]
