@@ -479,8 +479,14 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
     c128 cur = ((const c128*)stage(1))[ctr];
     double fzm = 0.;
     if (VAR) fzm = ((const double*)(stage(1) + C::FZ_OFF))[ty * TX + tx];
+    // residual form: the right-hand side element of the NEXT plane is requested one plane ahead (a plain load issued right
+    // before its use would expose a DRAM latency per plane and warp)
+    c128 bs_cur = cmake(0., 0.);
+    if (a.bsub && inb) bs_cur = __ldg(a.bsub + zs * plane + c_off);
     for (int p = 1; p + 1 < nplanes; p++) {
         const int64_t z = zs - 1 + p;
+        c128 bs_next = cmake(0., 0.);
+        if (a.bsub && inb && p + 2 < nplanes) bs_next = __ldg(a.bsub + (z + 1) * plane + c_off);
         mbar_wait(&full[(p + 1) % stages], (uint32_t)(((p + 1) / stages) & 1));
         const unsigned char* sn = stage(p + 1);
         const unsigned char* sc = stage(p);
@@ -518,10 +524,10 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                 else if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
                 s = csub(xr, cmul(a.k, s));
             }
-            if (a.bsub) s = csub(__ldg(a.bsub + z * plane + c_off), s);
+            if (a.bsub) s = csub(bs_cur, s);
             st_stream(a.y + z * plane + c_off, s);
         }
-        prev = cur; cur = next; fzm = fzp;
+        prev = cur; cur = next; fzm = fzp; bs_cur = bs_next;
     }
 }
 

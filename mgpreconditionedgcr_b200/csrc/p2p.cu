@@ -117,6 +117,24 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
+// A rank that died (or never reached the matching exchange) must not leave its peers spinning for ever: after 60 s of
+// waiting the kernel traps, the stream reports an error and the caller fails loudly.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct SpinGuard {
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ void tick() {
+        if ((++spins & 0x3fffu) != 0) return;
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 60000000000ull) __trap();
+    }
+};
+
 struct PeerPtrs { uint64_t* p[16]; };
 
 // slot layout of one parity: [source rank][2 * P2P_AR_MAX] words, word 2i / 2i+1 = {low / high half of element i, seq}
@@ -134,8 +152,9 @@ static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, ui
         for (int r = 0; r < nranks; r++) {
             const uint64_t* w = mine + (size_t)r * (2 * P2P_AR_MAX) + 2 * i;
             uint64_t lo, hi;
-            do { lo = ld_volatile_u64(w); } while ((uint32_t)(lo >> 32) != seq);
-            do { hi = ld_volatile_u64(w + 1); } while ((uint32_t)(hi >> 32) != seq);
+            SpinGuard guard;
+            while ((uint32_t)((lo = ld_volatile_u64(w)) >> 32) != seq) guard.tick();
+            while ((uint32_t)((hi = ld_volatile_u64(w + 1)) >> 32) != seq) guard.tick();
             sum += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
         }
         buf[i] = sum;
@@ -185,8 +204,9 @@ static __global__ void __launch_bounds__(256) k_p2p_halo(const c128* __restrict_
     if (flag_at_lo) st_release_sys_u32(flag_at_lo, seq);
     if (flag_at_hi) st_release_sys_u32(flag_at_hi, seq);
     // the kernel ends when the neighbours' planes of the same exchange have landed here
-    if (my_flag_lo) while ((int32_t)(ld_acquire_sys_u32(my_flag_lo) - seq) < 0) {}
-    if (my_flag_hi) while ((int32_t)(ld_acquire_sys_u32(my_flag_hi) - seq) < 0) {}
+    SpinGuard guard;
+    if (my_flag_lo) while ((int32_t)(ld_acquire_sys_u32(my_flag_lo) - seq) < 0) guard.tick();
+    if (my_flag_hi) while ((int32_t)(ld_acquire_sys_u32(my_flag_hi) - seq) < 0) guard.tick();
 }
 
 // receive area per parity: [n c128 from the lower neighbour][n c128 from the upper neighbour]; flags: lo at +0, hi at +128
