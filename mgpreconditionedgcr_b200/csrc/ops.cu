@@ -415,7 +415,7 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 struct HopMaps { CUtensorMap x, lo, hi, fz, fy, fx, dg; };
 
 template <int TX, int TY, bool VAR>
-__global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_tma(const __grid_constant__ HopMaps maps, HopArgs a, int stages, int dbg_skip) {
+__global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_tma(const __grid_constant__ HopMaps maps, HopArgs a, int stages) {
     typedef HopTmaCfg<TX, TY, VAR> C;
     extern __shared__ unsigned char hop_smem_raw[];
     __shared__ __align__(8) uint64_t full[HOP_TMA_MAX_STAGES], empty[HOP_TMA_MAX_STAGES];
@@ -433,11 +433,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
     if (threadIdx.x >= C::CONSUMERS) {
         // ---- producer: one elected thread of the last warp ----
         if (threadIdx.x == C::CONSUMERS) {
-            uint32_t tx_bytes = (uint32_t)(C::TILE * 16) + (VAR ? (uint32_t)(C::DG_OFF - C::FZ_OFF) + (use_diag ? (uint32_t)(TX * TY * 8) : 0u) : 0u);
-            if (VAR && (dbg_skip & 1)) tx_bytes -= TX * TY * 8;
-            if (VAR && (dbg_skip & 2)) tx_bytes -= TX * (TY + 1) * 8;
-            if (VAR && (dbg_skip & 4)) tx_bytes -= C::FXW * TY * 8;
-            if (use_diag && (dbg_skip & 8)) tx_bytes -= TX * TY * 8;
+            const uint32_t tx_bytes = (uint32_t)(C::TILE * 16) + (VAR ? (uint32_t)(C::DG_OFF - C::FZ_OFF) + (use_diag ? (uint32_t)(TX * TY * 8) : 0u) : 0u);
             for (int p = 0; p < nplanes; p++) {
                 const int s = p % stages;
                 if (p >= stages) mbar_wait(&empty[s], (uint32_t)((p / stages - 1) & 1));
@@ -453,10 +449,10 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                     // bonds below the plane exist for z = 0 .. n2 (n2+1 planes); in-plane bonds and the diagonal only for the
                     // planes that are computed -- neighbour planes get an out-of-range coordinate (zero fill, no traffic)
                     const int zin = (z >= 0 && z < a.n2) ? (int)z : -1;
-                    if (!(dbg_skip & 1)) tma_load_3d(st + C::FZ_OFF, &maps.fz, (int)x0, (int)y0, (int)z, &full[s]);
-                    if (!(dbg_skip & 2)) tma_load_3d(st + C::FY_OFF, &maps.fy, (int)x0, (int)(y0 - 1), zin, &full[s]);
-                    if (!(dbg_skip & 4)) tma_load_3d(st + C::FX_OFF, &maps.fx, (int)(x0 - 2), (int)y0, zin, &full[s]);
-                    if (use_diag && !(dbg_skip & 8)) tma_load_3d(st + C::DG_OFF, &maps.dg, (int)x0, (int)y0, zin, &full[s]);
+                    tma_load_3d(st + C::FZ_OFF, &maps.fz, (int)x0, (int)y0, (int)z, &full[s]);
+                    tma_load_3d(st + C::FY_OFF, &maps.fy, (int)x0, (int)(y0 - 1), zin, &full[s]);
+                    tma_load_3d(st + C::FX_OFF, &maps.fx, (int)(x0 - 2), (int)y0, zin, &full[s]);
+                    if (use_diag) tma_load_3d(st + C::DG_OFF, &maps.dg, (int)x0, (int)y0, zin, &full[s]);
                 }
             }
         }
@@ -562,7 +558,6 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
     HopArgs a = a0;
     static const int stages_env = getenv("MGCR_HOP_STAGES") ? atoi(getenv("MGCR_HOP_STAGES")) : 0;   // experiment knobs
     static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;
-    static const int dbg_skip = getenv("MGCR_HOP_SKIP") ? atoi(getenv("MGCR_HOP_SKIP")) : 0;   // debugging: leave bond tiles out
     // two CTAs per SM (registers); the ring takes what shared memory allows: 8 planes of the operand tile in flight per CTA
     // saturate HBM (profiles/r01_stencil_tma_sweep.txt), 4 with the bond / diagonal tiles riding along
     const int stages_max = std::min((int)HOP_TMA_MAX_STAGES, (int)((111 * 1024 - 128) / C::STAGE_BYTES));
@@ -593,7 +588,7 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
     grid.z = (unsigned)((nz + a.zc - 1) / a.zc);
     ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
     a.z_lo = z_lo; a.z_hi = z_hi;
-    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY, VAR><<<grid, C::THREADS, smem, ctx->stream>>>(maps, a, stages, dbg_skip)));
+    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY, VAR><<<grid, C::THREADS, smem, ctx->stream>>>(maps, a, stages)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
