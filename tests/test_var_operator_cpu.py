@@ -132,3 +132,26 @@ def test_multigrid_on_anisotropic_operator_oracle():
     assert hist[-1] <= 1e-10 and np.linalg.norm(A(x) - rhs) / np.linalg.norm(rhs) < 1.5e-10
     _, _, it0 = orc.gcr_solve(A, orc.gcr_param(0, 10, 3000, 1e-10), rhs)
     assert it * 3 < it0
+
+
+def test_bench_anisotropic_hierarchy_shapes_and_slab_alignment():
+    """bench.py's mg3d_aniso: five levels 1024x512x512 -> 1024x512x64 -> 512x256x16 -> 128x64x4 -> 32x16x1, every aggregate
+    shape divides its lattice, and at 8 GPUs the slabs are multiples of the product of the aggregate sizes along the
+    partitioned dimension of the levels that stay distributed"""
+    import bench
+    wl = bench.WORKLOADS["mg3d_aniso"]
+    lv = bench.scalar_levels(wl["dims"], wl["mg"]["subs"], wl["mg"]["n_eigen"])
+    assert [l["site_dims"][1:] for l in lv] == [[1024, 512, 512], [1024, 512, 64], [512, 256, 16], [128, 64, 4]]
+    assert [l["n_col"] for l in lv] == [1, 2, 4, 4] and [l["n_eigen"] for l in lv] == [2, 4, 4, 4]
+    for l in lv:
+        assert all(d % s == 0 for d, s in zip(l["site_dims"], l["sub"]))
+    coarsest = [d // s for d, s in zip(lv[-1]["site_dims"][1:], lv[-1]["sub"][1:])]
+    assert coarsest == [32, 16, 1]
+    align = 1
+    for sub in wl["mg"]["subs"]:
+        if wl["dims"][0] // (align * sub[0]) >= 8:
+            align *= sub[0]
+    assert align == 32 and (wl["dims"][0] // 8) % align == 0
+    # the CPU sample of the reference arm keeps the aggregate shapes of the first levels
+    cl = bench.scalar_levels(wl["cpu_sample"], wl["cpu_mg"]["subs"], wl["cpu_mg"]["n_eigen"])
+    assert [l["sub"] for l in cl][:2] == [l["sub"] for l in lv][:2]
