@@ -110,8 +110,11 @@ int mgcr_vec_gamma5(mgcr_ctx* ctx, int ndim, const int64_t* h_dims, int axis, co
 /* Field::init_rand(seed) (Fields.h:125-135): the glibc srand/rand stream, drawn on the host (imaginary part first,
  * as g++ evaluates it) and uploaded -- the GPU never re-implements rand(). */
 int mgcr_vec_init_rand(mgcr_ctx* ctx, int seed, int64_t n, mgcr_c128* d_out);
-/* elements [skip, skip+n) of the same stream: the local slab of a distributed Field::init_rand(seed) */
+/* elements [skip, skip+n) of the same stream: the local slab of a distributed Field::init_rand(seed).  The generator is a
+ * linear recurrence, so the slab starts from a jump over its prefix and is drawn by several host threads (csrc/rand.cu) */
 int mgcr_vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, mgcr_c128* d_out);
+/* the same elements into a HOST buffer (no device involved) */
+int mgcr_rand_stream(int seed, int64_t skip, int64_t n, mgcr_c128* h_out);
 
 /* Mesh<num_type>::blocking(sub, mask) (src/Mesh.h:236-298), generalised to a per-dimension block size.
  * Exactly 4 dims must be masked.  Writes block_map[b*bs + o] = site (int64, HOST array of prod(masked dims)
@@ -159,6 +162,9 @@ typedef int (*mgcr_apply_fn)(void* user, const mgcr_c128* d_x, mgcr_c128* d_y);
 int mgcr_callback_op_create(mgcr_ctx* ctx, int64_t n, mgcr_apply_fn fn, void* user, mgcr_op** out);
 /* Operator::operator()(const Field&) (Operator.h:18): y = A x.  x and y must not alias. */
 int mgcr_op_apply(mgcr_ctx* ctx, mgcr_op* op, const mgcr_c128* d_x, mgcr_c128* d_y);
+/* r = b - A x in one pass (what `rhs - A(x)` costs three Field temporaries for in the reference; the multigrid cycle's
+ * residual).  Operators with their own kernels fold `b -` into the apply's store.  x, b must not alias r. */
+int mgcr_op_residual(mgcr_ctx* ctx, mgcr_op* op, const mgcr_c128* d_x, const mgcr_c128* d_b, mgcr_c128* d_r);
 int mgcr_op_dim(mgcr_op* op, int64_t* n_local, int64_t* n_global);                   /* Operator.h:20 get_dim  */
 /* algorithmic bytes one apply moves (SURVEY 8d formulas for the layout actually traversed) */
 int mgcr_op_apply_bytes(mgcr_op* op, double* bytes_out);
@@ -213,6 +219,10 @@ int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr_level_cfg*
                    const mgcr_gcr_param* coarse, const mgcr_gcr_param* smooth, int flags, const mgcr_c128* d_nearnull0,
                    mgcr_mg** out);
 int mgcr_mg_destroy(mgcr_mg* mg);
+/* wall-clock seconds of the set-up stages (names owned by the hierarchy): "total", "aggregate", "near_null" (Arnoldi::solve,
+ * MG.h:142-143; "rand" = its init_rand part), "project_orthonormalise" (MG.h:158-198), "ghost_prolongator", "galerkin"
+ * (MG.h:203-281), "coarse_halo_gather", "streaming_image".  *n_out = number of stages. */
+int mgcr_mg_setup_profile(mgcr_mg* mg, int cap, const char** names, double* seconds, int* n_out);
 /* structure export for parity (all HOST outputs).  level l = 0 .. n_level-1 */
 int mgcr_mg_level_info(mgcr_mg* mg, int level, int64_t* n_fine, int64_t* n_blocks, int* ne, int64_t* block_len);
 int mgcr_mg_export_block_map(mgcr_mg* mg, int level, int64_t* h_block_map);                 /* Mesh.h:270-293   */

@@ -74,6 +74,7 @@ SIGNATURES = {
     "mgcr_vec_gamma5": [_vp, _int, _pi64, _int, _vp, _vp],
     "mgcr_vec_init_rand": [_vp, _int, _i64, _vp],
     "mgcr_vec_init_rand_slab": [_vp, _int, _i64, _i64, _vp],
+    "mgcr_rand_stream": [_int, _i64, _i64, _vp],
     "mgcr_blocking_build": [_vp, _int, _pi64, _pi64, C.POINTER(C.c_uint8), _pi64, _pi64, _pi64],
     "mgcr_csr_create": [_vp, _i64, _i64, _vp, _vp, _vp, _pvp],
     "mgcr_csr_create_dist": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _pvp],
@@ -85,6 +86,7 @@ SIGNATURES = {
     "mgcr_blockcsr_create": [_vp, _i64, _int, _vp, _vp, _vp, _pvp],
     "mgcr_callback_op_create": [_vp, _i64, _vp, _vp, _pvp],
     "mgcr_op_apply": [_vp, _vp, _vp, _vp],
+    "mgcr_op_residual": [_vp, _vp, _vp, _vp, _vp],
     "mgcr_op_dim": [_vp, _pi64, _pi64],
     "mgcr_op_apply_bytes": [_vp, _pdbl],
     "mgcr_op_destroy": [_vp],
@@ -95,6 +97,7 @@ SIGNATURES = {
     "mgcr_arnoldi": [_vp, _vp, _pgp, _int, _vp],
     "mgcr_mg_create": [_vp, _vp, _int, _plc, _pgp, _pgp, _pgp, _int, _vp, _pvp],
     "mgcr_mg_destroy": [_vp],
+    "mgcr_mg_setup_profile": [_vp, _int, C.POINTER(C.c_char_p), _pdbl, _pint],
     "mgcr_mg_level_info": [_vp, _int, _pi64, _pi64, _pint, _pi64],
     "mgcr_mg_export_block_map": [_vp, _int, _vp],
     "mgcr_mg_export_prolongator": [_vp, _int, _vp],

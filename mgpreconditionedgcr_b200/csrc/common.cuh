@@ -85,6 +85,9 @@ struct mgcr_ctx {
     unsigned int* d_ticket = nullptr;
     double* d_scratch = nullptr;            // small device scalar scratch for the BLAS-1 entry points
     double* h_pinned = nullptr;             // pinned host mirror (256 doubles)
+    double rand_seconds_ms = 0; int64_t rand_calls = 0;   // host wall-clock (ms) spent drawing + uploading init_rand fields (rand.cu)
+    void* h_stage = nullptr;                // pinned staging ring for host-generated fields (rand.cu), allocated on first use
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     int64_t launches = 0;
     // host-side time spent inside the allocator and waiting on the device (diagnostics: reported as the profile classes
     // "host_alloc" / "host_sync" when profiling is on)
@@ -110,6 +113,8 @@ struct mgcr_ctx {
     void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
     int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,
                                             // the exchanges are latency- and skew-bound; profiles/r01_halo_overlap_n8.txt)
+    std::vector<cudaEvent_t> depth_events;  // read-back event of each solver nesting depth (gcr.cu)
+    std::map<const void*, int> dyn_smem;    // kernels whose dynamic shared-memory limit has been raised on THIS device
     // profiling
     bool profile = false;
     std::map<std::string, ProfEntry> prof;
@@ -167,6 +172,15 @@ template <typename T> static inline int dev_alloc_t(mgcr_ctx* ctx, size_t count,
     return dev_alloc(ctx, count * sizeof(T), (void**)out);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remembered per context, not per process
+static inline int ensure_dyn_smem(mgcr_ctx* ctx, const void* kernel, int bytes) {
+    auto it = ctx->dyn_smem.find(kernel);
+    if (it != ctx->dyn_smem.end() && it->second >= bytes) return MGCR_OK;
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ctx->dyn_smem[kernel] = bytes;
+    return MGCR_OK;
+}
+
 // peer-memory exchanges (p2p.cu)
 struct PeerHalo { bool on = false; size_t buf_off[2] = {0, 0}; size_t flag_off = 0; int64_t n = 0; uint32_t seq = 0; };
 int p2p_init(mgcr_ctx* ctx);
@@ -174,6 +188,7 @@ void p2p_destroy(mgcr_ctx* ctx);
 bool p2p_enabled(mgcr_ctx* ctx);
 int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
 int p2p_halo_create(mgcr_ctx* ctx, int64_t n, PeerHalo* h);
+void p2p_halo_destroy(mgcr_ctx* ctx, PeerHalo* h);
 int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi);
 
 // distributed helpers (dist.cu)

@@ -133,8 +133,10 @@ extern "C" int mgcr_ctx_destroy(mgcr_ctx* c) {
     mem_trim(c);
     for (auto& kv : c->mem_live) cudaFree(kv.first);
     cudaFree(c->d_partials); cudaFree(c->d_ticket); cudaFree(c->d_scratch); cudaFreeHost(c->h_pinned);
+    if (c->h_stage) { cudaFreeHost(c->h_stage); cudaEventDestroy(c->ev_stage[0]); cudaEventDestroy(c->ev_stage[1]); }
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b); cudaEventDestroy(c->ev_scal);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->depth_events) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream); cudaStreamDestroy(c->aux_stream);
     delete c;
     return MGCR_OK;

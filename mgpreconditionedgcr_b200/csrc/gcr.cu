@@ -35,11 +35,7 @@ static void launch_dot_hist(mgcr_ctx* ctx, int grid, int64_t n, const c128* Ar, 
 template <int NH>
 static int launch_dot_hist_tma(mgcr_ctx* ctx, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int std_conj,
                                double* out, const double* guard, double tol2) {
-    static thread_local bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_gcr_dot_hist_tma<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_gcr_dot_hist_tma<NH>, 200 * 1024));
     // tile = 256*ept elements of each of the 1+NH vectors; ring of `stages` tiles in ~150 KB (measured: scripts/kbench_dot5.cu)
     const int ept = NH <= 3 ? 4 : NH <= 7 ? 2 : 1;
     const size_t stage_bytes = (size_t)(1 + NH) * RED_THREADS * ept * sizeof(c128);
@@ -95,15 +91,12 @@ static void update_p(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* z, 
 struct SolveSlot { double* h; cudaEvent_t ev; };
 static int acquire_slot(mgcr_ctx* ctx, int depth, SolveSlot* s) {
     ARG_CHECK(depth < 12, "GCR: solver nesting deeper than 12");
-    static thread_local std::map<std::pair<mgcr_ctx*, int>, cudaEvent_t> events;
-    auto key = std::make_pair(ctx, depth);
-    auto it = events.find(key);
-    if (it == events.end()) {
+    while ((int)ctx->depth_events.size() <= depth) {   // owned by the context, destroyed with it
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        it = events.emplace(key, e).first;
+        ctx->depth_events.push_back(e);
     }
-    s->ev = it->second;
+    s->ev = ctx->depth_events[(size_t)depth];
     s->h = ctx->h_pinned + 16 + 8 * depth;
     return MGCR_OK;
 }
@@ -151,10 +144,31 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     GTRY(dev_alloc_t(ctx, (size_t)n, &Ar));
     if (right) GTRY(dev_alloc_t(ctx, (size_t)n, &z));
     // a solve of max_iter iterations stores at most max_iter + 1 directions (slot indices stay below that): short smoother /
-    // coarse solves with a long nominal restart do not hold the unused ring slots (15 GB per cycle on the 1024x512x512 lattice)
-    const int slots_alloc = std::min(storage, prm->max_iter + 1);
+    // coarse solves with a long nominal restart do not hold the unused ring slots (15 GB per cycle on the 1024x512x512 lattice).
+    // Long rings (full GCR: storage = max_iter, src/GCR.h:171-185, whose `new Field[storage]` fills lazily, :208-209) start with
+    // 32 slots and double when the iteration reaches the end: a full GCR that converges in tens of iterations never holds more.
+    int slots_alloc = std::min(std::min(storage, prm->max_iter + 1), 32);
     GTRY(dev_alloc_t(ctx, (size_t)stride * slots_alloc, &ps));
     GTRY(dev_alloc_t(ctx, (size_t)stride * slots_alloc, &Aps));
+    auto grow_ring = [&](int need_slot) -> int {
+        if (need_slot < slots_alloc) return MGCR_OK;
+        const int cap = std::min(storage, std::max(2 * slots_alloc, need_slot + 1));
+        c128 *nps = nullptr, *nAps = nullptr;
+        int s2 = dev_alloc_t(ctx, (size_t)stride * cap, &nps);
+        if (s2 == MGCR_OK) s2 = dev_alloc_t(ctx, (size_t)stride * cap, &nAps);
+        if (s2 != MGCR_OK) {
+            dev_free(ctx, nps);
+            mgcr_set_error("GCR: no device memory for %d stored search directions of %lld elements; bound the history with GCR_Param::truncation or "
+                           "::restart (src/GCR.h:171-185)", cap, (long long)n);
+            return MGCR_ERR_OOM;
+        }
+        cudaError_t e = cudaMemcpyAsync(nps, ps, sizeof(c128) * (size_t)stride * slots_alloc, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nAps, Aps, sizeof(c128) * (size_t)stride * slots_alloc, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { dev_free(ctx, nps); dev_free(ctx, nAps); mgcr_set_error("GCR ring growth: %s", cudaGetErrorString(e)); return MGCR_ERR_CUDA; }
+        dev_free(ctx, ps); dev_free(ctx, Aps);
+        ps = nps; Aps = nAps; slots_alloc = cap;
+        return MGCR_OK;
+    };
     if (storage > GCR_CHUNK) { GTRY(dev_alloc_t(ctx, (size_t)n, &acc_p)); GTRY(dev_alloc_t(ctx, (size_t)n, &acc_Ap)); }
     GTRY(dev_alloc_t(ctx, (size_t)nscal, &scal));
     GCUDA(cudaMemsetAsync(scal, 0, sizeof(double) * nscal, ctx->stream));
@@ -211,7 +225,10 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
                 const int cnt = std::min((int)GCR_CHUNK, lim - c0);
                 for (int k = 0; k < GCR_CHUNK; k++) hl.slot[k] = k < cnt ? c0 + k : 0;
                 ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + cnt));
-                GTRY(dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, scal + S_BNUM + 2 * c0, guard, tol2));
+                // distributed: scal[S_RR] still holds this rank's PARTIAL ||r||^2 here (it is all-reduced together with the inner
+                // products below), so a device-side stopping test would compare a partial norm with the global ||rhs||^2 and
+                // ranks could disagree on whether this kernel runs; its output is unused once converged, so it runs unguarded
+                GTRY(dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, scal + S_BNUM + 2 * c0, dist ? nullptr : guard, tol2));
             }
             GCUDA(cudaGetLastError());
         }
@@ -225,6 +242,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
             // p = z + p_corr, Ap = Ar + Ap_corr into the ring slot, next alpha's inner products          (GCR.h:259-266, 277-287)
             int next_iter = (iter % restart == 0) ? 0 : iter;
             int new_slot = next_iter % storage;
+            GTRY(grow_ring(new_slot));
             int nchunks = std::max(1, (lim + GCR_CHUNK - 1) / GCR_CHUNK);
             for (int c = 0; c < nchunks; c++) {
                 BetaList bl;
@@ -332,73 +350,6 @@ extern "C" int mgcr_gcr_op_retarget(mgcr_op* gcr, mgcr_op* A) {
     GcrOp* op = static_cast<GcrOp*>(gcr);
     if (op->n_local != A->n_local) { dev_free(op->ctx, op->d_rand2); op->d_rand2 = nullptr; }
     op->A = A; op->n_local = A->n_local; op->n_global = A->n_global; op->distributed = A->distributed;
-    return MGCR_OK;
-}
-
-// glibc rand() stream of Field::init_rand(seed), elements [skip, skip+n).
-// rand() itself costs ~10 ns per draw (a lock per call): 2.7 s for a 512^3 field.  glibc's generator is the additive
-// feedback r[i] = r[i-3] + r[i-31] (TYPE_3, seeded by the Lehmer sequence 16807 r mod 2^31-1, first 310 outputs dropped,
-// output r >> 1); GlibcRand restates it and is verified against the C library's rand() on every use -- if the first
-// draws ever differ (another libc), the C library's own rand() is used instead.
-struct GlibcRand {
-    uint32_t ring[31];
-    int f, b;
-    void seed(unsigned int s) {
-        if (s == 0) s = 1;
-        int32_t word = (int32_t)s;
-        ring[0] = (uint32_t)word;
-        for (int i = 1; i < 31; i++) {
-            long hi = word / 127773, lo = word % 127773;
-            word = (int32_t)(16807 * lo - 2836 * hi);
-            if (word < 0) word += 2147483647;
-            ring[i] = (uint32_t)word;
-        }
-        f = 3; b = 0;
-        for (int i = 0; i < 310; i++) next();
-    }
-    inline uint32_t next() {
-        ring[f] += ring[b];
-        const uint32_t out = ring[f] >> 1;
-        if (++f == 31) f = 0;
-        if (++b == 31) b = 0;
-        return out;
-    }
-};
-
-static bool glibc_rand_matches(int seed) {
-    GlibcRand g;
-    g.seed((unsigned int)seed);
-    srand(seed);
-    for (int i = 0; i < 64; i++) if ((int)g.next() != rand()) return false;
-    return true;
-}
-
-int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d_out) {
-    if (n == 0) return MGCR_OK;
-    c128* h = nullptr;
-    CUDA_TRY(cudaMallocHost(&h, sizeof(c128) * (size_t)n));
-    if (glibc_rand_matches(seed)) {
-        GlibcRand g;
-        g.seed((unsigned int)seed);
-        for (int64_t i = 0; i < 2 * skip; i++) (void)g.next();
-        for (int64_t i = 0; i < n; i++) {
-            double im = (int)(g.next() % 2000) / 1000. - 1;     // the imaginary argument is evaluated first (g++), SURVEY.md 8a row a9
-            double re = (int)(g.next() % 2000) / 1000. - 1;
-            h[i] = cmake(re, im);
-        }
-    } else {
-        srand(seed);
-        for (int64_t i = 0; i < 2 * skip; i++) (void)rand();
-        for (int64_t i = 0; i < n; i++) {
-            double im = (rand() % 2000) / 1000. - 1;
-            double re = (rand() % 2000) / 1000. - 1;
-            h[i] = cmake(re, im);
-        }
-    }
-    cudaError_t e = cudaMemcpyAsync(d_out, h, sizeof(c128) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFreeHost(h);
-    CUDA_TRY(e);
     return MGCR_OK;
 }
 

@@ -260,66 +260,96 @@ static __global__ void __launch_bounds__(RED_THREADS) k_pack_P_plane(LevelGeom g
 // ----------------------------------------------------------------------------------------------------------
 // restrict / prolong
 // ----------------------------------------------------------------------------------------------------------
-// xc[b*ne+e] = sum_q conj(P[b][e][q]) x[map(b,q)]   (MG.h:366-383).  One CTA per aggregate: the aggregate's slice of x
-// is gathered into shared memory once, warp w reduces near-null vectors e = w, w+nw, ... with lanes striding over q.
-static __global__ void __launch_bounds__(256) k_restrict(LevelGeom g, const int64_t* __restrict__ block_map, const c128* __restrict__ P,
+// Aggregates are boxes of a structured lattice, so the fine index of (aggregate b, position q inside it) is arithmetic:
+// first element of the aggregate (from b's block coordinates, 32-bit: a shard has < 2^31 sites) + a per-level table
+// q_off[q] (element offset of in-aggregate position q, bl int32 entries, L1-resident).  Round 1 read the int64 block_map
+// (src/Mesh.h:270-293) instead: 8 B per site of extra traffic (+10 % at ne = 4) and a dependent DRAM round trip in front of
+// every gather; block_map is now only exported and used by the set-up kernels.
+struct AggGeom {
+    int bd[4], sub[4], sd[4];
+    int dof;
+    int linear;   // aggregates are runs of consecutive sites (sub = 1,1,1,s): first element = b * bl
+};
+__device__ __forceinline__ int64_t agg_first_elem(const AggGeom& a, int64_t bl, int64_t b) {
+    if (a.linear) return b * bl;
+    unsigned int t = (unsigned int)b;
+    const unsigned int b3 = t % (unsigned int)a.bd[3]; t /= (unsigned int)a.bd[3];
+    const unsigned int b2 = t % (unsigned int)a.bd[2]; t /= (unsigned int)a.bd[2];
+    const unsigned int b1 = t % (unsigned int)a.bd[1]; t /= (unsigned int)a.bd[1];
+    const int64_t site = (((int64_t)t * a.sub[0] * a.sd[1] + (int64_t)b1 * a.sub[1]) * a.sd[2] + (int64_t)b2 * a.sub[2]) * a.sd[3] + (int64_t)b3 * a.sub[3];
+    return site * a.dof;
+}
+// q_off[q] for q = o*dof + d: element offset of in-aggregate site o = (o0,o1,o2,o3) row-major over sub
+static __global__ void k_agg_offsets(AggGeom a, int bl, int32_t* __restrict__ q_off) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < bl; q += gridDim.x * blockDim.x) {
+        int o = q / a.dof;
+        const int d = q - o * a.dof;
+        const int o3 = o % a.sub[3]; o /= a.sub[3];
+        const int o2 = o % a.sub[2]; o /= a.sub[2];
+        const int o1 = o % a.sub[1]; o /= a.sub[1];
+        const int64_t site = (((int64_t)o * a.sd[1] + o1) * a.sd[2] + o2) * a.sd[3] + o3;
+        q_off[q] = (int32_t)(site * a.dof + d);
+    }
+}
+
+// xc[b*ne+e] = sum_q conj(P[b][e][q]) x[map(b,q)]   (MG.h:366-383).  One CTA per aggregate (grid-stride): the aggregate's
+// slice of x is gathered into shared memory once, warp w reduces near-null vectors e = w, w+nw, ... with lanes striding over q.
+static __global__ void __launch_bounds__(256) k_restrict(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                          const c128* __restrict__ xf, c128* __restrict__ xc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* xs = (c128*)smem_raw;
-    const int64_t b = blockIdx.x;
-    for (int64_t q = threadIdx.x; q < g.bl; q += blockDim.x) {
-        const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
-        xs[q] = __ldg(xf + site * g.dof + q % g.dof);
-    }
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int e = warp; e < g.ne; e += nw) {
-        const c128* pv = P + (b * g.ne + e) * g.bl;
-        double sr = 0., si = 0.;
-        for (int64_t q = lane; q < g.bl; q += 32) {
-            c128 t = cmulc(ld_stream(pv + q), xs[q]);
-            sr += t.x; si += t.y;
+    for (int64_t b = blockIdx.x; b < g.nb; b += gridDim.x) {
+        const c128* xb = xf + agg_first_elem(ag, g.bl, b);
+        __syncthreads();                             // the previous aggregate's slice has been consumed
+        for (int64_t q = threadIdx.x; q < g.bl; q += blockDim.x) xs[q] = __ldg(xb + __ldg(q_off + q));
+        __syncthreads();
+        for (int e = warp; e < g.ne; e += nw) {
+            const c128* pv = P + (b * g.ne + e) * g.bl;
+            double sr = 0., si = 0.;
+            for (int64_t q = lane; q < g.bl; q += 32) {
+                c128 t = cmulc(ld_stream(pv + q), xs[q]);
+                sr += t.x; si += t.y;
+            }
+            sr = warp_sum(sr); si = warp_sum(si);
+            if (lane == 0) xc[b * g.ne + e] = cmake(sr, si);
         }
-        sr = warp_sum(sr); si = warp_sum(si);
-        if (lane == 0) xc[b * g.ne + e] = cmake(sr, si);
     }
 }
 
 // The same for small aggregates (up to 32*QPL dofs, the synthetic configurations: 4^3 sites x 1..4 dofs): one WARP per
-// aggregate, its slice of x held in registers, no shared memory and no block barrier; 8 aggregates per CTA keep ~10
-// independent 128-bit loads per lane in flight.  The per-lane accumulation order is that of k_restrict (q = lane, lane+32,
-// ..., then the shuffle tree), so both kernels give bit-identical results.
+// aggregate, its slice of x held in registers, no shared memory and no block barrier.  Persistent: the warps of a grid
+// sized to the machine stride over the aggregates, so that at any time the whole GPU works on one window of consecutive
+// aggregates (round 1 launched 262 144 eight-aggregate CTAs per restrict at 512^3).  The per-lane accumulation order is that
+// of k_restrict (q = lane, lane+32, ..., then the shuffle tree), so both kernels give bit-identical results.
 template <int QPL>
-static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, const int64_t* __restrict__ block_map, const c128* __restrict__ P,
+static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                               const c128* __restrict__ xf, c128* __restrict__ xc) {
-    const int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (b >= g.nb) return;
     const int lane = threadIdx.x & 31;
-    c128 xs[QPL];
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int qo[QPL];
 #pragma unroll
-    for (int j = 0; j < QPL; j++) {
-        const int64_t q = lane + 32 * j;
-        if (q < g.bl) {
-            const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
-            xs[j] = __ldg(xf + site * g.dof + q % g.dof);
-        } else {
-            xs[j] = cmake(0., 0.);
-        }
-    }
+    for (int j = 0; j < QPL; j++) qo[j] = lane + 32 * j < g.bl ? __ldg(q_off + lane + 32 * j) : 0;
+    for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; b < g.nb; b += nwarps) {
+        const c128* xb = xf + agg_first_elem(ag, g.bl, b);
+        c128 xs[QPL];
+#pragma unroll
+        for (int j = 0; j < QPL; j++) xs[j] = lane + 32 * j < g.bl ? __ldg(xb + qo[j]) : cmake(0., 0.);
 #pragma unroll 4
-    for (int e = 0; e < g.ne; e++) {
-        const c128* pv = P + (b * g.ne + e) * g.bl;
-        double sr = 0., si = 0.;
+        for (int e = 0; e < g.ne; e++) {
+            const c128* pv = P + (b * g.ne + e) * g.bl;
+            double sr = 0., si = 0.;
 #pragma unroll
-        for (int j = 0; j < QPL; j++) {
-            const int64_t q = lane + 32 * j;
-            if (q < g.bl) {
-                c128 t = cmulc(ld_stream(pv + q), xs[j]);
-                sr += t.x; si += t.y;
+            for (int j = 0; j < QPL; j++) {
+                const int64_t q = lane + 32 * j;
+                if (q < g.bl) {
+                    c128 t = cmulc(ld_stream(pv + q), xs[j]);
+                    sr += t.x; si += t.y;
+                }
             }
+            sr = warp_sum(sr); si = warp_sum(si);
+            if (lane == 0) xc[b * g.ne + e] = cmake(sr, si);
         }
-        sr = warp_sum(sr); si = warp_sum(si);
-        if (lane == 0) xc[b * g.ne + e] = cmake(sr, si);
     }
 }
 
@@ -327,64 +357,89 @@ static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, const
 // aggregate, 32/G aggregates per warp, so that no lane idles.  Lane q of the group holds dof q; the group's shuffle tree
 // (xor G/2 .. 1) is the tail of the full warp tree, whose upper steps would only add zeros: bit-identical to k_restrict_warp.
 template <int G>
-static __global__ void __launch_bounds__(256) k_restrict_sub(LevelGeom g, const int64_t* __restrict__ block_map, const c128* __restrict__ P,
+static __global__ void __launch_bounds__(256) k_restrict_sub(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                              const c128* __restrict__ xf, c128* __restrict__ xc) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t b = t / G;
-    const int q = (int)(t % G);
-    const bool on = b < g.nb && q < g.bl;
-    c128 xv = cmake(0., 0.);
-    if (on) {
-        const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
-        xv = __ldg(xf + site * g.dof + q % g.dof);
-    }
-    for (int e = 0; e < g.ne; e++) {
-        double sr = 0., si = 0.;
-        if (on) {
-            c128 v = cmulc(ld_stream(P + (b * g.ne + e) * g.bl + q), xv);
-            sr = v.x; si = v.y;
-        }
+    const int q = (int)(threadIdx.x % G);
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    const int qo = q < g.bl ? __ldg(q_off + q) : 0;
+    const int64_t nb_round = (g.nb + (32 / G) - 1) / (32 / G) * (32 / G);   // whole warps run the shuffles together
+    for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G; b < nb_round; b += T / G) {
+        const bool on = b < g.nb && q < g.bl;
+        c128 xv = cmake(0., 0.);
+        if (on) xv = __ldg(xf + agg_first_elem(ag, g.bl, b) + qo);
+        for (int e = 0; e < g.ne; e++) {
+            double sr = 0., si = 0.;
+            if (on) {
+                c128 v = cmulc(ld_stream(P + (b * g.ne + e) * g.bl + q), xv);
+                sr = v.x; si = v.y;
+            }
 #pragma unroll
-        for (int o = G / 2; o >= 1; o >>= 1) {
-            sr += __shfl_xor_sync(0xffffffffu, sr, o);
-            si += __shfl_xor_sync(0xffffffffu, si, o);
+            for (int o = G / 2; o >= 1; o >>= 1) {
+                sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                si += __shfl_xor_sync(0xffffffffu, si, o);
+            }
+            if (on && q == 0) xc[b * g.ne + e] = cmake(sr, si);
         }
-        if (on && q == 0) xc[b * g.ne + e] = cmake(sr, si);
     }
 }
 
-// x[map(b,q)] = sum_e xc[b*ne+e] P[b][e][q]   (MG.h:347-364): one thread per fine dof, e in the reference's order
-static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, int64_t total, const int64_t* __restrict__ block_map,
-                                                        const c128* __restrict__ P, const c128* __restrict__ xc, c128* __restrict__ xf, int add) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int64_t b = t / g.bl, q = t - b * g.bl;
-    const c128* pv = P + b * g.ne * g.bl + q;
-    const c128* a = xc + b * g.ne;
-    c128 acc = cmake(0., 0.);
+// x[map(b,q)] = sum_e xc[b*ne+e] P[b][e][q]   (MG.h:347-364), e in the reference's order.  One warp per aggregate
+// (persistent, like k_restrict_warp): the ne coarse coefficients are warp-uniform, lane l forms the dofs q = l, l+32, ...
+static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
+                                                        const c128* __restrict__ xc, c128* __restrict__ xf, int add) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; b < g.nb; b += nwarps) {
+        c128* xb = xf + agg_first_elem(ag, g.bl, b);
+        const c128* pb = P + b * g.ne * g.bl;
+        const c128* a = xc + b * g.ne;
+        for (int64_t q0 = 0; q0 < g.bl; q0 += 64) {          // two dofs per lane and trip: 2*ne independent loads in flight
+            const int64_t qa = q0 + lane, qb = q0 + 32 + lane;
+            const bool ona = qa < g.bl, onb = qb < g.bl;
+            c128 acca = cmake(0., 0.), accb = cmake(0., 0.);
+            c128* da = ona ? xb + __ldg(q_off + qa) : nullptr;
+            c128* db = onb ? xb + __ldg(q_off + qb) : nullptr;
+            c128 olda = cmake(0., 0.), oldb = cmake(0., 0.);
+            if (add) { if (ona) olda = *da; if (onb) oldb = *db; }
 #pragma unroll 4
-    for (int e = 0; e < g.ne; e++) acc = cadd(acc, cmul(__ldg(a + e), ld_stream(pv + (int64_t)e * g.bl)));
-    const int64_t site = __ldg(block_map + b * g.bs + q / g.dof);
-    c128* dst = xf + site * g.dof + q % g.dof;
-    *dst = add ? cadd(*dst, acc) : acc;   // add: the cycle's x += P xc
+            for (int e = 0; e < g.ne; e++) {
+                const c128 ce = __ldg(a + e);
+                if (ona) acca = cadd(acca, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qa)));
+                if (onb) accb = cadd(accb, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qb)));
+            }
+            if (ona) *da = add ? cadd(olda, acca) : acca;      // add: the cycle's x += P xc
+            if (onb) *db = add ? cadd(oldb, accb) : accb;
+        }
+    }
+}
+
+static AggGeom agg_geom(const LevelGeom& g) {
+    AggGeom a;
+    for (int i = 0; i < 4; i++) { a.bd[i] = (int)g.bd[i]; a.sub[i] = (int)g.sub[i]; a.sd[i] = (int)g.sd[i]; }
+    a.dof = g.dof;
+    a.linear = (g.sub[0] == 1 && g.sub[1] == 1 && g.sub[2] == 1) ? 1 : 0;
+    return a;
 }
 
 static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
     const LevelGeom& g = L.g;
     if (g.nb == 0) return MGCR_OK;
     const double bytes = 16. * L.n * (1 + g.ne) + 16. * L.nc;
+    const AggGeom ag = agg_geom(g);
+    const int64_t resident = (int64_t)ctx->num_sms * 8;       // CTAs of 256 threads the machine holds
     if (g.bl <= 256) {
-        const unsigned grid = (unsigned)((g.nb * 32 + 255) / 256);
         ProfScope ps_(ctx, "mg_restrict", bytes);
-        if (g.bl <= 8) k_restrict_sub<8><<<(unsigned)((g.nb * 8 + 255) / 256), 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
-        else if (g.bl <= 16) k_restrict_sub<16><<<(unsigned)((g.nb * 16 + 255) / 256), 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
-        else if (g.bl <= 64) k_restrict_warp<2><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
-        else if (g.bl <= 128) k_restrict_warp<4><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
-        else k_restrict_warp<8><<<grid, 256, 0, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc);
+        const unsigned grid = (unsigned)std::min<int64_t>(resident, (g.nb * 32 + 255) / 256);
+        if (g.bl <= 8) k_restrict_sub<8><<<(unsigned)std::min<int64_t>(resident, (g.nb * 8 + 255) / 256), 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
+        else if (g.bl <= 16) k_restrict_sub<16><<<(unsigned)std::min<int64_t>(resident, (g.nb * 16 + 255) / 256), 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
+        else if (g.bl <= 64) k_restrict_warp<2><<<grid, 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
+        else if (g.bl <= 128) k_restrict_warp<4><<<grid, 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
+        else k_restrict_warp<8><<<grid, 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
     } else {
         int threads = 32 * (int)std::min<int64_t>(8, std::max<int64_t>(1, g.ne));
         size_t smem = sizeof(c128) * (size_t)g.bl;
-        KLAUNCH(ctx, "mg_restrict", bytes, (k_restrict<<<(unsigned)g.nb, threads, smem, ctx->stream>>>(g, L.d_block_map, L.d_P, xf, xc)));
+        const unsigned grid = (unsigned)std::min<int64_t>(g.nb, (int64_t)ctx->num_sms * 4);
+        KLAUNCH(ctx, "mg_restrict", bytes, (k_restrict<<<grid, threads, smem, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc)));
     }
     CHECK_LAUNCH();
     return MGCR_OK;
@@ -393,7 +448,8 @@ static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
 static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf, bool add = false) {
     const LevelGeom& g = L.g;
     if (L.n == 0) return MGCR_OK;
-    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc, (k_prolong<<<(unsigned)((L.n + 255) / 256), 256, 0, ctx->stream>>>(g, L.n, L.d_block_map, L.d_P, xc, xf, add ? 1 : 0)));
+    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)ctx->num_sms * 8, (g.nb * 32 + 255) / 256);
+    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc, (k_prolong<<<grid, 256, 0, ctx->stream>>>(g, agg_geom(g), L.d_q_off, L.d_P, xc, xf, add ? 1 : 0)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -462,7 +518,7 @@ static int galerkin_launch(mgcr_ctx* ctx, MgLevel& L, const Rows& rows, int32_t*
     const int qc = std::max(1, 256 / g.ne);
     size_t smem = sizeof(c128) * ((size_t)L.K * g.ne * g.ne + (size_t)qc * L.K * g.ne);
     ARG_CHECK(smem <= 200 * 1024, "MG setup: %d near-null vectors per aggregate need %zu bytes of shared memory for the coarse blocks", g.ne, smem);
-    CUDA_TRY(cudaFuncSetAttribute(k_galerkin<Rows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_galerkin<Rows>, (int)smem));
     KLAUNCH(ctx, "mg_galerkin", 0., (k_galerkin<Rows><<<(unsigned)g.nb, 256, smem, ctx->stream>>>(rows, g, L.K, L.Ac->d_brow, L.d_block_map, L.d_site_block,
                                                                                                 L.d_site_off, L.d_P, L.d_Pg, bcol, L.d_bslot, bval)));
     CHECK_LAUNCH();
@@ -598,12 +654,21 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
     const int64_t n = L.n;
     const int nv = c.n_eigen, ne = g.ne;
     // aggregation (Mesh::blocking)
+    SetupStage* stage = new SetupStage(mg, "aggregate");
+    struct StageGuard { SetupStage** s; ~StageGuard() { delete *s; *s = nullptr; } } stage_guard{&stage};
+    auto next_stage = [&](const char* name) { delete stage; stage = new SetupStage(mg, name); };
     MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nsite, &L.d_block_map));
     MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nsite, &L.d_site_block));
     MGCR_TRY(dev_alloc_t(ctx, (size_t)L.nsite, &L.d_site_off));
     int64_t bd[4];
     MGCR_TRY(blocking_device(ctx, g.sd, g.sub, bd, L.d_block_map, L.d_site_block, L.d_site_off));
+    ARG_CHECK(g.bl < (int64_t)INT32_MAX && L.n < ((int64_t)1 << 40), "MG level %d: aggregate too large", l);
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)g.bl, &L.d_q_off));
+    k_agg_offsets<<<(unsigned)std::min<int64_t>(64, (g.bl + 255) / 256), 256, 0, ctx->stream>>>(agg_geom(g), (int)g.bl, L.d_q_off);
+    CHECK_LAUNCH();
     // near-null vectors (Arnoldi::solve) and chirality doubling
+    next_stage("near_null");
+    const double rand_ms0 = ctx->rand_seconds_ms;
     c128* ev = nullptr;
     MGCR_TRY(dev_alloc_t(ctx, (size_t)n * ne, &ev));
     c128* base = doubled ? nullptr : ev;
@@ -624,6 +689,8 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
         MGCR_TRY(dev_free(ctx, raw));
     }
     // block projection into compact storage + per-aggregate Gram-Schmidt
+    mg->setup_s["rand"] += 1e-3 * (ctx->rand_seconds_ms - rand_ms0);   // part of near_null: the init_rand(9) start vector
+    next_stage("project_orthonormalise");
     MGCR_TRY(dev_alloc_t(ctx, (size_t)n * ne, &L.d_P));
     KLAUNCH(ctx, "mg_project", 32. * n * ne, (k_project<<<stream_grid(ctx, n * ne, 8), RED_THREADS, 0, ctx->stream>>>(n * ne, g, n, L.d_block_map, ev, L.d_P)));
     CHECK_LAUNCH();
@@ -631,6 +698,7 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
     KLAUNCH(ctx, "mg_block_mgs", 0., (k_block_mgs<<<(unsigned)g.nb, 128, 0, ctx->stream>>>(g, L.d_P)));
     CHECK_LAUNCH();
     // slab-partitioned level: the prolongator rows of the neighbour ranks' adjacent planes (ghost sites)
+    next_stage("ghost_prolongator");
     const int64_t lo_blocks = g.has_lo ? g.plane_blocks : 0, hi_blocks = g.has_hi ? g.plane_blocks : 0;
     if (dist && (g.has_lo || g.has_hi)) {
         const size_t plane_elems = (size_t)g.plane_sites * g.dof * ne;
@@ -655,6 +723,7 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
         MGCR_TRY(dev_free(ctx, send_hi));
     }
     // Galerkin coarse operator, written straight into the block-CSR compute layout
+    next_stage("galerkin");
     std::vector<int32_t> hrow((size_t)g.nb + 1, 0);
     int kmax = 0;
     {
@@ -683,6 +752,7 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
         CHECK_LAUNCH();
     }
     L.nc_global = L.nc; L.nc_offset = 0;
+    next_stage("coarse_halo_gather");
     if (dist) {
         // the coarse operator inherits the slab partition: one plane of aggregates to / from each neighbour per apply
         MGCR_TRY(dist_allgather_host_i64(ctx, L.nc, L.nc_counts));
@@ -736,6 +806,7 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
 }
 
 static void level_free(mgcr_ctx* ctx, MgLevel& L) {
+    dev_free(ctx, L.d_q_off);
     dev_free(ctx, L.d_block_map); dev_free(ctx, L.d_site_block); dev_free(ctx, L.d_site_off); dev_free(ctx, L.d_P);
     dev_free(ctx, L.d_bslot); dev_free(ctx, L.d_r); dev_free(ctx, L.d_rc); dev_free(ctx, L.d_xc);
     dev_free(ctx, L.d_Pg); dev_free(ctx, L.d_rc_full); dev_free(ctx, L.d_xc_full); dev_free(ctx, L.d_pad);
@@ -765,6 +836,8 @@ extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr
     mg->lv.resize((size_t)n_level);
     for (int l = 0; l < n_level; l++) mg->lv[l].cfg = cfg[l];
     mgcr_op* cur = A;
+    cudaStreamSynchronize(ctx->stream);
+    const auto t_total0 = std::chrono::steady_clock::now();
     for (int l = 0; l < n_level; l++) {
         mg->lv[l].A = cur;
         int st = level_setup(mg, l, l == 0 ? (const c128*)d_nearnull0 : nullptr);
@@ -778,13 +851,32 @@ extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr
         mg->lv[l].deeper = op;
     }
     // the hierarchy is complete: large coarse operators keep only their streaming image (ops.cu, BlockCsrOp::build_sliced)
+    cudaStreamSynchronize(ctx->stream);
+    const auto t_img0 = std::chrono::steady_clock::now();
     for (int l = 0; l < n_level; l++) {
         BlockCsrOp* used = mg->lv[l].gather ? mg->lv[l].Ac_full : mg->lv[l].Ac;
         if (!used) continue;
         if (used->sliced == 0) { int st = used->build_sliced(); if (st != MGCR_OK) { mgcr_mg_destroy(mg); return st; } }
         used->drop_assembly_values();
     }
+    cudaStreamSynchronize(ctx->stream);
+    const auto t_end = std::chrono::steady_clock::now();
+    mg->setup_s["streaming_image"] = std::chrono::duration<double>(t_end - t_img0).count();
+    mg->setup_s["total"] = std::chrono::duration<double>(t_end - t_total0).count();
     *out = mg;
+    return MGCR_OK;
+}
+
+// wall-clock seconds per set-up stage, summed over the levels: "total", "aggregate", "near_null" (Arnoldi::solve; "rand" is
+// its init_rand part), "project_orthonormalise", "ghost_prolongator", "galerkin", "coarse_halo_gather", "streaming_image"
+extern "C" int mgcr_mg_setup_profile(mgcr_mg* mg, int cap, const char** names, double* seconds, int* n_out) {
+    ARG_CHECK(mg && n_out, "mgcr_mg_setup_profile: NULL argument");
+    int i = 0;
+    for (auto& kv : mg->setup_s) {
+        if (i < cap) { if (names) names[i] = kv.first.c_str(); if (seconds) seconds[i] = kv.second; }
+        i++;
+    }
+    *n_out = i;
     return MGCR_OK;
 }
 

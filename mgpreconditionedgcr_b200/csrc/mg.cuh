@@ -27,6 +27,7 @@ struct MgLevel {
     int64_t* d_block_map = nullptr;   // [nb][bs] -> site   (src/Mesh.h:270-293)
     int32_t* d_site_block = nullptr;  // [nsite]
     int32_t* d_site_off = nullptr;    // [nsite]
+    int32_t* d_q_off = nullptr;       // [bl] element offset of in-aggregate position q from the aggregate's first element (restrict / prolong)
     c128* d_P = nullptr;              // compact prolongator [nb][ne][bl]: every fine dof lies in exactly one aggregate
     int8_t* d_bslot = nullptr;        // [nb*K] reference slot (0 self, 2d+1 from the block below in d, 2d+2 from above)
     BlockCsrOp* Ac = nullptr;         // Galerkin coarse operator, owned
@@ -47,6 +48,18 @@ struct mgcr_mg {
     std::vector<MgLevel> lv;
     mgcr_gcr_param eigen, coarse, smooth;
     int flags = 0;
+    // wall-clock seconds of the set-up stages, summed over the levels (stream synchronised at the stage boundaries)
+    std::map<std::string, double> setup_s;
+};
+
+// brackets one set-up stage: synchronises the stream on both sides and adds the wall-clock time to mg->setup_s[name]
+struct SetupStage {
+    mgcr_mg* mg; const char* name; std::chrono::steady_clock::time_point t0;
+    SetupStage(mgcr_mg* m, const char* n) : mg(m), name(n) { cudaStreamSynchronize(mg->ctx->stream); t0 = std::chrono::steady_clock::now(); }
+    ~SetupStage() {
+        cudaStreamSynchronize(mg->ctx->stream);
+        mg->setup_s[name] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
 };
 
 int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* right, const c128* rhs, c128* x, double* hist,

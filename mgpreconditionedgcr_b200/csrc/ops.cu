@@ -402,7 +402,7 @@ struct HopTmaCfg {
     static constexpr int STAGE_BYTES = VAR ? DG_OFF + TX * TY * 8 : X_BYTES;
     static_assert(!VAR || (FY_OFF % 128 == 0 && FX_OFF % 128 == 0 && DG_OFF % 128 == 0 && STAGE_BYTES % 128 == 0), "TMA destinations are 128-byte aligned");
 };
-enum { HOP_TMA_MAX_STAGES = 12 };
+enum { HOP_TMA_MAX_STAGES = 12, HOP_TMA_SMEM = 112 * 1024 };   // two CTAs per SM: 2 x (112 KB + static + 1 KB reserved) <= 228 KB
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -412,11 +412,16 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-struct HopMaps { CUtensorMap x, lo, hi, fz, fy, fx, dg; };
+struct HopMaps { CUtensorMap x, lo, hi, fz, fy, fx, dg, b; };
 
 template <int TX, int TY, bool VAR>
-__global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_tma(const __grid_constant__ HopMaps maps, HopArgs a, int stages) {
+__global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_tma(const __grid_constant__ HopMaps maps, HopArgs a, int stages,
+                                                                                     int stage_bytes) {
     typedef HopTmaCfg<TX, TY, VAR> C;
+    // residual form (a.bsub): the stage of plane z also carries the TX x TY tile of the right-hand side, appended to the
+    // operand (and bond) tiles -- stage_bytes = C::STAGE_BYTES + TX*TY*16 -- so that b arrives through the same ring as x
+    // instead of one exposed HBM-latency load per thread and plane (0.62 of the copy peak in round 1)
+    constexpr int B_OFF = C::STAGE_BYTES;
     extern __shared__ unsigned char hop_smem_raw[];
     __shared__ __align__(8) uint64_t full[HOP_TMA_MAX_STAGES], empty[HOP_TMA_MAX_STAGES];
     unsigned char* ring = (unsigned char*)(((uintptr_t)hop_smem_raw + 127) & ~(uintptr_t)127);
@@ -442,8 +447,9 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                 int zc = (int)z;                                       // z = -1 / n2 without a slab neighbour: out of range, zero-filled
                 if (z < 0 && a.halo_lo) { m = &maps.lo; zc = 0; }
                 else if (z >= a.n2 && a.halo_hi) { m = &maps.hi; zc = 0; }
-                unsigned char* st = ring + (size_t)s * C::STAGE_BYTES;
-                mbar_expect_tx(&full[s], tx_bytes);
+                unsigned char* st = ring + (size_t)s * stage_bytes;
+                const bool own = z >= zs && z < ze;                    // a plane this CTA computes (not a neighbour plane)
+                mbar_expect_tx(&full[s], tx_bytes + ((a.bsub && own) ? (uint32_t)(TX * TY * 16) : 0u));
                 tma_load_3d(st, m, (int)(2 * (x0 - 1)), (int)(y0 - 1), zc, &full[s]);
                 if (VAR) {
                     // bonds below the plane exist for z = 0 .. n2 (n2+1 planes); in-plane bonds and the diagonal only for the
@@ -454,6 +460,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                     tma_load_3d(st + C::FX_OFF, &maps.fx, (int)(x0 - 2), (int)y0, zin, &full[s]);
                     if (use_diag) tma_load_3d(st + C::DG_OFF, &maps.dg, (int)x0, (int)y0, zin, &full[s]);
                 }
+                if (a.bsub && own) tma_load_3d(st + B_OFF, &maps.b, (int)(2 * x0), (int)y0, (int)z, &full[s]);
             }
         }
         return;
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
     const int64_t plane = a.n1 * a.n0;
     const int64_t c_off = gy * a.n0 + gx;
     const int ctr = (ty + 1) * C::ROW + tx + 1;
-    auto stage = [&](int p) -> const unsigned char* { return ring + (size_t)(p % stages) * C::STAGE_BYTES; };
+    auto stage = [&](int p) -> const unsigned char* { return ring + (size_t)(p % stages) * stage_bytes; };
     mbar_wait(&full[0], 0);
     c128 prev = ((const c128*)stage(0))[ctr];
     __syncwarp();
@@ -475,14 +482,8 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
     c128 cur = ((const c128*)stage(1))[ctr];
     double fzm = 0.;
     if (VAR) fzm = ((const double*)(stage(1) + C::FZ_OFF))[ty * TX + tx];
-    // residual form: the right-hand side element of the NEXT plane is requested one plane ahead (a plain load issued right
-    // before its use would expose a DRAM latency per plane and warp)
-    c128 bs_cur = cmake(0., 0.);
-    if (a.bsub && inb) bs_cur = __ldg(a.bsub + zs * plane + c_off);
     for (int p = 1; p + 1 < nplanes; p++) {
         const int64_t z = zs - 1 + p;
-        c128 bs_next = cmake(0., 0.);
-        if (a.bsub && inb && p + 2 < nplanes) bs_next = __ldg(a.bsub + (z + 1) * plane + c_off);
         mbar_wait(&full[(p + 1) % stages], (uint32_t)(((p + 1) / stages) & 1));
         const unsigned char* sn = stage(p + 1);
         const unsigned char* sc = stage(p);
@@ -506,6 +507,8 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
             vyp = cmake(cyp * vyp.x, cyp * vyp.y);
             vzp = cmake(fzp * vzp.x, fzp * vzp.y);
         }
+        c128 bs = cmake(0., 0.);
+        if (a.bsub) bs = ((const c128*)(sc + B_OFF))[ty * TX + tx];
         c128 s = cadd(vzm, vym);
         s = cadd(s, vxm);
         s = cadd(s, vxp);
@@ -520,10 +523,10 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                 else if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
                 s = csub(xr, cmul(a.k, s));
             }
-            if (a.bsub) s = csub(bs_cur, s);
+            if (a.bsub) s = csub(bs, s);
             st_stream(a.y + z * plane + c_off, s);
         }
-        prev = cur; cur = next; fzm = fzp; bs_cur = bs_next;
+        prev = cur; cur = next; fzm = fzp;
     }
 }
 
@@ -560,12 +563,14 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
     static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;
     // two CTAs per SM (registers); the ring takes what shared memory allows: 8 planes of the operand tile in flight per CTA
     // saturate HBM (profiles/r01_stencil_tma_sweep.txt), 4 with the bond / diagonal tiles riding along
-    const int stages_max = std::min((int)HOP_TMA_MAX_STAGES, (int)((111 * 1024 - 128) / C::STAGE_BYTES));
+    const int stage_bytes = C::STAGE_BYTES + (a.bsub ? TX * TY * 16 : 0);
+    const int stages_max = std::min((int)HOP_TMA_MAX_STAGES, (int)((HOP_TMA_SMEM - 128) / stage_bytes));
     const int stages = std::max(3, std::min(stages_max, stages_env > 0 ? stages_env : 8));
-    const size_t smem = (size_t)stages * C::STAGE_BYTES + 128;
+    const size_t smem = (size_t)stages * stage_bytes + 128;
     HopMaps maps;
     MGCR_TRY(hop_tensor_map(&maps.x, a.x, 2 * a.n0, a.n1, a.n2, 2 * (TX + 2), TY + 2));
-    maps.lo = maps.x; maps.hi = maps.x; maps.fz = maps.x; maps.fy = maps.x; maps.fx = maps.x; maps.dg = maps.x;
+    maps.lo = maps.x; maps.hi = maps.x; maps.fz = maps.x; maps.fy = maps.x; maps.fx = maps.x; maps.dg = maps.x; maps.b = maps.x;
+    if (a.bsub) MGCR_TRY(hop_tensor_map(&maps.b, a.bsub, 2 * a.n0, a.n1, a.n2, 2 * TX, TY));
     if (a.halo_lo) MGCR_TRY(hop_tensor_map(&maps.lo, a.halo_lo, 2 * a.n0, a.n1, 1, 2 * (TX + 2), TY + 2));
     if (a.halo_hi) MGCR_TRY(hop_tensor_map(&maps.hi, a.halo_hi, 2 * a.n0, a.n1, 1, 2 * (TX + 2), TY + 2));
     if (VAR) {
@@ -574,8 +579,7 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
         MGCR_TRY(hop_tensor_map(&maps.fx, a.fx, a.n0, a.n1, a.n2, C::FXW, TY));
         if (a.dirac && a.diag) MGCR_TRY(hop_tensor_map(&maps.dg, a.diag, a.n0, a.n1, a.n2, TX, TY));
     }
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_hopping_tma<TX, TY, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 111 * 1024)); attr_set = true; }
+    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_hopping_tma<TX, TY, VAR>, HOP_TMA_SMEM));
     const int64_t nz = z_hi - z_lo;
     dim3 grid((unsigned)((a.n0 + TX - 1) / TX), (unsigned)((a.n1 + TY - 1) / TY), 1);
     // chunks of planes: enough CTAs for ~8 waves of the resident set (the last, partial wave is the tail), but chunks of
@@ -588,7 +592,7 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
     grid.z = (unsigned)((nz + a.zc - 1) / a.zc);
     ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
     a.z_lo = z_lo; a.z_hi = z_hi;
-    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY, VAR><<<grid, C::THREADS, smem, ctx->stream>>>(maps, a, stages)));
+    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY, VAR><<<grid, C::THREADS, smem, ctx->stream>>>(maps, a, stages, stage_bytes)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -596,6 +600,7 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
 HoppingOp::~HoppingOp() {
     for (int d = 0; d < 3; d++) dev_free(ctx, d_face[d]);
     dev_free(ctx, d_halo_lo); dev_free(ctx, d_halo_hi);
+    p2p_halo_destroy(ctx, &ph);
 }
 
 int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag, const c128* bsub) {
@@ -1097,8 +1102,7 @@ template <int NE>
 static int blockcsr_ring_launch(BlockCsrOp* op, const c128* x, const c128* ghost, const c128* bsub, c128* y) {
     mgcr_ctx* ctx = op->ctx;
     const size_t smem = (size_t)op->sl_stages * op->sl_stage_bytes + 128;
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_blockcsr_ring<NE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024)); attr_set = true; }
+    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_blockcsr_ring<NE>, 201 * 1024));
     const int threads = 32 * op->sl_stages;
     const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms, (op->nslices + op->sl_stages - 1) / op->sl_stages);
     k_blockcsr_ring<NE><<<grid, threads, smem, ctx->stream>>>(op->nb, op->nslices, op->d_sl_ptr, op->d_sl_blob, x, ghost, op->n_local / op->ne, bsub, y,
@@ -1237,6 +1241,10 @@ extern "C" int mgcr_op_apply(mgcr_ctx* ctx, mgcr_op* op, const mgcr_c128* x, mgc
     ARG_CHECK(ctx && op && x && y, "mgcr_op_apply: NULL argument");
     return op->apply((const c128*)x, (c128*)y);
 }
+extern "C" int mgcr_op_residual(mgcr_ctx* ctx, mgcr_op* op, const mgcr_c128* x, const mgcr_c128* b, mgcr_c128* r) {
+    ARG_CHECK(ctx && op && x && b && r, "mgcr_op_residual: NULL argument");
+    return op->apply_residual((const c128*)x, (const c128*)b, (c128*)r);
+}
 extern "C" int mgcr_op_dim(mgcr_op* op, int64_t* n_local, int64_t* n_global) {
     ARG_CHECK(op, "mgcr_op_dim: NULL operator");
     if (n_local) *n_local = op->n_local;
@@ -1302,6 +1310,7 @@ int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x) {
 
 void halo_free(mgcr_ctx* ctx, HaloPlan* h) {
     if (!h) return;
+    p2p_halo_destroy(ctx, &h->ph);
     dev_free(ctx, h->d_send_idx); dev_free(ctx, h->d_send_buf); dev_free(ctx, h->d_ghost);
     delete h;
 }

@@ -19,6 +19,7 @@ enum { P2P_AR_MAX = 64, P2P_ALIGN = 256 };
 struct PeerState {
     unsigned char* heap = nullptr;
     size_t bytes = 0, used = 0;
+    std::map<size_t, size_t> free_list;    // offset -> bytes of the areas handed back (coalesced); first fit before the bump pointer
     std::vector<unsigned char*> peer;      // peer[r] = rank r's heap mapped here (peer[rank] = heap)
     size_t ar_off = 0;                     // all-reduce area: [2][nranks][2 * P2P_AR_MAX] uint64
     uint32_t ar_seq = 0;
@@ -28,13 +29,42 @@ struct PeerState {
 static PeerState* state(mgcr_ctx* ctx) { return (PeerState*)ctx->p2p; }
 bool p2p_enabled(mgcr_ctx* ctx) { return ctx->p2p != nullptr; }
 
+// Every rank calls p2p_alloc / p2p_free in the same order with the same sizes (operators and hierarchies are created and
+// destroyed collectively), so first fit over the same free list gives the same offset everywhere.
+static size_t p2p_round(size_t bytes) { return (bytes + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN; }
+static bool p2p_fits(PeerState* s, size_t bytes) {
+    for (auto& kv : s->free_list) if (kv.second >= bytes) return true;
+    return s->used + bytes <= s->bytes;
+}
 int p2p_alloc(mgcr_ctx* ctx, size_t bytes, size_t* off) {
     PeerState* s = state(ctx);
-    bytes = (bytes + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN;
-    if (!s || s->used + bytes > s->bytes) return MGCR_ERR_OOM;
+    bytes = p2p_round(bytes);
+    if (!s) return MGCR_ERR_OOM;
+    for (auto it = s->free_list.begin(); it != s->free_list.end(); ++it) {
+        if (it->second < bytes) continue;
+        *off = it->first;
+        const size_t rest = it->second - bytes;
+        s->free_list.erase(it);
+        if (rest) s->free_list[*off + bytes] = rest;
+        return MGCR_OK;
+    }
+    if (s->used + bytes > s->bytes) return MGCR_ERR_OOM;
     *off = s->used;
     s->used += bytes;
     return MGCR_OK;
+}
+void p2p_free(mgcr_ctx* ctx, size_t off, size_t bytes) {
+    PeerState* s = state(ctx);
+    if (!s || bytes == 0) return;
+    bytes = p2p_round(bytes);
+    auto it = s->free_list.emplace(off, bytes).first;
+    auto nx = std::next(it);
+    if (nx != s->free_list.end() && it->first + it->second == nx->first) { it->second += nx->second; s->free_list.erase(nx); }
+    if (it != s->free_list.begin()) {
+        auto pv = std::prev(it);
+        if (pv->first + pv->second == it->first) { pv->second += it->second; s->free_list.erase(it); it = pv; }
+    }
+    if (it->first + it->second == s->used) { s->used = it->first; s->free_list.erase(it); }   // the top of the heap: lower the bump pointer
 }
 unsigned char* p2p_ptr(mgcr_ctx* ctx, int rank, size_t off) { return state(ctx)->peer[(size_t)rank] + off; }
 
@@ -216,13 +246,35 @@ int p2p_halo_create(mgcr_ctx* ctx, int64_t n, PeerHalo* h) {
     size_t o0, o1, of;
     // all three or nothing: the decision is the same on every rank (same sizes, same allocation order)
     PeerState* s = state(ctx);
-    const size_t need = 2 * ((sizeof(c128) * 2 * (size_t)n + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN) + P2P_ALIGN;
-    if (s->used + need > s->bytes) return MGCR_OK;
-    MGCR_TRY(p2p_alloc(ctx, sizeof(c128) * 2 * (size_t)n, &o0));
-    MGCR_TRY(p2p_alloc(ctx, sizeof(c128) * 2 * (size_t)n, &o1));
-    MGCR_TRY(p2p_alloc(ctx, 256, &of));
+    // one area [buffer 0 | buffer 1 | flags]: all of it or nothing, decided identically on every rank.  When the heap is full
+    // the object keeps exchanging through NCCL send/recv; MGCR_VERBOSE reports it (raise MGCR_P2P_HEAP_MB).
+    const size_t half = p2p_round(sizeof(c128) * 2 * (size_t)n);
+    const size_t need = 2 * half + P2P_ALIGN;
+    if (!p2p_fits(s, need)) {
+        if (getenv("MGCR_VERBOSE")) fprintf(stderr, "mgcr: peer heap full (%zu of %zu bytes used, %zu wanted): this halo uses NCCL send/recv\n", s->used, s->bytes, need);
+        return MGCR_OK;
+    }
+    MGCR_TRY(p2p_alloc(ctx, need, &o0));
+    o1 = o0 + half; of = o1 + half;
+    // A recycled area starts with clean sequence flags, and nobody may store into it before every rank has cleaned its own
+    // and is done with whatever lived there before (its destroy synchronised its stream): one barrier per creation.
+    CUDA_TRY(cudaMemsetAsync(s->heap + of, 0, P2P_ALIGN, ctx->stream));
+    double* d_bar = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, 1, &d_bar));
+    CUDA_TRY(cudaMemsetAsync(d_bar, 0, sizeof(double), ctx->stream));
+    MGCR_TRY(dist_allreduce_sum(ctx, d_bar, 1));   // completes on a rank only when every rank has contributed
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, d_bar);
     h->buf_off[0] = o0; h->buf_off[1] = o1; h->flag_off = of; h->n = n; h->seq = 0; h->on = true;
     return MGCR_OK;
+}
+
+// hands the receive area back (collective in the same sense as its creation: every rank destroys the object)
+void p2p_halo_destroy(mgcr_ctx* ctx, PeerHalo* h) {
+    if (!h->on || !p2p_enabled(ctx)) return;
+    cudaStreamSynchronize(ctx->stream);
+    p2p_free(ctx, h->buf_off[0], 2 * p2p_round(sizeof(c128) * 2 * (size_t)h->n) + P2P_ALIGN);
+    h->on = false;
 }
 
 // sends n elements starting at send_lo to the lower neighbour and at send_hi to the upper one; *recv_lo / *recv_hi point at

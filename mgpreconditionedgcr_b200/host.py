@@ -255,6 +255,17 @@ class Operator:
         check(self.ctx.lib.mgcr_op_apply(self.ctx.h, self.h, f.ptr, out.ptr))
         return out
 
+    def residual(self, x, b, out=None):
+        """b - A x in one pass (numpy in -> numpy out, Field in -> Field out)"""
+        if isinstance(x, np.ndarray):
+            res = Field(self.ctx, self.get_dim())
+            check(self.ctx.lib.mgcr_op_residual(self.ctx.h, self.h, self.ctx.from_numpy(x).ptr, self.ctx.from_numpy(b).ptr, res.ptr))
+            return res.numpy()
+        if out is None:
+            out = Field(self.ctx, self.get_dim())
+        check(self.ctx.lib.mgcr_op_residual(self.ctx.h, self.h, x.ptr, b.ptr, out.ptr))
+        return out
+
     def destroy(self):
         if self.owned and self.h is not None and self.ctx.h:
             self.ctx.lib.mgcr_op_destroy(self.h)
@@ -421,6 +432,15 @@ class MG(Operator):
         h = C.c_void_p()
         check(ctx.lib.mgcr_mg_op_create(ctx.h, mg, C.byref(h)))
         super().__init__(ctx, h, keep=(A, eigen, coarse, smooth))
+
+    def setup_profile(self):
+        """wall-clock seconds per set-up stage (summed over the levels)"""
+        cap = 32
+        names = (C.c_char_p * cap)()
+        sec = (C.c_double * cap)()
+        n = C.c_int()
+        check(self.ctx.lib.mgcr_mg_setup_profile(self.mg, cap, names, sec, C.byref(n)))
+        return {names[i].decode(): sec[i] for i in range(min(n.value, cap))}
 
     def info(self, l=0):
         nf, nb, bl = C.c_int64(), C.c_int64(), C.c_int64()

@@ -9,10 +9,12 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mgpreconditionedgcr_b200 import host  # noqa: E402
 
-kernel = int(sys.argv[1])
-lattices = [[int(v) for v in a.split("x")] for a in sys.argv[2:]] or [[256, 256, 256]]
+args = [a for a in sys.argv[1:] if a != "--residual"]
+residual = "--residual" in sys.argv          # time r = b - A x (the multigrid cycle's form) instead of y = A x
+kernel = int(args[0])
+lattices = [[int(v) for v in a.split("x")] for a in args[1:]] or [[256, 256, 256]]
 ctx = host.Context(0)
-tag = ("var " if os.environ.get("HOP_VAR") else "") + "kernel=%d stages=%s zc=%s tile=%s" % (kernel, os.environ.get("MGCR_HOP_STAGES", "-"), os.environ.get("MGCR_HOP_ZC", "-"), os.environ.get("MGCR_HOP_TILE", "-"))
+tag = ("residual " if residual else "") + ("var " if os.environ.get("HOP_VAR") else "") + "kernel=%d stages=%s zc=%s tile=%s" % (kernel, os.environ.get("MGCR_HOP_STAGES", "-"), os.environ.get("MGCR_HOP_ZC", "-"), os.environ.get("MGCR_HOP_TILE", "-"))
 for dims in lattices:
     V = int(np.prod(dims))
     x = ctx.init_rand(1, V)
@@ -25,12 +27,14 @@ for dims in lattices:
     else:
         A = host.DiracOp(ctx, host.Hopping(ctx, dims), 1.0 / 6.01)
     y = ctx.field(V)
+    b = ctx.init_rand(2, V) if residual else None
+    run = (lambda out: A.residual(x, b, out=out)) if residual else (lambda out: A(x, out=out))
     for _ in range(3):
-        A(x, out=y)
+        run(y)
     ctx.sync()
     ctx.set_profile(True)
     for _ in range(20):
-        A(x, out=y)
+        run(y)
     ctx.sync()
     prof = ctx.profile()
     ctx.set_profile(False)
@@ -39,6 +43,6 @@ for dims in lattices:
     if kernel != 1 and V <= 2 ** 25:
         ctx.set_option("hopping_kernel", 1)
         yr = ctx.field(V)
-        A(x, out=yr)
+        run(yr)
         line += " exact=%s" % bool(np.array_equal(y.numpy(), yr.numpy()))
     print(line, flush=True)

@@ -195,6 +195,11 @@ def test_tma_staged_stencil_is_bit_exact(ctx, host, orc, dims):
         assert np.array_equal(Hv(x), Hvo(x))
         assert np.array_equal(host.DiracOp(ctx, Hv, 1.0, diag=diag)(x), orc.dirac(Hvo, 1.0, diag)(x))
         assert np.array_equal(host.DiracOp(ctx, Hv, k)(x), orc.dirac(Hvo, k)(x))
+        # residual form b - A x: the right-hand side tile rides through the same ring (every operator form)
+        b = orc.init_rand(6, n)
+        for Ad, Ado in ((host.DiracOp(ctx, H, k), orc.dirac(Ho, k)), (host.DiracOp(ctx, H, 0.2, diag=diag), orc.dirac(Ho, 0.2, diag)),
+                        (host.DiracOp(ctx, Hv, 1.0, diag=diag), orc.dirac(Hvo, 1.0, diag)), (host.DiracOp(ctx, Hv, k), orc.dirac(Hvo, k))):
+            assert np.array_equal(Ad.residual(x, b), b - Ado(x))
         # and it agrees with the register-marching form it replaces
         ctx.set_option("hopping_kernel", 1)
         assert np.array_equal(host.DiracOp(ctx, Hv, 1.0, diag=diag)(x), orc.dirac(Hvo, 1.0, diag)(x))

@@ -130,3 +130,22 @@ def test_multigrid_on_the_anisotropic_operator(ctx, host, orc):
     x0 = ctx.field(n).set_zero()
     it0, _ = host.GCR(ctx, A, host.GCR_Param(0, 10, 3000, 1e-10, False, None, None)).solve(ctx.from_numpy(rhs), x0)
     assert it * 3 < it0
+
+
+def test_bench_parameterisation_aniso_against_oracle_64(ctx, host):
+    """mg3d_aniso's parameters (MG_DEFAULT cycle, semi-coarsened aggregates 1x1x8 -> 2x2x4 -> ..., 2/4/4 near-null vectors,
+    outer restart 3, 1e-10) at 64^3 with the level shapes bench.py's CPU arm uses, against the CPU restatement on the same
+    near-null vectors: north-star gates (tests/test_gpu_mg.py::assert_north_star)."""
+    import bench
+    from oracle import parity
+    from test_gpu_mg import assert_north_star
+    wl = bench.WORKLOADS["mg3d_aniso"]
+    dims = wl["cpu_sample"]
+    subs, nes = wl["cpu_mg"]["subs"], wl["cpu_mg"]["n_eigen"]
+    lv = bench.scalar_levels(dims, subs, nes)
+    A, Ao = parity.operators(host, ctx, dims, aniso=wl["aniso"])
+    ref = parity.oracle_solve(Ao, lv, wl["mg"], wl["restart"], wl["max_iter"], wl["tol"])
+    env, spread = parity.oracle_envelope(Ao, ref, nper=2)
+    gpu = parity.gpu_solve(host, ctx, A, lv, wl["mg"], wl["restart"], wl["max_iter"], wl["tol"], ref["rhs"], nearnull=ref["nearnull"])
+    c = assert_north_star(gpu, ref, env, spread)
+    print("parity aniso 64^3:", c, "envelope max %.2e" % env.max())
