@@ -4,8 +4,9 @@
 // and coefficient stays in HBM; semantics follow src/GCR.h:158-302 exactly: r = rhs (x0 is never
 // used to form the residual), conjugated alpha/beta, restart only drops history, max_iter = 0 runs one iteration.
 // Deviations: a right preconditioner is applied in the flexible form z = R(r) (Q4; identical when
-// R is null); left preconditioning is not provided (aborts with a message); the legacy raw-pointer dense solve
-// (src/GCR.h:79-156, only reachable from a commented-out test) is not provided.
+// R is null); a left preconditioner is applied exactly as the reference does (src/GCR.h:201-204, 245-247: r <- L(r) once,
+// Ar <- L(A r) per iteration); the legacy raw-pointer dense solve (src/GCR.h:79-156, only reachable from a commented-out
+// test) is not provided.
 #ifndef MGCR_DROPIN_GCR_H
 #define MGCR_DROPIN_GCR_H
 
@@ -65,12 +66,13 @@ public:
     mgcr_op* device_op() override {
         mgcr_op* a = A_operator->device_op();
         mgcr_op* r = device_of(param->right_precond);
+        mgcr_op* l = device_of(param->left_precond);
         mgcr_gcr_param p = param->c_param();
-        if (!this->handle || a != a_seen || r != r_seen || std::memcmp(&p, &p_seen, sizeof p) != 0) {   // parameters may be edited between calls
+        if (!this->handle || a != a_seen || r != r_seen || l != l_seen || std::memcmp(&p, &p_seen, sizeof p) != 0) {   // parameters may be edited between calls
             this->release_handle();
             p_seen = p;
-            MGCR_CALL(mgcr_gcr_op_create(mgcr::context(), a, &p, device_of(param->left_precond), r, &this->handle));
-            a_seen = a; r_seen = r;
+            MGCR_CALL(mgcr_gcr_op_create(mgcr::context(), a, &p, l, r, &this->handle));
+            a_seen = a; r_seen = r; l_seen = l;
         }
         return this->handle;
     }
@@ -83,7 +85,7 @@ private:
     static mgcr_op* device_of(Operator<num_type>* op) { return op ? op->device_op() : nullptr; }
     Operator<num_type>* A_operator = nullptr;
     GCR_Param<num_type>* param = nullptr;
-    mgcr_op *a_seen = nullptr, *r_seen = nullptr;
+    mgcr_op *a_seen = nullptr, *r_seen = nullptr, *l_seen = nullptr;
     mgcr_gcr_param p_seen = {};
     int last_iterations = 0;
 };

@@ -184,7 +184,9 @@ typedef struct {
 } mgcr_gcr_param;
 
 /* GCR::solve(const Field& rhs, Field& x) (GCR.h:158-302): x += A^-1 rhs (no b - A x0: GCR.h:189).  d_rhs may alias
- * d_x (src/MG.h:102).  `right` (optional) is applied in the flexible form z = R(r); `left` must be NULL.
+ * d_x (src/MG.h:102).  `right` (optional) is applied in the flexible form z = R(r).  `left` (optional) is applied exactly as the
+ * reference does (GCR.h:201-204, 245-247): r <- L(r) once after p = rhs, Ap = A p were formed from the raw right-hand side, then
+ * Ar <- L(A r) in every iteration; what the loop reduces and reports is then L(rhs) - sum alpha Ap.
  * h_hist (optional, hist_cap doubles) receives ||r_g||/||rhs|| for g = 0..iters.  *iters_out = iterations run. */
 int mgcr_gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right,
                    const mgcr_c128* d_rhs, mgcr_c128* d_x, double* h_hist, int hist_cap, int* iters_out);
@@ -218,6 +220,11 @@ enum {
 int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr_level_cfg* cfg, const mgcr_gcr_param* eigen,
                    const mgcr_gcr_param* coarse, const mgcr_gcr_param* smooth, int flags, const mgcr_c128* d_nearnull0,
                    mgcr_mg** out);
+/* the same with near-null vectors for ANY level: d_nearnull is NULL or an array of n_level device pointers (NULL entries: that
+ * level runs Arnoldi::solve); entry l holds cfg[l].n_eigen vectors of the level's (local) length */
+int mgcr_mg_create_nn(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr_level_cfg* cfg, const mgcr_gcr_param* eigen,
+                      const mgcr_gcr_param* coarse, const mgcr_gcr_param* smooth, int flags, const mgcr_c128* const* d_nearnull,
+                      mgcr_mg** out);
 int mgcr_mg_destroy(mgcr_mg* mg);
 /* wall-clock seconds of the set-up stages (names owned by the hierarchy): "total", "aggregate", "near_null" (Arnoldi::solve,
  * MG.h:142-143; "rand" = its init_rand part), "project_orthonormalise" (MG.h:158-198), "ghost_prolongator", "galerkin"

@@ -96,6 +96,7 @@ SIGNATURES = {
     "mgcr_gcr_op_retarget": [_vp, _vp],
     "mgcr_arnoldi": [_vp, _vp, _pgp, _int, _vp],
     "mgcr_mg_create": [_vp, _vp, _int, _plc, _pgp, _pgp, _pgp, _int, _vp, _pvp],
+    "mgcr_mg_create_nn": [_vp, _vp, _int, _plc, _pgp, _pgp, _pgp, _int, _vp, _pvp],
     "mgcr_mg_destroy": [_vp],
     "mgcr_mg_setup_profile": [_vp, _int, C.POINTER(C.c_char_p), _pdbl, _pint],
     "mgcr_mg_level_info": [_vp, _int, _pi64, _pi64, _pint, _pi64],

@@ -111,6 +111,7 @@ struct mgcr_ctx {
     void* nccl_comm = nullptr;
     void* p2p = nullptr;                    // peer-memory state (p2p.cu): mapped heaps of all ranks, NULL = NCCL for everything
     void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
+    int pdl = 1;                            // option "pdl" / MGCR_PDL: programmatic dependent launch of the solve's kernels (launch_pdl)
     int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,
                                             // the exchanges are latency- and skew-bound; profiles/r01_halo_overlap_n8.txt)
     std::vector<cudaEvent_t> depth_events;  // read-back event of each solver nesting depth (gcr.cu)
@@ -182,14 +183,34 @@ static inline int ensure_dyn_smem(mgcr_ctx* ctx, const void* kernel, int bytes) 
 }
 
 // peer-memory exchanges (p2p.cu)
-struct PeerHalo { bool on = false; size_t buf_off[2] = {0, 0}; size_t flag_off = 0; int64_t n = 0; uint32_t seq = 0; };
+struct PeerHalo {
+    bool on = false; size_t buf_off[2] = {0, 0}; size_t flag_off = 0; int64_t n = 0; uint32_t seq = 0;
+    // deferred wait (p2p_halo_exchange(..., defer = true)): the put kernel does not wait for the neighbours' planes; the kernel
+    // that consumes them polls these flags (NULL = no neighbour on that side) for `seq` right before its first ghost access
+    const uint32_t* wait_lo = nullptr; const uint32_t* wait_hi = nullptr;
+};
+// consumer side of a deferred halo wait: spin until the neighbour's flag has reached seq (ld.acquire.sys)
+__device__ __forceinline__ void p2p_flag_wait(const uint32_t* flag, uint32_t seq) {
+    uint32_t v;
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        if ((++spins & 0x3fffu) == 0) {   // a peer that never arrives must not hang this GPU for ever: trap after 60 s
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now; else if (now - t0 > 60000000000ull) __trap();
+        }
+    } while (true);
+}
 int p2p_init(mgcr_ctx* ctx);
 void p2p_destroy(mgcr_ctx* ctx);
 bool p2p_enabled(mgcr_ctx* ctx);
 int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
 int p2p_halo_create(mgcr_ctx* ctx, int64_t n, PeerHalo* h);
 void p2p_halo_destroy(mgcr_ctx* ctx, PeerHalo* h);
-int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi);
+int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi, bool defer = false);
 
 // distributed helpers (dist.cu)
 void dist_destroy(mgcr_ctx* ctx);
@@ -207,6 +228,36 @@ int dist_recv(mgcr_ctx* ctx, void* d_recv, size_t bytes, int peer, cudaStream_t 
 int dist_allgather_host_i64(mgcr_ctx* ctx, int64_t mine, std::vector<int64_t>& all);
 int dist_allgather_host_bytes(mgcr_ctx* ctx, const void* mine, size_t bytes, std::vector<unsigned char>& all);
 int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+
+// ----------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A solve is thousands of short kernels in one stream (12 000 per 512^3 solve at 8 GPUs,
+// 40-100 us each): between two ordinary launches the GPU drains completely, then pays the launch latency and the CTA
+// ramp of the next kernel.  Kernels launched through launch_pdl() carry the programmatic-stream-serialisation attribute:
+// their CTAs are scheduled while the previous kernel's last CTAs are still running and block in PDL_ENTRY() (griddepcontrol.wait)
+// until that kernel has completed and its writes are visible; PDL_ENTRY() then lets the kernel after this one be scheduled
+// in the same way.  Every kernel that is launched this way starts with PDL_ENTRY() before it touches memory; without the
+// attribute the two instructions are no-ops, and any other stream operation in between is an ordinary dependency.
+// ----------------------------------------------------------------------------------------------------------
+#define PDL_ENTRY()                                                       \
+    do {                                                                  \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
+    } while (0)
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(mgcr_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (ctx->pdl && !ctx->profile) ? 1 : 0;   // the profile's event records sit between the kernels anyway
+    (void)cudaLaunchKernelEx(&cfg, kernel, args...);      // a failure is picked up by cudaGetLastError() like a <<<>>> launch
+}
+#endif
 
 // ----------------------------------------------------------------------------------------------------------
 // deterministic reduction: warp shuffle -> shared memory -> one partial per block -> the LAST block to finish

@@ -12,6 +12,8 @@ int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* 
 int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist);
 int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist);
 
+int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, const c128* rhs, c128* x, double* hist,
+                 int hist_cap, int* iters_out);
 int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const c128* rhs, c128* x, double* hist, int hist_cap,
                     int* iters_out, int storage, int restart, int* handled);
 
@@ -19,6 +21,7 @@ struct GcrOp : mgcr_op {
     mgcr_op* A = nullptr;
     mgcr_gcr_param prm;
     mgcr_op* right = nullptr;
+    mgcr_op* left = nullptr;
     c128* d_rand2 = nullptr;   // cached init_rand(2) start vector (src/GCR.h:63-68)
     ~GcrOp() override { dev_free(ctx, d_rand2); }
     int apply(const c128* x, c128* y) override;
@@ -30,7 +33,7 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 template <int NK, int KS>
 static void launch_dot_hist(mgcr_ctx* ctx, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int nh,
                             int std_conj, double* out, const double* guard, double tol2) {
-    k_gcr_dot_hist<NK, KS><<<grid, RED_THREADS, 0, ctx->stream>>>(n, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2);
+    launch_pdl(ctx, k_gcr_dot_hist<NK, KS>, grid, RED_THREADS, 0, n, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2);
 }
 template <int NH>
 static int launch_dot_hist_tma(mgcr_ctx* ctx, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int std_conj,
@@ -42,8 +45,8 @@ static int launch_dot_hist_tma(mgcr_ctx* ctx, int64_t n, const c128* Ar, const c
     const int stages = (int)std::max<size_t>(2, std::min<size_t>(4, (150 * 1024) / stage_bytes));
     const int64_t tiles = (n + (int64_t)RED_THREADS * ept - 1) / ((int64_t)RED_THREADS * ept);
     const int grid = (int)std::min<int64_t>(ctx->num_sms, tiles);
-    k_gcr_dot_hist_tma<NH><<<grid, RED_THREADS, stages * stage_bytes, ctx->stream>>>(n, Ar, Aps, stride, hl, std_conj, ept, stages, out,
-                                                                                    ctx->d_partials, ctx->d_ticket, guard, tol2);
+    launch_pdl(ctx, k_gcr_dot_hist_tma<NH>, grid, RED_THREADS, stages * stage_bytes, n, Ar, Aps, stride, hl, std_conj, ept, stages, out,
+               ctx->d_partials, ctx->d_ticket, guard, tol2);
     return MGCR_OK;
 }
 
@@ -70,8 +73,8 @@ template <int NH, int MINB>
 static void launch_update_p(mgcr_ctx* ctx, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                             int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
                             int bden_off, double* scal, const double* guard, double tol2) {
-    k_gcr_update_p<NH, MINB><<<grid, RED_THREADS, 0, ctx->stream>>>(n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
-                                                                  bden_off, scal, ctx->d_partials, ctx->d_ticket, guard, tol2);
+    launch_pdl(ctx, k_gcr_update_p<NH, MINB>, grid, RED_THREADS, 0, n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
+               bden_off, scal, ctx->d_partials, ctx->d_ticket, guard, tol2);
 }
 static void update_p(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                      int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj, int bden_off,
@@ -106,6 +109,15 @@ struct DepthGuard { DepthGuard() { g_depth++; } ~DepthGuard() { g_depth--; } };
 
 int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* right, const c128* rhs, c128* x, double* hist,
               int hist_cap, int* iters_out) {
+    return gcr_solve_lr(ctx, A, prm, nullptr, right, rhs, x, hist, hist_cap, iters_out);
+}
+
+// `left`: the reference's left preconditioner, replicated operation for operation (src/GCR.h:201-204, 245-247): r <- L(r) ONCE,
+// after p = rhs and Ap = A p have been formed from the raw right-hand side; then Ar <- L(A r) in every iteration.  The first
+// direction is therefore unpreconditioned and what the loop reduces (and prints) is L(rhs) - sum alpha Ap, not a residual of
+// the original system -- the reference's behaviour, kept because it is deterministic (SURVEY.md Appendix B, Q4 for the right side).
+int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, const c128* rhs, c128* x, double* hist,
+                 int hist_cap, int* iters_out) {
     const int64_t n = A->n_local;
     ARG_CHECK(prm->truncation == 0 || prm->restart == 0, "Do not support concurrent restarting and truncation. (src/GCR.h:165)");
     ARG_CHECK(prm->truncation >= 0 && prm->restart >= 0 && prm->max_iter >= 0, "GCR: negative parameter");
@@ -118,7 +130,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     const bool aliased = (rhs == x);
     const int std_conj = prm->std_conj;
     const bool dist = A->distributed;   // vectors are row slabs: partial inner products are all-reduced (NCCL)
-    if (!right) {   // small operators: the whole solve as one persistent cooperative kernel (gcr_small.cu)
+    if (!right && !left) {   // small operators: the whole solve as one persistent cooperative kernel (gcr_small.cu)
         int handled = 0;
         MGCR_TRY(gcr_solve_small(ctx, A, prm, rhs, x, hist, hist_cap, iters_out, storage, restart, &handled));
         if (handled) return MGCR_OK;
@@ -127,7 +139,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     SolveSlot slot;
     MGCR_TRY(acquire_slot(ctx, g_depth - 1, &slot));
 
-    c128 *r = nullptr, *Ar = nullptr, *z = nullptr, *ps = nullptr, *Aps = nullptr, *acc_p = nullptr, *acc_Ap = nullptr;
+    c128 *r = nullptr, *Ar = nullptr, *z = nullptr, *ps = nullptr, *Aps = nullptr, *acc_p = nullptr, *acc_Ap = nullptr, *Lt = nullptr;
     double* scal = nullptr;
     static const int64_t ring_pad = getenv("MGCR_RING_PAD") ? atoll(getenv("MGCR_RING_PAD")) : 0;   // experiment knob
     const int64_t stride = n + ring_pad;
@@ -136,13 +148,14 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     int st = MGCR_OK;
     auto cleanup = [&]() {
         dev_free(ctx, r); dev_free(ctx, Ar); dev_free(ctx, z); dev_free(ctx, ps); dev_free(ctx, Aps);
-        dev_free(ctx, acc_p); dev_free(ctx, acc_Ap); dev_free(ctx, scal);
+        dev_free(ctx, acc_p); dev_free(ctx, acc_Ap); dev_free(ctx, scal); dev_free(ctx, Lt);
     };
 #define GTRY(expr) do { st = (expr); if (st != MGCR_OK) { cleanup(); return st; } } while (0)
 #define GCUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { mgcr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); cleanup(); return MGCR_ERR_CUDA; } } while (0)
     GTRY(dev_alloc_t(ctx, (size_t)n, &r));
     GTRY(dev_alloc_t(ctx, (size_t)n, &Ar));
     if (right) GTRY(dev_alloc_t(ctx, (size_t)n, &z));
+    if (left) GTRY(dev_alloc_t(ctx, (size_t)n, &Lt));
     // a solve of max_iter iterations stores at most max_iter + 1 directions (slot indices stay below that): short smoother /
     // coarse solves with a long nominal restart do not hold the unused ring slots (15 GB per cycle on the 1024x512x512 lattice).
     // Long rings (full GCR: storage = max_iter, src/GCR.h:171-185, whose `new Field[storage]` fills lazily, :208-209) start with
@@ -180,12 +193,22 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     // kernel in the pass that forms the first inner products
     if (right) GTRY(right->apply(rhs, ps));
     GTRY(A->apply(right ? ps : rhs, Aps));
-    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (k_gcr_init<<<grid, RED_THREADS, 0, ctx->stream>>>(n, rhs, Aps, std_conj, r, right ? nullptr : ps, ctx->d_partials, ctx->d_ticket, scal)));
+    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, n, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, scal)));
     GCUDA(cudaGetLastError());
+    if (left) {
+        // r <- L(r) (GCR.h:201-204): the first alpha and the step-0 print use the preconditioned r with the UNpreconditioned Ap
+        GTRY(left->apply(rhs, r));
+        GTRY(vec_dot_dev(ctx, n, std_conj ? Aps : r, std_conj ? r : Aps, scal + S_ANUM, false));   // <r,Ap> (or <Ap,r>), local part
+        GTRY(vec_norm2_dev(ctx, n, r, scal + S_RR, false));
+    }
     if (dist) GTRY(dist_allreduce_sum(ctx, scal, 5));
     // Short solves nobody watches (the smoothers of the multigrid cycle): no read-back at all, the kernels carry the
     // stopping test themselves (gcr_converged) and the host enqueues max_iter iterations back to back.
-    const bool blind = !hist && !iters_out && !prm->verbose && !aliased && !right && prm->max_iter <= 4;
+    // A right preconditioner does not change that: its applies run whether or not the solve has converged (wasted work in the
+    // rare case that a <= 4-iteration solve converges early, but no host round trip per iteration -- the K-cycle's coarse solves
+    // were 235 of the 260 host synchronisations of a 512^3 solve in round 1).
+    static const int blind_precond = env_int("MGCR_BLIND_PRECOND", 1);   // experiment knob: 0 = round-1 behaviour
+    const bool blind = !hist && !iters_out && !prm->verbose && !aliased && !left && prm->max_iter <= 4 && (!right || blind_precond);
     const double* guard = blind ? scal : nullptr;
     const double tol2 = prm->tol * prm->tol;
     double bb = 1., rr = 1.;
@@ -198,6 +221,11 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
         bb = slot.h[0];
         rr = bb;
     }
+    if (left && !blind) {   // step 0 shows ||L(rhs)|| / ||rhs|| (GCR.h:214)
+        GCUDA(cudaMemcpyAsync(slot.h, scal + S_RR, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        GCUDA(cudaStreamSynchronize(ctx->stream));
+        rr = slot.h[0];
+    }
     if (hist && hist_cap > 0) hist[0] = sqrt(rr) / sqrt(bb);
     if (prm->verbose) printf("Step %d residual norm = %.10e\n", 0, sqrt(rr) / sqrt(bb));
 
@@ -205,11 +233,11 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
     do {
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
-        KLAUNCH(ctx, "gcr_update_xr", 96. * n, (k_gcr_update_xr<<<grid, RED_THREADS, 0, ctx->stream>>>(n, ps + (int64_t)cur * stride, Aps + (int64_t)cur * stride, x, r,
-                                                                                          scal, bden_off + cur, ctx->d_partials, ctx->d_ticket, guard, tol2)));
+        KLAUNCH(ctx, "gcr_update_xr", 96. * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, n, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
+                                                                 scal, bden_off + cur, ctx->d_partials, ctx->d_ticket, guard, tol2)));
         GCUDA(cudaGetLastError());
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
-            KLAUNCH(ctx, "vec_norm2", 16. * n, (k_norm2<<<grid, RED_THREADS, 0, ctx->stream>>>(n, x, ctx->d_partials, ctx->d_ticket, scal + S_BB)));
+            KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, n, (const c128*)x, ctx->d_partials, ctx->d_ticket, scal + S_BB)));
             GCUDA(cudaGetLastError());
             if (dist) GTRY(dist_allreduce_sum(ctx, scal + S_BB, 1));
         }
@@ -219,6 +247,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
         if (!final_iter) {
             if (right) { GTRY(right->apply(r, z)); zz = z; }                                      // flexible form of GCR.h:236-238
             GTRY(A->apply(zz, Ar));                                                               // GCR.h:242
+            if (left) { GTRY(left->apply(Ar, Lt)); std::swap(Ar, Lt); }                           // GCR.h:245-247
             lim = std::min(storage, iter);                                                        // GCR.h:251
             for (int c0 = 0; c0 < lim; c0 += GCR_CHUNK) {                                         // GCR.h:257-258 numerators
                 HistList hl;
@@ -281,9 +310,10 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
 extern "C" int mgcr_gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, const mgcr_c128* rhs,
                               mgcr_c128* x, double* hist, int hist_cap, int* iters) {
     ARG_CHECK(ctx && A && prm && rhs && x, "mgcr_gcr_solve: NULL argument");
-    if (left) { mgcr_set_error("mgcr_gcr_solve: left preconditioning (src/GCR.h:201-204,245-247) is not provided"); return MGCR_ERR_UNSUPPORTED; }
     ARG_CHECK(!right || right->n_local == A->n_local, "x dimension does not match with Operator! (src/GCR.h:161)");
-    return gcr_solve(ctx, A, prm, right, (const c128*)rhs, (c128*)x, hist, hist_cap, iters);
+    ARG_CHECK(!left || left->n_local == A->n_local, "x dimension does not match with Operator! (src/GCR.h:161)");
+    ARG_CHECK(!left || rhs != x, "mgcr_gcr_solve: a left-preconditioned solve cannot alias rhs and x");
+    return gcr_solve_lr(ctx, A, prm, left, right, (const c128*)rhs, (c128*)x, hist, hist_cap, iters);
 }
 
 extern "C" int mgcr_gcr_solve_host(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right,
@@ -332,14 +362,13 @@ int GcrOp::apply(const c128* x, c128* y) {
     }
     mgcr_gcr_param p = prm;
     p.verbose = prm.verbose;
-    return gcr_solve(ctx, A, &p, right, x, y, nullptr, 0, nullptr);
+    return gcr_solve_lr(ctx, A, &p, left, right, x, y, nullptr, 0, nullptr);
 }
 
 extern "C" int mgcr_gcr_op_create(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, mgcr_op** out) {
     ARG_CHECK(ctx && A && prm && out, "mgcr_gcr_op_create: NULL argument");
-    if (left) { mgcr_set_error("mgcr_gcr_op_create: left preconditioning is not provided"); return MGCR_ERR_UNSUPPORTED; }
     GcrOp* op = new GcrOp();
-    op->kind = OP_GCR; op->ctx = ctx; op->A = A; op->prm = *prm; op->right = right;
+    op->kind = OP_GCR; op->ctx = ctx; op->A = A; op->prm = *prm; op->right = right; op->left = left;
     op->n_local = A->n_local; op->n_global = A->n_global; op->distributed = A->distributed;
     *out = op;
     return MGCR_OK;

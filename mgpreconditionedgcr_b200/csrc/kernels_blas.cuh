@@ -7,11 +7,13 @@
 #define GRID_STRIDE(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
 
 static __global__ void __launch_bounds__(RED_THREADS) k_fill(int64_t n, c128 v, c128* __restrict__ out) {
+    PDL_ENTRY();
     GRID_STRIDE(i, n) st_stream(out + i, v);
 }
 
 // out = a + s*b   (Field::operator+ / operator- / += / -=; the product is formed first, as `s * field[i]`)
 static __global__ void __launch_bounds__(RED_THREADS) k_axpy(int64_t n, c128 s, const c128* b, const c128* a, c128* out) {
+    PDL_ENTRY();
     GRID_STRIDE(i, n) {
         c128 t = cmul(s, ld_plain(b + i));
         st_stream(out + i, cadd(ld_plain(a + i), t));
@@ -19,12 +21,14 @@ static __global__ void __launch_bounds__(RED_THREADS) k_axpy(int64_t n, c128 s, 
 }
 
 static __global__ void __launch_bounds__(RED_THREADS) k_scale(int64_t n, c128 s, const c128* a, c128* out) {
+    PDL_ENTRY();
     GRID_STRIDE(i, n) st_stream(out + i, cmul(s, ld_plain(a + i)));
 }
 
 // a *= 1./sqrt(*nrm2)   (Field::normalise: `field[i] *= 1./norm`, complex *= real-as-complex... the reference
 // multiplies by the double 1./norm, i.e. component-wise)
 static __global__ void __launch_bounds__(RED_THREADS) k_scale_inv_sqrt(int64_t n, const double* __restrict__ nrm2, c128* a) {
+    PDL_ENTRY();
     const double s = 1. / sqrt(*nrm2);
     GRID_STRIDE(i, n) {
         c128 v = ld_plain(a + i);
@@ -34,6 +38,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_scale_inv_sqrt(int64_t n
 
 static __global__ void __launch_bounds__(RED_THREADS) k_dot(int64_t n, const c128* __restrict__ a, const c128* __restrict__ b,
                                                      double* partials, unsigned int* ticket, double* out) {
+    PDL_ENTRY();
     double v[2] = {0., 0.};
     GRID_STRIDE(i, n) {
         c128 t = cmulc(ld_stream(a + i), ld_stream(b + i));
@@ -44,6 +49,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_dot(int64_t n, const c12
 
 static __global__ void __launch_bounds__(RED_THREADS) k_norm2(int64_t n, const c128* __restrict__ a, double* partials,
                                                        unsigned int* ticket, double* out) {
+    PDL_ENTRY();
     double v[1] = {0.};
     GRID_STRIDE(i, n) {
         c128 t = ld_stream(a + i);
@@ -56,6 +62,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_norm2(int64_t n, const c
 // out[.., s', ..] = in[.., s, ..] with s' = s^2 for s < 4 (0<->2, 1<->3), identity above.
 static __global__ void __launch_bounds__(RED_THREADS) k_gamma5(int64_t n, int64_t inner, int64_t axis_dim, const c128* __restrict__ in,
                                                         c128* __restrict__ out) {
+    PDL_ENTRY();
     GRID_STRIDE(j, n) {
         int64_t s = (j / inner) % axis_dim;
         int64_t src = s < 4 ? (s ^ 2) : s;
@@ -89,6 +96,7 @@ __device__ __forceinline__ bool gcr_converged(const double* guard, double tol2) 
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, const c128* __restrict__ r, const c128* __restrict__ Ap,
                                                           int std_conj, c128* __restrict__ r_out, c128* __restrict__ p_out,
                                                           double* partials, unsigned int* ticket, double* out5) {
+    PDL_ENTRY();
     double v[5] = {0., 0., 0., 0., 0.};
     GRID_STRIDE(i, n) {
         c128 rv = ld_stream(r + i), av = ld_stream(Ap + i);
@@ -108,6 +116,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, cons
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n, const c128* __restrict__ p, const c128* __restrict__ Ap,
                                                                c128* x, c128* r, double* scal, int bden_slot, double* partials,
                                                                unsigned int* ticket, const double* guard, double tol2) {
+    PDL_ENTRY();
     if (gcr_converged(guard, tol2)) return;
     const double aden = scal[S_ADEN];
     const c128 alpha = cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
@@ -179,6 +188,7 @@ template <int NK, int KS>
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                               int64_t stride, HistList hl, int nh, int std_conj, double* out /* 2*nh */,
                                                               double* partials, unsigned int* ticket, const double* guard, double tol2) {
+    PDL_ENTRY();
     if (gcr_converged(guard, tol2)) return;
     constexpr int GT = RED_THREADS / KS;     // threads per group
     constexpr int GW = GT / 32;              // warps per group
@@ -278,6 +288,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int6
                                                                      int64_t stride, HistList hl, int std_conj, int ept, int stages,
                                                                      double* out /* 2*NH */, double* partials, unsigned int* ticket,
                                                                      const double* guard, double tol2) {
+    PDL_ENTRY();
     if (gcr_converged(guard, tol2)) return;
     extern __shared__ __align__(128) unsigned char dot_smem[];
     __shared__ __align__(8) uint64_t full[DOT_TMA_MAX_STAGES];
@@ -349,6 +360,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64
                                                                     c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
                                                                     c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, double* scal,
                                                                     double* partials, unsigned int* ticket, const double* guard, double tol2) {
+    PDL_ENTRY();
     if (gcr_converged(guard, tol2)) return;
     constexpr int NHS = NH > 0 ? NH : 1;
     __shared__ c128 beta[NHS];
@@ -412,6 +424,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64
 // out = a + sign * s * b with the complex scalar s in device memory (Gram-Schmidt updates: src/MG.h:116-118, 192-194)
 static __global__ void __launch_bounds__(RED_THREADS) k_axpy_devscal(int64_t n, const double* __restrict__ s2, double sign, const c128* b,
                                                               const c128* a, c128* out) {
+    PDL_ENTRY();
     const c128 s = cmake(s2[0], s2[1]);
     GRID_STRIDE(i, n) {
         c128 t = cmul(s, ld_plain(b + i));

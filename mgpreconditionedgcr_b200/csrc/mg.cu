@@ -296,6 +296,7 @@ static __global__ void k_agg_offsets(AggGeom a, int bl, int32_t* __restrict__ q_
 // slice of x is gathered into shared memory once, warp w reduces near-null vectors e = w, w+nw, ... with lanes striding over q.
 static __global__ void __launch_bounds__(256) k_restrict(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                          const c128* __restrict__ xf, c128* __restrict__ xc) {
+    PDL_ENTRY();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* xs = (c128*)smem_raw;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -325,6 +326,7 @@ static __global__ void __launch_bounds__(256) k_restrict(LevelGeom g, AggGeom ag
 template <int QPL>
 static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                               const c128* __restrict__ xf, c128* __restrict__ xc) {
+    PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int qo[QPL];
@@ -359,6 +361,7 @@ static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, AggGe
 template <int G>
 static __global__ void __launch_bounds__(256) k_restrict_sub(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                              const c128* __restrict__ xf, c128* __restrict__ xc) {
+    PDL_ENTRY();
     const int q = (int)(threadIdx.x % G);
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
     const int qo = q < g.bl ? __ldg(q_off + q) : 0;
@@ -387,6 +390,7 @@ static __global__ void __launch_bounds__(256) k_restrict_sub(LevelGeom g, AggGeo
 // (persistent, like k_restrict_warp): the ne coarse coefficients are warp-uniform, lane l forms the dofs q = l, l+32, ...
 static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                         const c128* __restrict__ xc, c128* __restrict__ xf, int add) {
+    PDL_ENTRY();
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; b < g.nb; b += nwarps) {
@@ -430,16 +434,16 @@ static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
     if (g.bl <= 256) {
         ProfScope ps_(ctx, "mg_restrict", bytes);
         const unsigned grid = (unsigned)std::min<int64_t>(resident, (g.nb * 32 + 255) / 256);
-        if (g.bl <= 8) k_restrict_sub<8><<<(unsigned)std::min<int64_t>(resident, (g.nb * 8 + 255) / 256), 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
-        else if (g.bl <= 16) k_restrict_sub<16><<<(unsigned)std::min<int64_t>(resident, (g.nb * 16 + 255) / 256), 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
-        else if (g.bl <= 64) k_restrict_warp<2><<<grid, 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
-        else if (g.bl <= 128) k_restrict_warp<4><<<grid, 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
-        else k_restrict_warp<8><<<grid, 256, 0, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc);
+        if (g.bl <= 8) launch_pdl(ctx, k_restrict_sub<8>, (unsigned)std::min<int64_t>(resident, (g.nb * 8 + 255) / 256), 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
+        else if (g.bl <= 16) launch_pdl(ctx, k_restrict_sub<16>, (unsigned)std::min<int64_t>(resident, (g.nb * 16 + 255) / 256), 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
+        else if (g.bl <= 64) launch_pdl(ctx, k_restrict_warp<2>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
+        else if (g.bl <= 128) launch_pdl(ctx, k_restrict_warp<4>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
+        else launch_pdl(ctx, k_restrict_warp<8>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
     } else {
         int threads = 32 * (int)std::min<int64_t>(8, std::max<int64_t>(1, g.ne));
         size_t smem = sizeof(c128) * (size_t)g.bl;
         const unsigned grid = (unsigned)std::min<int64_t>(g.nb, (int64_t)ctx->num_sms * 4);
-        KLAUNCH(ctx, "mg_restrict", bytes, (k_restrict<<<grid, threads, smem, ctx->stream>>>(g, ag, L.d_q_off, L.d_P, xf, xc)));
+        KLAUNCH(ctx, "mg_restrict", bytes, (launch_pdl(ctx, k_restrict, grid, threads, smem, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc)));
     }
     CHECK_LAUNCH();
     return MGCR_OK;
@@ -449,7 +453,7 @@ static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf, bool 
     const LevelGeom& g = L.g;
     if (L.n == 0) return MGCR_OK;
     const unsigned grid = (unsigned)std::min<int64_t>((int64_t)ctx->num_sms * 8, (g.nb * 32 + 255) / 256);
-    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc, (k_prolong<<<grid, 256, 0, ctx->stream>>>(g, agg_geom(g), L.d_q_off, L.d_P, xc, xf, add ? 1 : 0)));
+    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc, (launch_pdl(ctx, k_prolong, grid, 256, 0, g, agg_geom(g), (const int32_t*)L.d_q_off, (const c128*)L.d_P, xc, xf, add ? 1 : 0)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -825,6 +829,14 @@ extern "C" int mgcr_mg_destroy(mgcr_mg* mg) {
 
 extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr_level_cfg* cfg, const mgcr_gcr_param* eigen,
                               const mgcr_gcr_param* coarse, const mgcr_gcr_param* smooth, int flags, const mgcr_c128* d_nearnull0, mgcr_mg** out) {
+    std::vector<const mgcr_c128*> nn((size_t)std::max(n_level, 1), nullptr);
+    nn[0] = d_nearnull0;
+    return mgcr_mg_create_nn(ctx, A, n_level, cfg, eigen, coarse, smooth, flags, nn.data(), out);
+}
+
+extern "C" int mgcr_mg_create_nn(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr_level_cfg* cfg, const mgcr_gcr_param* eigen,
+                                 const mgcr_gcr_param* coarse, const mgcr_gcr_param* smooth, int flags, const mgcr_c128* const* d_nearnull,
+                                 mgcr_mg** out) {
     ARG_CHECK(ctx && A && cfg && eigen && coarse && smooth && out && n_level >= 1, "mgcr_mg_create: bad argument");
     *out = nullptr;
     mgcr_mg* mg = new mgcr_mg();
@@ -840,7 +852,7 @@ extern "C" int mgcr_mg_create(mgcr_ctx* ctx, mgcr_op* A, int n_level, const mgcr
     const auto t_total0 = std::chrono::steady_clock::now();
     for (int l = 0; l < n_level; l++) {
         mg->lv[l].A = cur;
-        int st = level_setup(mg, l, l == 0 ? (const c128*)d_nearnull0 : nullptr);
+        int st = level_setup(mg, l, d_nearnull ? (const c128*)d_nearnull[l] : nullptr);
         if (st != MGCR_OK) { mgcr_mg_destroy(mg); return st; }
         cur = mg->lv[l].gather ? (mgcr_op*)mg->lv[l].Ac_full : (mgcr_op*)mg->lv[l].Ac;
     }

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) k_sell_spmv(int64_t nrow, const int64_t* 
                                                    const c128* __restrict__ val, const c128* __restrict__ x, const c128* __restrict__ ghost,
                                                    int64_t n_local, c128 k, const double* __restrict__ diag, const c128* __restrict__ bsub,
                                                    c128* __restrict__ y) {
+    PDL_ENTRY();
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t slice = row >> 5;
     const int lane = threadIdx.x & 31;
@@ -56,9 +57,9 @@ static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, c
     if (op->nrow == 0) return MGCR_OK;
     int grid = (int)((op->nslices * 32 + 255) / 256);
     if (dirac)
-        KLAUNCH(ctx, "sell_dirac", op->apply_bytes(), (k_sell_spmv<true><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, bsub, y)));
+        KLAUNCH(ctx, "sell_dirac", op->apply_bytes(), (launch_pdl(ctx, k_sell_spmv<true>, grid, 256, 0, op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, bsub, y)));
     else
-        KLAUNCH(ctx, "sell_spmv", op->apply_bytes(), (k_sell_spmv<false><<<grid, 256, 0, ctx->stream>>>(op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, bsub, y)));
+        KLAUNCH(ctx, "sell_spmv", op->apply_bytes(), (launch_pdl(ctx, k_sell_spmv<false>, grid, 256, 0, op->nrow, op->d_slice_ptr, op->d_col, op->d_val, x, ghost, op->n_local, k, diag, bsub, y)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -239,6 +240,7 @@ struct HopArgs {
     int64_t z_lo, z_hi;      // planes [z_lo, z_hi) are computed by this launch (interior / boundary split of the halo overlap)
     const c128* x; c128* y;
     const c128* halo_lo; const c128* halo_hi;   // plane below local z=0 / above z=n2-1 (NULL = Dirichlet)
+    const uint32_t* flag_lo; const uint32_t* flag_hi; uint32_t flag_seq;   // deferred halo wait (p2p.cu): poll before the first read of halo_lo / halo_hi
     int dirac; c128 k; const double* diag;
     const c128* bsub;        // non-NULL: store b - (A x) (the multigrid residual)
     // variable bond coefficients (NULL = unit hopping): fx[i] / fy[i] = bond between site i and i+1 / i+n0,
@@ -320,6 +322,7 @@ enum { HL_THREADS = 512 };
 
 template <bool VAR>
 __global__ void __launch_bounds__(HL_THREADS) k_hopping_l1(HopArgs a, int hl_tx) {
+    PDL_ENTRY();
     const int hl_ty = HL_THREADS / hl_tx;
     const int64_t gx = (int64_t)blockIdx.x * hl_tx + threadIdx.x % hl_tx;
     const int64_t gy = (int64_t)blockIdx.y * hl_ty + threadIdx.x / hl_tx;
@@ -414,14 +417,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
 
 struct HopMaps { CUtensorMap x, lo, hi, fz, fy, fx, dg, b; };
 
-template <int TX, int TY, bool VAR>
-__global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_tma(const __grid_constant__ HopMaps maps, HopArgs a, int stages,
-                                                                                     int stage_bytes) {
+template <int TX, int TY, bool VAR, bool RES>
+__global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_tma(const __grid_constant__ HopMaps maps, HopArgs a, int stages) {
     typedef HopTmaCfg<TX, TY, VAR> C;
-    // residual form (a.bsub): the stage of plane z also carries the TX x TY tile of the right-hand side, appended to the
-    // operand (and bond) tiles -- stage_bytes = C::STAGE_BYTES + TX*TY*16 -- so that b arrives through the same ring as x
-    // instead of one exposed HBM-latency load per thread and plane (0.62 of the copy peak in round 1)
+    // residual form (RES, r = b - A x): the stage of plane z also carries the TX x TY tile of the right-hand side, appended to
+    // the operand (and bond) tiles, so that b arrives through the same ring as x instead of one exposed HBM-latency load per
+    // thread and plane (0.62 of the copy peak in round 1).  A template parameter: the plain apply compiles to the round-1 code.
     constexpr int B_OFF = C::STAGE_BYTES;
+    constexpr int stage_bytes = C::STAGE_BYTES + (RES ? TX * TY * 16 : 0);
     extern __shared__ unsigned char hop_smem_raw[];
     __shared__ __align__(8) uint64_t full[HOP_TMA_MAX_STAGES], empty[HOP_TMA_MAX_STAGES];
     unsigned char* ring = (unsigned char*)(((uintptr_t)hop_smem_raw + 127) & ~(uintptr_t)127);
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    PDL_ENTRY();
     if (threadIdx.x >= C::CONSUMERS) {
         // ---- producer: one elected thread of the last warp ----
         if (threadIdx.x == C::CONSUMERS) {
@@ -445,11 +449,18 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                 const int64_t z = zs - 1 + p;
                 const CUtensorMap* m = &maps.x;
                 int zc = (int)z;                                       // z = -1 / n2 without a slab neighbour: out of range, zero-filled
-                if (z < 0 && a.halo_lo) { m = &maps.lo; zc = 0; }
-                else if (z >= a.n2 && a.halo_hi) { m = &maps.hi; zc = 0; }
+                if (z < 0 && a.halo_lo) {
+                    // the neighbour's plane may still be on its way: only this CTA's first copy waits for it, the chunks in the
+                    // interior of the slab never do.  The copy engine reads through the async proxy: order it after the acquire.
+                    if (a.flag_lo) { p2p_flag_wait(a.flag_lo, a.flag_seq); asm volatile("fence.proxy.async;" ::: "memory"); }
+                    m = &maps.lo; zc = 0;
+                } else if (z >= a.n2 && a.halo_hi) {
+                    if (a.flag_hi) { p2p_flag_wait(a.flag_hi, a.flag_seq); asm volatile("fence.proxy.async;" ::: "memory"); }
+                    m = &maps.hi; zc = 0;
+                }
                 unsigned char* st = ring + (size_t)s * stage_bytes;
                 const bool own = z >= zs && z < ze;                    // a plane this CTA computes (not a neighbour plane)
-                mbar_expect_tx(&full[s], tx_bytes + ((a.bsub && own) ? (uint32_t)(TX * TY * 16) : 0u));
+                mbar_expect_tx(&full[s], tx_bytes + ((RES && own) ? (uint32_t)(TX * TY * 16) : 0u));
                 tma_load_3d(st, m, (int)(2 * (x0 - 1)), (int)(y0 - 1), zc, &full[s]);
                 if (VAR) {
                     // bonds below the plane exist for z = 0 .. n2 (n2+1 planes); in-plane bonds and the diagonal only for the
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                     tma_load_3d(st + C::FX_OFF, &maps.fx, (int)(x0 - 2), (int)y0, zin, &full[s]);
                     if (use_diag) tma_load_3d(st + C::DG_OFF, &maps.dg, (int)x0, (int)y0, zin, &full[s]);
                 }
-                if (a.bsub && own) tma_load_3d(st + B_OFF, &maps.b, (int)(2 * x0), (int)y0, (int)z, &full[s]);
+                if (RES && own) tma_load_3d(st + B_OFF, &maps.b, (int)(2 * x0), (int)y0, (int)z, &full[s]);
             }
         }
         return;
@@ -508,7 +519,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
             vzp = cmake(fzp * vzp.x, fzp * vzp.y);
         }
         c128 bs = cmake(0., 0.);
-        if (a.bsub) bs = ((const c128*)(sc + B_OFF))[ty * TX + tx];
+        if (RES) bs = ((const c128*)(sc + B_OFF))[ty * TX + tx];
         c128 s = cadd(vzm, vym);
         s = cadd(s, vxm);
         s = cadd(s, vxp);
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(HopTmaCfg<TX, TY, VAR>::THREADS, 2) k_hopping_
                 else if (a.diag) { double d = __ldg(a.diag + z * plane + c_off); xr = cmake(d * xr.x, d * xr.y); }
                 s = csub(xr, cmul(a.k, s));
             }
-            if (a.bsub) s = csub(bs, s);
+            if (RES) s = csub(bs, s);
             st_stream(a.y + z * plane + c_off, s);
         }
         prev = cur; cur = next; fzm = fzp;
@@ -555,22 +566,22 @@ static int hop_tensor_map(CUtensorMap* m, const void* base, int64_t inner, int64
     return MGCR_OK;
 }
 
-template <int TX, int TY, bool VAR>
-static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_t z_hi, const char* name, double bytes) {
+template <int TX, int TY, bool VAR, bool RES>
+static int hop_tma_launch_res(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_t z_hi, const char* name, double bytes) {
     typedef HopTmaCfg<TX, TY, VAR> C;
     HopArgs a = a0;
     static const int stages_env = getenv("MGCR_HOP_STAGES") ? atoi(getenv("MGCR_HOP_STAGES")) : 0;   // experiment knobs
     static const int zc_env = getenv("MGCR_HOP_ZC") ? atoi(getenv("MGCR_HOP_ZC")) : 0;
     // two CTAs per SM (registers); the ring takes what shared memory allows: 8 planes of the operand tile in flight per CTA
     // saturate HBM (profiles/r01_stencil_tma_sweep.txt), 4 with the bond / diagonal tiles riding along
-    const int stage_bytes = C::STAGE_BYTES + (a.bsub ? TX * TY * 16 : 0);
+    const int stage_bytes = C::STAGE_BYTES + (RES ? TX * TY * 16 : 0);
     const int stages_max = std::min((int)HOP_TMA_MAX_STAGES, (int)((HOP_TMA_SMEM - 128) / stage_bytes));
     const int stages = std::max(3, std::min(stages_max, stages_env > 0 ? stages_env : 8));
     const size_t smem = (size_t)stages * stage_bytes + 128;
     HopMaps maps;
     MGCR_TRY(hop_tensor_map(&maps.x, a.x, 2 * a.n0, a.n1, a.n2, 2 * (TX + 2), TY + 2));
     maps.lo = maps.x; maps.hi = maps.x; maps.fz = maps.x; maps.fy = maps.x; maps.fx = maps.x; maps.dg = maps.x; maps.b = maps.x;
-    if (a.bsub) MGCR_TRY(hop_tensor_map(&maps.b, a.bsub, 2 * a.n0, a.n1, a.n2, 2 * TX, TY));
+    if (RES) MGCR_TRY(hop_tensor_map(&maps.b, a.bsub, 2 * a.n0, a.n1, a.n2, 2 * TX, TY));
     if (a.halo_lo) MGCR_TRY(hop_tensor_map(&maps.lo, a.halo_lo, 2 * a.n0, a.n1, 1, 2 * (TX + 2), TY + 2));
     if (a.halo_hi) MGCR_TRY(hop_tensor_map(&maps.hi, a.halo_hi, 2 * a.n0, a.n1, 1, 2 * (TX + 2), TY + 2));
     if (VAR) {
@@ -579,7 +590,7 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
         MGCR_TRY(hop_tensor_map(&maps.fx, a.fx, a.n0, a.n1, a.n2, C::FXW, TY));
         if (a.dirac && a.diag) MGCR_TRY(hop_tensor_map(&maps.dg, a.diag, a.n0, a.n1, a.n2, TX, TY));
     }
-    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_hopping_tma<TX, TY, VAR>, HOP_TMA_SMEM));
+    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_hopping_tma<TX, TY, VAR, RES>, HOP_TMA_SMEM));
     const int64_t nz = z_hi - z_lo;
     dim3 grid((unsigned)((a.n0 + TX - 1) / TX), (unsigned)((a.n1 + TY - 1) / TY), 1);
     // chunks of planes: enough CTAs for ~8 waves of the resident set (the last, partial wave is the tail), but chunks of
@@ -592,9 +603,14 @@ static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a0, int64_t z_lo, int64_
     grid.z = (unsigned)((nz + a.zc - 1) / a.zc);
     ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
     a.z_lo = z_lo; a.z_hi = z_hi;
-    KLAUNCH(ctx, name, bytes, (k_hopping_tma<TX, TY, VAR><<<grid, C::THREADS, smem, ctx->stream>>>(maps, a, stages, stage_bytes)));
+    KLAUNCH(ctx, name, bytes, (launch_pdl(ctx, k_hopping_tma<TX, TY, VAR, RES>, grid, C::THREADS, smem, maps, a, stages)));
     CHECK_LAUNCH();
     return MGCR_OK;
+}
+
+template <int TX, int TY, bool VAR>
+static int hop_tma_launch(mgcr_ctx* ctx, const HopArgs& a, int64_t z_lo, int64_t z_hi, const char* name, double bytes) {
+    return a.bsub ? hop_tma_launch_res<TX, TY, VAR, true>(ctx, a, z_lo, z_hi, name, bytes) : hop_tma_launch_res<TX, TY, VAR, false>(ctx, a, z_lo, z_hi, name, bytes);
 }
 
 HoppingOp::~HoppingOp() {
@@ -610,13 +626,19 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
     a.n2 = n2_local; a.n1 = gdims[1]; a.n0 = gdims[2];
     a.x = x; a.y = y; a.dirac = dirac; a.k = k; a.diag = diag;
     a.halo_lo = nullptr; a.halo_hi = nullptr;
+    a.flag_lo = nullptr; a.flag_hi = nullptr; a.flag_seq = 0;
     a.fz = d_face[0]; a.fy = d_face[1]; a.fx = d_face[2];
     const int64_t plane = a.n1 * a.n0;
     const int lo = ctx->rank - 1, hi = ctx->rank + 1;
     const bool has_lo = distributed && lo >= 0, has_hi = distributed && hi < ctx->nranks;
+    const bool tma_form = ctx->hopping_kernel == 2 && a.n0 >= 64 && a.n1 >= 8 && (!var || d_face[1]) && n_local >= ctx->hopping_tma_rows;
     if (distributed && ph.on) {
-        // one plane to each slab neighbour, stored straight into its receive buffer over NVLink (p2p.cu)
-        MGCR_TRY(p2p_halo_exchange(ctx, &ph, x, x + (n2_local - 1) * plane, &a.halo_lo, &a.halo_hi));
+        // one plane to each slab neighbour, stored straight into its receive buffer over NVLink (p2p.cu); the TMA-staged kernel
+        // waits for the neighbours' planes itself, in the producer threads of the CTAs that touch them
+        static const int defer_env = getenv("MGCR_HALO_DEFER") ? atoi(getenv("MGCR_HALO_DEFER")) : 1;
+        const bool defer = tma_form && defer_env && n_local > 0;
+        MGCR_TRY(p2p_halo_exchange(ctx, &ph, x, x + (n2_local - 1) * plane, &a.halo_lo, &a.halo_hi, defer));
+        if (defer) { a.flag_lo = ph.wait_lo; a.flag_hi = ph.wait_hi; a.flag_seq = ph.seq; }
     } else if (distributed) {
         // one plane to each slab neighbour (NCCL send/recv; on the auxiliary stream when the exchange is overlapped)
         cudaStream_t hs;
@@ -644,7 +666,6 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
     // TMA-staged form on lattices at least one tile wide with enough sites to fill the machine (small ones are latency-bound
     // and the register-marching form starts faster: 11 us against 13 us at 40 x 33 x 130)
     static const int tma_tile_env = getenv("MGCR_HOP_TILE") ? atoi(getenv("MGCR_HOP_TILE")) : 0;   // experiment knob: 1 = 32 x 16 tile
-    const bool tma_form = ctx->hopping_kernel == 2 && a.n0 >= 64 && a.n1 >= 8 && (!var || d_face[1]) && n_local >= ctx->hopping_tma_rows;
     auto launch = [&](int64_t z_lo, int64_t z_hi) -> int {   // planes [z_lo, z_hi)
         if (z_hi <= z_lo) return MGCR_OK;
         const int64_t nz = z_hi - z_lo;
@@ -665,9 +686,9 @@ int HoppingOp::run(const c128* x, c128* y, int dirac, c128 k, const double* diag
         ARG_CHECK(grid.y <= 65535 && grid.z <= 65535, "hopping: lattice too large for the launch grid");
         a.z_lo = z_lo; a.z_hi = z_hi;
         if (var)
-            KLAUNCH(ctx, dirac ? "hopping_var_dirac" : "hopping_var", bytes_per_plane * nz, (k_hopping_l1<true><<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
+            KLAUNCH(ctx, dirac ? "hopping_var_dirac" : "hopping_var", bytes_per_plane * nz, (launch_pdl(ctx, k_hopping_l1<true>, grid, HL_THREADS, 0, a, hl_tx)));
         else if (l1_form)
-            KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (k_hopping_l1<false><<<grid, HL_THREADS, 0, ctx->stream>>>(a, hl_tx)));
+            KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (launch_pdl(ctx, k_hopping_l1<false>, grid, HL_THREADS, 0, a, hl_tx)));
         else
             KLAUNCH(ctx, dirac ? "hopping_dirac" : "hopping", bytes_per_plane * nz, (k_hopping<<<grid, HOP_TX * HOP_TY, 0, ctx->stream>>>(a)));
         CHECK_LAUNCH();
@@ -771,6 +792,7 @@ extern "C" int mgcr_hopping_create_dev(mgcr_ctx* ctx, int ndim, const int64_t* d
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RED_THREADS) k_dirac_combine(int64_t n, c128 k, const double* __restrict__ diag, const c128* __restrict__ x,
                                                                c128* y /* in: D x, out: diag.x - k D x */) {
+    PDL_ENTRY();
     GRID_STRIDE(i, n) {
         c128 xr = ld_stream(x + i);
         if (diag) { double d = __ldg(diag + i); xr = cmake(d * xr.x, d * xr.y); }
@@ -785,7 +807,7 @@ int DiracOp::apply(const c128* x, c128* y) {
     if (D->kind == OP_HOPPING) return static_cast<HoppingOp*>(D)->apply_dirac(x, y, k, d_diag);
     MGCR_TRY(D->apply(x, y));
     if (n_local == 0) return MGCR_OK;
-    KLAUNCH(ctx, "dirac_combine", 48. * n_local, (k_dirac_combine<<<stream_grid(ctx, n_local, 8), RED_THREADS, 0, ctx->stream>>>(n_local, k, d_diag, x, y)));
+    KLAUNCH(ctx, "dirac_combine", 48. * n_local, (launch_pdl(ctx, k_dirac_combine, stream_grid(ctx, n_local, 8), RED_THREADS, 0, n_local, k, (const double*)d_diag, x, y)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -869,6 +891,7 @@ __global__ void __launch_bounds__(256) k_blockcsr_apply_ne(int64_t nb, const int
                                                            const c128* __restrict__ bval, const c128* __restrict__ x, const c128* __restrict__ ghost,
                                                            int64_t nb_local_cols, const c128* __restrict__ bsub, c128* __restrict__ y,
                                                            int64_t row0) {
+    PDL_ENTRY();
     const int64_t t = row0 * NE + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // block rows [row0, nb) of this launch
     const int64_t R = t / NE;
     const int r = (int)(t - R * NE);
@@ -926,7 +949,8 @@ template <int NE>
 __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(int64_t nb, int64_t nslices, const int64_t* __restrict__ sl_ptr,
                                                                                 const unsigned char* __restrict__ blob, const c128* __restrict__ x,
                                                                                 const c128* __restrict__ ghost, int64_t nb_local_cols,
-                                                                                const c128* __restrict__ bsub, c128* __restrict__ y, int nst, int stage_bytes) {
+                                                                                const c128* __restrict__ bsub, c128* __restrict__ y, int nst, int stage_bytes,
+                                                                                const uint32_t* flag_lo, const uint32_t* flag_hi, uint32_t flag_seq) {
     constexpr int S = 32 / NE;
     constexpr int SLOT = NE * 512 + S * 4;                 // bytes per block slot: NE columns x 32 lanes of c128, then S int32 columns
     constexpr int PRE = RingCfg<NE>::PRE;
@@ -942,7 +966,17 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    PDL_ENTRY();
     const int rin = lane / NE;
+    // deferred halo wait (p2p.cu): the ghost blocks may still be on their way; a lane polls the neighbours' flags right before
+    // its first ghost access, so only the warps whose slices couple to another rank's aggregates ever wait
+    bool ghost_ok = (flag_lo == nullptr && flag_hi == nullptr);
+    auto ghost_ready = [&]() {
+        if (ghost_ok) return;
+        if (flag_lo) p2p_flag_wait(flag_lo, flag_seq);
+        if (flag_hi) p2p_flag_wait(flag_hi, flag_seq);
+        ghost_ok = true;
+    };
     unsigned char* stage = ring + (size_t)warp * stage_bytes;
     auto fetch = [&](int64_t base, int w) {                // lane 0: start the copy of a slice into this warp's stage
         mbar_expect_tx(&full[warp], (uint32_t)w * SLOT);
@@ -969,6 +1003,7 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
         for (int i = 0; i < PRE; i++) {
             if (i < w) {
                 const int64_t bc = col[i];
+                if (bc >= nb_local_cols) ghost_ready();
                 const c128* xb = bc < nb_local_cols ? x + bc * NE : ghost + (bc - nb_local_cols) * NE;
 #pragma unroll
                 for (int c = 0; c < NE; c++) xv[i][c] = __ldg(xb + c);
@@ -998,6 +1033,7 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
             for (int i = 0; i < PRE; i++) {
                 if (l0 + i < w) {
                     const int64_t bc = ((const int32_t*)(stage + (size_t)(l0 + i) * SLOT + NE * 512))[rin];
+                    if (bc >= nb_local_cols) ghost_ready();
                     const c128* xb = bc < nb_local_cols ? x + bc * NE : ghost + (bc - nb_local_cols) * NE;
 #pragma unroll
                     for (int c = 0; c < NE; c++) xv[i][c] = __ldg(xb + c);
@@ -1025,6 +1061,8 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
 #pragma unroll
         for (int i = 0; i < PRE; i++) col[i] = coln[i];
     }
+    // the exchange is complete when this kernel is: somebody has to have seen both flags even if no row needed a ghost
+    if (blockIdx.x == 0 && threadIdx.x == 0) ghost_ready();
 }
 
 static __global__ void __launch_bounds__(256) k_slice_width(int64_t nb, int64_t nslices, int S, const int32_t* __restrict__ brow, int64_t* __restrict__ width) {
@@ -1105,8 +1143,10 @@ static int blockcsr_ring_launch(BlockCsrOp* op, const c128* x, const c128* ghost
     MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_blockcsr_ring<NE>, 201 * 1024));
     const int threads = 32 * op->sl_stages;
     const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms, (op->nslices + op->sl_stages - 1) / op->sl_stages);
-    k_blockcsr_ring<NE><<<grid, threads, smem, ctx->stream>>>(op->nb, op->nslices, op->d_sl_ptr, op->d_sl_blob, x, ghost, op->n_local / op->ne, bsub, y,
-                                                             op->sl_stages, op->sl_stage_bytes);
+    const PeerHalo* ph = (op->halo && op->halo_deferred) ? &op->halo->ph : nullptr;
+    launch_pdl(ctx, k_blockcsr_ring<NE>, grid, threads, smem, op->nb, op->nslices, (const int64_t*)op->d_sl_ptr, (const unsigned char*)op->d_sl_blob, x, ghost,
+               op->n_local / op->ne, bsub, y, op->sl_stages, op->sl_stage_bytes, ph ? ph->wait_lo : (const uint32_t*)nullptr,
+               ph ? ph->wait_hi : (const uint32_t*)nullptr, ph ? ph->seq : 0u);
     return MGCR_OK;
 }
 
@@ -1125,9 +1165,12 @@ int BlockCsrOp::apply_residual(const c128* x, const c128* b, c128* r) {
 int BlockCsrOp::run(const c128* x, c128* y, const c128* bsub) {
     ARG_CHECK(x != y, "operator apply: input and output alias");
     const c128* ghost = nullptr;
-    if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x)); ghost = halo->ghost_cur; }
+    if (sliced == 0 && nb > 0) MGCR_TRY(build_sliced());
+    // the ring kernel waits for the neighbours' ghost blocks itself (peer-memory halo only)
+    static const int defer_env = getenv("MGCR_HALO_DEFER") ? atoi(getenv("MGCR_HALO_DEFER")) : 1;
+    halo_deferred = halo && halo->ph.on && !halo->d_send_idx && sliced == 1 && nb > 0 && defer_env;
+    if (halo) { MGCR_TRY(halo_exchange(ctx, halo, x, halo_deferred)); ghost = halo->ghost_cur; }
     if (nb == 0) return dist_halo_wait(ctx);
-    if (sliced == 0) MGCR_TRY(build_sliced());
     const double bytes_per_row = (apply_bytes() + (bsub ? 16. * n_local : 0.)) / (double)nb;
     if (sliced == 1 && !(halo && !halo->ph.on && dist_halo_overlap(ctx))) {
         MGCR_TRY(dist_halo_wait(ctx));
@@ -1145,9 +1188,9 @@ int BlockCsrOp::run(const c128* x, c128* y, const c128* bsub) {
         const int grid = (int)(((r1 - r0) * ne + 255) / 256);
         ProfScope ps_(ctx, "blockcsr_apply", bytes_per_row * (r1 - r0));
         switch (ne) {
-            case 2: k_blockcsr_apply_ne<2><<<grid, 256, 0, ctx->stream>>>(r1, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
-            case 4: k_blockcsr_apply_ne<4><<<grid, 256, 0, ctx->stream>>>(r1, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
-            case 8: k_blockcsr_apply_ne<8><<<grid, 256, 0, ctx->stream>>>(r1, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
+            case 2: launch_pdl(ctx, k_blockcsr_apply_ne<2>, grid, 256, 0, r1, (const int32_t*)d_brow, (const int32_t*)d_bcol, (const c128*)d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
+            case 4: launch_pdl(ctx, k_blockcsr_apply_ne<4>, grid, 256, 0, r1, (const int32_t*)d_brow, (const int32_t*)d_bcol, (const c128*)d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
+            case 8: launch_pdl(ctx, k_blockcsr_apply_ne<8>, grid, 256, 0, r1, (const int32_t*)d_brow, (const int32_t*)d_bcol, (const c128*)d_bval, x, ghost, n_local / ne, bsub, y, r0); break;
             default: k_blockcsr_apply<<<grid, 256, 0, ctx->stream>>>(r1, ne, d_brow, d_bcol, d_bval, x, ghost, n_local / ne, bsub, y, r0);
         }
         return MGCR_OK;
@@ -1269,13 +1312,14 @@ extern "C" int mgcr_op_destroy(mgcr_op* op) {
 // ----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RED_THREADS) k_pack(int64_t n_items, int elem, const int32_t* __restrict__ idx, const c128* __restrict__ x,
                                                       c128* __restrict__ buf) {
+    PDL_ENTRY();
     GRID_STRIDE(t, n_items * elem) {
         int64_t it = t / elem; int e = (int)(t - it * elem);
         buf[t] = x[(int64_t)idx[it] * elem + e];
     }
 }
 
-int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x) {
+int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x, bool defer) {
     if (!h || h->npeers == 0) return MGCR_OK;
     h->ghost_cur = h->d_ghost;
     if (h->ph.on && !h->d_send_idx) {
@@ -1285,7 +1329,7 @@ int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x) {
             if (h->peer[p] == ctx->rank - 1) send_lo = x + h->send_start[p] * h->elem;
             if (h->peer[p] == ctx->rank + 1) send_hi = x + h->send_start[p] * h->elem;
         }
-        MGCR_TRY(p2p_halo_exchange(ctx, &h->ph, send_lo, send_hi, &recv_lo, &recv_hi));
+        MGCR_TRY(p2p_halo_exchange(ctx, &h->ph, send_lo, send_hi, &recv_lo, &recv_hi, defer));
         h->ghost_cur = recv_lo ? recv_lo : recv_hi;   // [lower plane][upper plane] contiguous; without a lower neighbour the upper one comes first
         return MGCR_OK;
     }

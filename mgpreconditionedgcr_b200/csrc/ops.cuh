@@ -100,6 +100,7 @@ struct BlockCsrOp : mgcr_op {
     unsigned char* d_sl_blob = nullptr;   // [sl_slots] slots of ne*512 + (32/ne)*4 bytes
     int sl_stages = 0, sl_stage_bytes = 0;   // ring geometry: one stage (the widest slice) per consumer warp
     int sliced = 0;                       // 0 = not tried yet, 1 = built, -1 = not applicable
+    bool halo_deferred = false;           // the latest halo exchange left its wait to the apply kernel (p2p.cu, deferred wait)
     int build_sliced();
     // after the hierarchy is complete nothing reads the assembly copy of a large operator's values any more: give it back
     void drop_assembly_values();
@@ -118,5 +119,5 @@ struct CallbackOp : mgcr_op {
     int apply(const c128* x, c128* y) override;
 };
 
-int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x);
+int halo_exchange(mgcr_ctx* ctx, HaloPlan* h, const c128* x, bool defer = false);
 void halo_free(mgcr_ctx* ctx, HaloPlan* h);

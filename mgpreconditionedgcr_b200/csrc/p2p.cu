@@ -169,6 +169,7 @@ struct PeerPtrs { uint64_t* p[16]; };
 
 // slot layout of one parity: [source rank][2 * P2P_AR_MAX] words, word 2i / 2i+1 = {low / high half of element i, seq}
 static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, uint64_t* mine, int rank, int nranks, int n, uint32_t seq, double* buf) {
+    PDL_ENTRY();
     const int words = 2 * n;
     for (int t = threadIdx.x; t < words * nranks; t += blockDim.x) {
         const int p = t / words, j = t - p * words;
@@ -201,7 +202,7 @@ int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
     const size_t par = (size_t)(s->ar_seq & 1) * (size_t)ctx->nranks * 2 * P2P_AR_MAX * sizeof(uint64_t);
     PeerPtrs pp;
     for (int r = 0; r < ctx->nranks; r++) pp.p[r] = (uint64_t*)(s->peer[(size_t)r] + s->ar_off + par);
-    KLAUNCH(ctx, "p2p_allreduce", 8. * n, (k_p2p_allreduce<<<1, 256, 0, ctx->stream>>>(pp, (uint64_t*)(s->heap + s->ar_off + par), ctx->rank, ctx->nranks, n, s->ar_seq, d_buf)));
+    KLAUNCH(ctx, "p2p_allreduce", 8. * n, (launch_pdl(ctx, k_p2p_allreduce, 1, 256, 0, pp, (uint64_t*)(s->heap + s->ar_off + par), ctx->rank, ctx->nranks, n, s->ar_seq, d_buf)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -219,6 +220,7 @@ __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) { as
 static __global__ void __launch_bounds__(256) k_p2p_halo(const c128* __restrict__ src_lo, c128* __restrict__ dst_lo, uint32_t* flag_at_lo,
                                                          const c128* __restrict__ src_hi, c128* __restrict__ dst_hi, uint32_t* flag_at_hi, int64_t n,
                                                          uint32_t seq, unsigned int* ticket, const uint32_t* my_flag_lo, const uint32_t* my_flag_hi) {
+    PDL_ENTRY();
     __shared__ bool is_last;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -279,7 +281,9 @@ void p2p_halo_destroy(mgcr_ctx* ctx, PeerHalo* h) {
 
 // sends n elements starting at send_lo to the lower neighbour and at send_hi to the upper one; *recv_lo / *recv_hi point at
 // what the neighbours sent (valid once the kernel enqueued here has completed, i.e. for everything enqueued after it)
-int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi) {
+// defer: the kernel only puts and raises the flags; the caller's consumer kernel waits (h->wait_lo / wait_hi / seq), so that the
+// wait for the slowest neighbour overlaps with everything of the consumer that needs no ghost data
+int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi, bool defer) {
     PeerState* s = state(ctx);
     const bool has_lo = ctx->rank > 0, has_hi = ctx->rank + 1 < ctx->nranks;
     h->seq++;
@@ -294,9 +298,11 @@ int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c12
     uint32_t* flag_at_hi = has_hi ? (uint32_t*)(s->peer[(size_t)ctx->rank + 1] + h->flag_off) : nullptr;
     const uint32_t* my_lo = has_lo ? (const uint32_t*)(s->heap + h->flag_off) : nullptr;
     const uint32_t* my_hi = has_hi ? (const uint32_t*)(s->heap + h->flag_off + 128) : nullptr;
+    h->wait_lo = defer ? my_lo : nullptr; h->wait_hi = defer ? my_hi : nullptr;
+    if (defer) { my_lo = nullptr; my_hi = nullptr; }
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(64, (h->n + 255) / 256));
     KLAUNCH(ctx, "p2p_halo", 32. * h->n * ((has_lo ? 1 : 0) + (has_hi ? 1 : 0)),
-            (k_p2p_halo<<<grid, 256, 0, ctx->stream>>>(send_lo, dst_lo, flag_at_lo, send_hi, dst_hi, flag_at_hi, h->n, h->seq, s->d_ticket, my_lo, my_hi)));
+            (launch_pdl(ctx, k_p2p_halo, grid, 256, 0, send_lo, dst_lo, flag_at_lo, send_hi, dst_hi, flag_at_hi, h->n, h->seq, s->d_ticket, my_lo, my_hi)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }

@@ -42,14 +42,14 @@ extern "C" int mgcr_vec_set_constant(mgcr_ctx* ctx, int64_t n, double re, double
         CUDA_TRY(cudaMemsetAsync(v, 0, sizeof(c128) * (size_t)n, ctx->stream));
         return MGCR_OK;
     }
-    KLAUNCH(ctx, "vec_fill", 16. * n, (k_fill<<<stream_grid(ctx, n, 8), RED_THREADS, 0, ctx->stream>>>(n, cmake(re, im), (c128*)v)));
+    KLAUNCH(ctx, "vec_fill", 16. * n, (launch_pdl(ctx, k_fill, stream_grid(ctx, n, 8), RED_THREADS, 0, n, cmake(re, im), (c128*)v)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
 
 int vec_axpy(mgcr_ctx* ctx, int64_t n, c128 s, const c128* b, const c128* a, c128* out) {
     if (n == 0) return MGCR_OK;
-    KLAUNCH(ctx, "vec_axpy", 48. * n, (k_axpy<<<stream_grid(ctx, n, 8), RED_THREADS, 0, ctx->stream>>>(n, s, b, a, out)));
+    KLAUNCH(ctx, "vec_axpy", 48. * n, (launch_pdl(ctx, k_axpy, stream_grid(ctx, n, 8), RED_THREADS, 0, n, s, b, a, out)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -61,7 +61,7 @@ extern "C" int mgcr_vec_axpy(mgcr_ctx* ctx, int64_t n, double s_re, double s_im,
 
 int vec_scale(mgcr_ctx* ctx, int64_t n, c128 s, const c128* a, c128* out) {
     if (n == 0) return MGCR_OK;
-    KLAUNCH(ctx, "vec_scale", 32. * n, (k_scale<<<stream_grid(ctx, n, 8), RED_THREADS, 0, ctx->stream>>>(n, s, a, out)));
+    KLAUNCH(ctx, "vec_scale", 32. * n, (launch_pdl(ctx, k_scale, stream_grid(ctx, n, 8), RED_THREADS, 0, n, s, a, out)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -73,14 +73,14 @@ extern "C" int mgcr_vec_scale(mgcr_ctx* ctx, int64_t n, double s_re, double s_im
 
 // device-resident result: d_out[0..1] = sum conj(a) b (this rank's part, then all-reduced)
 int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist) {
-    KLAUNCH(ctx, "vec_dot", 32. * n, (k_dot<<<stream_grid(ctx, n, 4, 2), RED_THREADS, 0, ctx->stream>>>(n, a, b, ctx->d_partials, ctx->d_ticket, d_out)));
+    KLAUNCH(ctx, "vec_dot", 32. * n, (launch_pdl(ctx, k_dot, stream_grid(ctx, n, 4, 2), RED_THREADS, 0, n, a, b, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
     if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 2));
     return MGCR_OK;
 }
 
 int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist) {
-    KLAUNCH(ctx, "vec_norm2", 16. * n, (k_norm2<<<stream_grid(ctx, n, 4, 2), RED_THREADS, 0, ctx->stream>>>(n, a, ctx->d_partials, ctx->d_ticket, d_out)));
+    KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, stream_grid(ctx, n, 4, 2), RED_THREADS, 0, n, a, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
     if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 1));
     return MGCR_OK;
@@ -108,7 +108,7 @@ extern "C" int mgcr_vec_squarednorm(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a
 // a *= 1/sqrt(sum |a|^2), scalar never leaves the device (src/Fields.h:237-243)
 int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist) {
     MGCR_TRY(vec_norm2_dev(ctx, n, a, ctx->d_scratch + 8, dist));
-    KLAUNCH(ctx, "vec_normalise", 32. * n, (k_scale_inv_sqrt<<<stream_grid(ctx, n, 8), RED_THREADS, 0, ctx->stream>>>(n, ctx->d_scratch + 8, a)));
+    KLAUNCH(ctx, "vec_normalise", 32. * n, (launch_pdl(ctx, k_scale_inv_sqrt, stream_grid(ctx, n, 8), RED_THREADS, 0, n, (const double*)(ctx->d_scratch + 8), a)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }

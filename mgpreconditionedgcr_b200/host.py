@@ -258,8 +258,8 @@ class Operator:
     def residual(self, x, b, out=None):
         """b - A x in one pass (numpy in -> numpy out, Field in -> Field out)"""
         if isinstance(x, np.ndarray):
-            res = Field(self.ctx, self.get_dim())
-            check(self.ctx.lib.mgcr_op_residual(self.ctx.h, self.h, self.ctx.from_numpy(x).ptr, self.ctx.from_numpy(b).ptr, res.ptr))
+            fx, fb, res = self.ctx.from_numpy(x), self.ctx.from_numpy(b), Field(self.ctx, self.get_dim())   # all three alive during the call
+            check(self.ctx.lib.mgcr_op_residual(self.ctx.h, self.h, fx.ptr, fb.ptr, res.ptr))
             return res.numpy()
         if out is None:
             out = Field(self.ctx, self.get_dim())
@@ -390,12 +390,13 @@ class GCR(Operator):
         """the same through host buffers (numpy in, numpy out)"""
         p = self.param
         right = getattr(p, "right_precond", None)
+        left = getattr(p, "left_precond", None)
         rhs = capi.c128(rhs)
         x = capi.c128(x0).copy()
         cap = p.max_iter + 2
         hist = np.zeros(cap)
         it = C.c_int()
-        check(self.ctx.lib.mgcr_gcr_solve_host(self.ctx.h, self.A.h, C.byref(p), None, right.h if right else None, capi.ptr(rhs),
+        check(self.ctx.lib.mgcr_gcr_solve_host(self.ctx.h, self.A.h, C.byref(p), left.h if left else None, right.h if right else None, capi.ptr(rhs),
                                                capi.ptr(x), capi.ptr(hist), cap, C.byref(it)))
         return x, it.value, hist[: it.value + 1].copy()
 
@@ -421,12 +422,15 @@ class MG(Operator):
             cfg[i].sub[:] = list(lv["sub"])
             cfg[i].n_spin, cfg[i].n_col, cfg[i].n_eigen = lv.get("n_spin", 1), lv.get("n_col", 1), lv["n_eigen"]
         flags = (capi.MG_NEG_NEIGHBOUR_BUG if neg_bug else 0) | (capi.MG_STD_CONJ if std_conj else 0)
-        nn = None
-        if nearnull is not None:
-            nn = nearnull if isinstance(nearnull, Field) else ctx.from_numpy(np.asarray(nearnull).reshape(-1))
+        # nearnull: the level-0 vectors (array / Field), or a list with one entry per level (None = own inverse iteration)
+        per_level = list(nearnull) if isinstance(nearnull, (list, tuple)) else [nearnull] + [None] * (len(levels) - 1)
+        assert len(per_level) == len(levels)
+        nn = [None if v is None else (v if isinstance(v, Field) else ctx.from_numpy(np.asarray(v).reshape(-1))) for v in per_level]
+        ptrs = (C.c_void_p * len(levels))(*[None if v is None else v.ptr.value for v in nn])
         mg = C.c_void_p()
-        check(ctx.lib.mgcr_mg_create(ctx.h, A.h, len(levels), cfg, C.byref(eigen), C.byref(coarse), C.byref(smooth), flags,
-                                     nn.ptr if nn is not None else None, C.byref(mg)))
+        check(ctx.lib.mgcr_mg_create_nn(ctx.h, A.h, len(levels), cfg, C.byref(eigen), C.byref(coarse), C.byref(smooth), flags,
+                                        ptrs, C.byref(mg)))
+        del nn
         self.mg = mg
         self.levels = levels
         h = C.c_void_p()

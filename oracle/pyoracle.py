@@ -41,6 +41,7 @@ def lib():
     if _LIB is None:
         L = C.CDLL(build())
         L.orc_init_rand.argtypes = [C.c_int, C.c_long, _cp]
+        L.orc_set_sum_order.argtypes = [C.c_int]
         L.orc_dot.argtypes = [C.c_long, _cp, _cp, _dp]
         L.orc_squarednorm.argtypes = [C.c_long, _cp]
         L.orc_squarednorm.restype = C.c_double
@@ -68,12 +69,18 @@ def lib():
         L.orc_op_apply.argtypes = [C.c_void_p, _cp, _cp]
         L.orc_gcr_solve.argtypes = [C.c_void_p, C.POINTER(GcrParam), C.c_void_p, _cp, _cp, C.c_void_p, C.c_int]
         L.orc_gcr_solve.restype = C.c_int
+        L.orc_gcr_solve_lr.argtypes = [C.c_void_p, C.POINTER(GcrParam), C.c_void_p, C.c_void_p, _cp, _cp, C.c_void_p, C.c_int]
+        L.orc_gcr_solve_lr.restype = C.c_int
         L.orc_gcr_op_new.argtypes = [C.c_void_p, C.POINTER(GcrParam), C.c_void_p, C.c_int]
         L.orc_gcr_op_new.restype = C.c_void_p
         L.orc_arnoldi.argtypes = [C.c_void_p, C.POINTER(GcrParam), C.c_int, _cp]
         L.orc_mg_new.argtypes = [C.c_void_p, C.c_int, C.POINTER(LevelCfg), C.POINTER(GcrParam), C.POINTER(GcrParam),
                                  C.POINTER(GcrParam), C.c_int, C.c_int, C.c_void_p]
         L.orc_mg_new.restype = C.c_void_p
+        L.orc_mg_new_nn.argtypes = [C.c_void_p, C.c_int, C.POINTER(LevelCfg), C.POINTER(GcrParam), C.POINTER(GcrParam),
+                                    C.POINTER(GcrParam), C.c_int, C.c_int, C.c_void_p]
+        L.orc_mg_new_nn.restype = C.c_void_p
+        L.orc_mg_export_nearnull.argtypes = [C.c_void_p, C.c_int, _cp]
         L.orc_mg_free.argtypes = [C.c_void_p]
         for f in ("orc_mg_nblocks", "orc_mg_block_len"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int]
@@ -100,6 +107,11 @@ def _c(a):
 
 def _l(a):
     return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def set_sum_order(mode):
+    """0 = the reference's left-to-right inner products (default); 1 = right to left; 2 = blocked -- see mgcr_oracle.c"""
+    lib().orc_set_sum_order(int(mode))
 
 
 def init_rand(seed, n):
@@ -188,8 +200,9 @@ def gcr_param(truncation=0, restart=0, max_iter=100, tol=1e-16, std_conj=0):
     return GcrParam(truncation, restart, max_iter, tol, std_conj)
 
 
-def gcr_solve(A, param, rhs, x0=None, precond=None, alias=False):
-    """Returns (x, hist, iters).  alias=True solves with rhs and x the same buffer (src/MG.h:102)."""
+def gcr_solve(A, param, rhs, x0=None, precond=None, alias=False, left=None):
+    """Returns (x, hist, iters).  alias=True solves with rhs and x the same buffer (src/MG.h:102).  left: the reference's
+    left preconditioner (src/GCR.h:201-204, 245-247)."""
     n = A.n
     cap = param.max_iter + 2
     hist = np.zeros(cap)
@@ -199,6 +212,10 @@ def gcr_solve(A, param, rhs, x0=None, precond=None, alias=False):
     else:
         rhs_buf = _c(rhs)
         x = np.zeros(n, dtype=c128) if x0 is None else _c(x0).copy()
+    if left is not None:
+        it = lib().orc_gcr_solve_lr(A.h, C.byref(param), left.h, precond.h if precond is not None else None, rhs_buf, x,
+                                    hist.ctypes.data_as(C.c_void_p), cap)
+        return x, hist[: it + 1].copy(), it
     it = lib().orc_gcr_solve(A.h, C.byref(param), precond.h if precond is not None else None, rhs_buf, x,
                              hist.ctypes.data_as(C.c_void_p), cap)
     return x, hist[: it + 1].copy(), it
@@ -223,18 +240,30 @@ class MG:
             cfg[i].site_dims[:] = list(lv["site_dims"])
             cfg[i].sub[:] = list(lv["sub"])
             cfg[i].n_spin, cfg[i].n_col, cfg[i].n_eigen = lv.get("n_spin", 1), lv.get("n_col", 1), lv["n_eigen"]
+        self.A = A
+        self.levels = levels
+        self.n_level = len(levels)
+        if isinstance(nearnull, (list, tuple)):   # one entry per level (None = the level runs its own inverse iteration)
+            self._nn = [None if v is None else _c(np.asarray(v).reshape(-1)) for v in nearnull]
+            arr = (C.c_void_p * len(levels))(*[None if v is None else v.ctypes.data for v in self._nn])
+            self.h = lib().orc_mg_new_nn(A.h, len(levels), cfg, C.byref(eigen), C.byref(coarse), C.byref(smooth), int(neg_bug), int(std_conj), arr)
+            return
         nn = None
         if nearnull is not None:
             self._nn = _c(np.asarray(nearnull).reshape(-1))
             nn = self._nn.ctypes.data_as(C.c_void_p)
-        self.A = A
-        self.levels = levels
-        self.n_level = len(levels)
         self.h = lib().orc_mg_new(A.h, len(levels), cfg, C.byref(eigen), C.byref(coarse), C.byref(smooth),
                                   int(neg_bug), int(std_conj), nn)
 
     def nblocks(self, l=0):
         return lib().orc_mg_nblocks(self.h, l)
+
+    def nearnull(self, l=0):
+        """the n_eigen near-null vectors level l was built from, shape (n_eigen, n_l)"""
+        n = self.A.n if l == 0 else self.nblocks(l - 1) * self.ne(l - 1)
+        out = np.empty(self.levels[l]["n_eigen"] * n, dtype=c128)
+        lib().orc_mg_export_nearnull(self.h, l, out)
+        return out.reshape(self.levels[l]["n_eigen"], n)
 
     def ne(self, l=0):
         return lib().orc_mg_ne(self.h, l)

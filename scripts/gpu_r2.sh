@@ -1,0 +1,56 @@
+#!/bin/bash
+# Round-2 GPU call driver: scripts/gpu_r2.sh <stage> [...]   (run under gpurun; everything lands in gpurun_out/)
+#   tests      pytest -m gpu (all failures shown, no -x)
+#   hop        stencil microbenchmark: plain / residual, unit / variable coefficients
+#   bench      default bench.py (headline + parity + other workloads)
+#   quick      bench.py without cpu baseline / secondary workloads (1 step)
+#   launches   ncu launch list of the quick bench
+#   ncufull    ncu --set full of the transfer + residual-stencil kernels
+cd "$(dirname "$0")/.." || exit 1
+O=gpurun_out; mkdir -p $O
+TAG=${TAG:-r02}
+for stage in "$@"; do
+case $stage in
+tests)
+    timeout 1500 python -m pytest tests -m gpu -q -s > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_gpu.log
+    grep -E "passed|failed|error|parity" $O/${TAG}_pytest_gpu.log | tail -15 ;;
+hop)
+    : > $O/${TAG}_hop.txt
+    for sz in 512x512x512 256x256x256 64x512x512; do
+        timeout 200 python scripts/hop_bench.py 2 $sz >> $O/${TAG}_hop.txt 2>&1
+        timeout 200 python scripts/hop_bench.py 2 --residual $sz >> $O/${TAG}_hop.txt 2>&1
+    done
+    HOP_VAR=1 timeout 200 python scripts/hop_bench.py 2 512x256x512 >> $O/${TAG}_hop.txt 2>&1
+    HOP_VAR=1 timeout 200 python scripts/hop_bench.py 2 --residual 512x256x512 >> $O/${TAG}_hop.txt 2>&1
+    cat $O/${TAG}_hop.txt ;;
+hopab)
+    # same box, same minute: the round-1 library (build/r1, made from commit 315125a) against the current one
+    : > $O/${TAG}_hopab.txt
+    for i in 1 2; do
+        for sz in 512x512x512 256x256x256; do
+            (cd build/r1 && timeout 200 python scripts/hop_bench.py 2 $sz 2>&1 | sed 's/^/r1  /') >> $O/${TAG}_hopab.txt
+            timeout 200 python scripts/hop_bench.py 2 $sz 2>&1 | sed 's/^/now /' >> $O/${TAG}_hopab.txt
+            MGCR_PDL=0 timeout 200 python scripts/hop_bench.py 2 $sz 2>&1 | sed 's/^/now pdl=0 /' >> $O/${TAG}_hopab.txt
+        done
+    done
+    cat $O/${TAG}_hopab.txt ;;
+bench)
+    timeout 900 python bench.py > $O/${TAG}_bench_default_n1.json 2> $O/${TAG}_bench_default_n1.err; echo "bench rc=$?"
+    python scripts/bench_brief.py $O/${TAG}_bench_default_n1.json ;;
+quick)
+    timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-others > $O/${TAG}_bench_quick_n1.json 2> $O/${TAG}_bench_quick_n1.err; echo "quick rc=$?"
+    python scripts/bench_brief.py $O/${TAG}_bench_quick_n1.json ;;
+launches)
+    CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-others --max-iter 2"
+    $CMD > $O/ncu_plain.log 2>&1 || { echo plain failed; tail -5 $O/ncu_plain.log; continue; }
+    timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file $O/${TAG}_launches_mg3d_512.csv $CMD > $O/ncu_a.log 2>&1; tail -1 $O/ncu_a.log ;;
+ncufull)
+    CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-others --max-iter 2"
+    $CMD > $O/ncu_plain.log 2>&1 || { echo plain failed; tail -5 $O/ncu_plain.log; continue; }
+    # set-up launches come first (Arnoldi: ~140 stencil applies); skip them so that the captures are the solve's fine-level launches
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_restrict_warp|k_prolong' --launch-skip 0 -c 6 -f -o $O/${TAG}_mg512_transfer $CMD > $O/ncu_c.log 2>&1; tail -1 $O/ncu_c.log
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_hopping_tma' --launch-skip 150 -c 8 -f -o $O/${TAG}_mg512_stencil $CMD > $O/ncu_d.log 2>&1; tail -1 $O/ncu_d.log
+    ls -la $O/*.ncu-rep ;;
+*) echo "unknown stage $stage" ;;
+esac
+done

@@ -45,40 +45,60 @@ def relerr(a, b):
 HIST_TOL = 1e-10
 
 
-def reference_envelope(solve_ref, ref_hist, it_ref, nper=4, eps=1e-16):
-    """How far the REFERENCE algorithm moves away from its own residual history when its right-hand side is perturbed
-    at the 1e-16 level (less than one rounding of the input).  Restarted/truncated GCR amplifies such noise
-    exponentially ("parity horizon"): on the shipped sample the history is reproducible to 1e-10 for ~40-200
-    iterations depending on the mode, on symmetric stencil operators for ~25.  Any implementation that sums in a
-    different order is a perturbation of exactly this kind, so this envelope is the tightest bar a parallel reduction
-    can be held to.  solve_ref(eps_vector) -> (hist, iters).  Returns (running-max envelope per iteration, iteration
-    count spread)."""
+ULP = 2.220446049250313e-16
+
+
+def reference_envelope(solve_ref, ref_hist, it_ref, nper=3, eps=ULP):
+    """How far the REFERENCE algorithm (the restatement, pinned bit-exactly to the reference) moves away from its own residual
+    history under changes that leave it the same algorithm in exact arithmetic: its inner products summed right to left and in
+    blocks instead of left to right (a sequential sum of n terms carries a rounding error ~sqrt(n) ulp that every parallel
+    reduction replaces by another one), and its right-hand side changed by one unit in the last place (every element times
+    1 +- 2^-52, random sign), `nper` times.  Restarted / truncated GCR amplifies such noise exponentially ("parity
+    horizon"): on the shipped sample the history is reproducible to 1e-10 for ~40-200 iterations depending on the mode, on
+    symmetric stencil operators for ~25.  This envelope is the tightest bar a parallel reduction can be held to.
+    solve_ref(rng, eps) -> (hist, iters).  Returns (running-max envelope per iteration -- finite everywhere: beyond the end
+    of a shorter run its last deviation is carried --, iteration count spread)."""
+    from oracle import pyoracle
     env = np.zeros(len(ref_hist))
     spread = 0
-    for s in range(nper):
-        h, it = solve_ref(np.random.default_rng(100 + s), eps)
+
+    def account(h, it):
+        nonlocal spread
         n = min(len(h), len(ref_hist))
         rel = np.maximum.accumulate(np.abs(h[:n] - ref_hist[:n]) / ref_hist[:n])
         env[:n] = np.maximum(env[:n], rel)
-        env[n:] = np.inf
+        env[n:] = np.maximum(env[n:], rel[-1])
         spread = max(spread, abs(it - it_ref))
+
+    for mode in (1, 2):
+        pyoracle.set_sum_order(mode)
+        try:
+            h, it = solve_ref(np.random.default_rng(0), 0.0)
+        finally:
+            pyoracle.set_sum_order(0)
+        account(h, it)
+    for s in range(nper):
+        h, it = solve_ref(np.random.default_rng(100 + s), eps)
+        account(h, it)
     return env, spread
 
 
-def check_hist(hist, ref, it, it_ref, env=None, spread=0, tol=HIST_TOL, safety=50.0):
+def check_hist(hist, ref, it, it_ref, env=None, spread=0, tol=HIST_TOL, safety=10.0):
     """residual history within `tol` relative of the reference's, iteration count within +-1 -- relaxed only where, and
-    only as far as, the reference's own 1e-16-perturbed history leaves that band (see reference_envelope)."""
+    only as far as (a finite multiple of), the reference's own history moves under another summation order / a one-ulp
+    change of its input (see reference_envelope)."""
     m = min(len(hist), len(ref))
     rel = np.maximum.accumulate(np.abs(hist[:m] - ref[:m]) / ref[:m])
     bound = np.full(m, tol) if env is None else np.maximum(tol, safety * env[:m])
     bad = np.nonzero(rel > bound)[0]
     assert bad.size == 0, "residual history deviates at step %d: rel %.3e > bound %.3e" % (int(bad[0]), rel[bad[0]], bound[bad[0]])
-    assert abs(it - it_ref) <= max(1, 2 * spread), (it, it_ref, spread)
+    assert bound.size == 0 or np.all(np.isfinite(bound))
+    assert abs(it - it_ref) <= max(1, spread), (it, it_ref, spread)
 
 
-def perturbed(orc, Ao, prm, rhs, x0=None, precond=None):
+def perturbed(orc, Ao, prm, rhs, x0=None, precond=None, left=None):
     def run(rng, eps):
-        _, h, it = orc.gcr_solve(Ao, prm, rhs * (1 + eps * rng.standard_normal(len(rhs))), x0=x0, precond=precond)
+        _, h, it = orc.gcr_solve(Ao, prm, rhs * (1 + eps * rng.choice([-1.0, 1.0], size=len(rhs))), x0=x0, precond=precond, left=left)
         return h, it
     return run
 

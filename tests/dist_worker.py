@@ -150,6 +150,19 @@ def main(rank, world, port, gather_dofs, mode="unit"):
     out["mg_iters"] = [itm1, itmd, it1]
     out["mg_true_res"] = r.norm() / rhsl.norm()
     out["mg_x_rel"] = float(np.linalg.norm(yl.numpy() - y1.numpy()[sl]) / np.linalg.norm(y1.numpy()[sl]))
+    out["mg_hist_rel"] = float(np.max(np.abs(hmd[:min(len(hmd), len(hm1), 12)] - hm1[:min(len(hmd), len(hm1), 12)]) / hm1[:min(len(hmd), len(hm1), 12)]))
+    # LOOSE inner tolerances: the smoother / coarse solves stop on their device-side test after different numbers of iterations;
+    # every rank must take the same decision from the all-reduced norms (a partial ||r||^2 in the test once made ranks disagree)
+    loose_c, loose_s = host.GCR_Param(0, 10, 4, 3e-1), host.GCR_Param(0, 4, 4, 3e-1)
+    mgl = host.MG(ctx, A, lv, eig, loose_c, loose_s)
+    mgl1 = host.MG(single, A1, lv, eig, loose_c, loose_s)
+    y1.set_zero(); yl.set_zero()
+    itl1, hl1 = host.GCR(single, A1, host.GCR_Param(0, 10, 200, 1e-10, False, None, mgl1)).solve(rhs, y1)
+    itld, hld = host.GCR(ctx, A, host.GCR_Param(0, 10, 200, 1e-10, False, None, mgl)).solve(rhsl, yl)
+    out["mg_loose_iters"] = [itl1, itld]
+    out["mg_loose_x_rel"] = float(np.linalg.norm(yl.numpy() - y1.numpy()[sl]) / np.linalg.norm(y1.numpy()[sl]))
+    rl = rhsl - A(yl)
+    out["mg_loose_true_res"] = rl.norm() / rhsl.norm()
     res = [None] * world
     dist.all_gather_object(res, out)
     if rank == 0:

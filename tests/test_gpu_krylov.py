@@ -308,6 +308,32 @@ def test_gcr_history_against_reference_golden(ctx, host, orc, golden, c1, mode, 
     assert relerr(x.numpy(), g[mode + "_x"]) < X_TOL
 
 
+@pytest.mark.parametrize("mode,restart", [("r5", 5), ("r10", 10)])
+def test_left_preconditioned_gcr_against_reference_golden(ctx, host, orc, golden, c1, mode, restart):
+    """the reference's left preconditioning (src/GCR.h:201-204, 245-247: r <- L(r) once, Ar <- L(A r) per iteration) with a
+    Jacobi-like real diagonal L, against the UNMODIFIED reference's history and solution (tests/golden/gcr_left.npz)"""
+    from oracle.make_golden_left import left_diagonal
+    g = golden.gcr_left
+    n = c1["n"]
+    D = host.Sparse(ctx, n, n, c1["row"], c1["col"], c1["val"])
+    A = host.DiracOp(ctx, D, c1["k"])
+    L = host.DiracOp(ctx, D, 0.0, diag=left_diagonal(n))          # diag.x - 0 (D x) = the diagonal operator
+    Do = orc.csr(n, n, c1["row"], c1["col"], c1["val"])
+    Ao, Lo = orc.dirac(Do, c1["k"]), orc.dirac(Do, 0.0, left_diagonal(n))
+    rhs = orc.init_rand(0, n)
+    x = ctx.field(n).set_zero()
+    it, hist = host.GCR(ctx, A, host.GCR_Param(0, restart, 4000, 1e-12, False, L, None)).solve(ctx.from_numpy(rhs), x)
+    ref = g[mode + "_hist"]
+    env, spread = reference_envelope(perturbed(orc, Ao, orc.gcr_param(0, restart, 4000, 1e-12), rhs, left=Lo), ref, len(ref) - 1)
+    check_hist(hist, ref, it, len(ref) - 1, env, spread)
+    m = min(20, len(hist), len(ref))
+    assert np.max(np.abs(hist[:m] - ref[:m]) / ref[:m]) < HIST_TOL           # step 0 is ||L(rhs)|| / ||rhs|| (GCR.h:214)
+    assert relerr(x.numpy(), g[mode + "_x"]) < X_TOL
+    # solver-as-operator and the host-buffer entry point take the same path
+    xh, ith, _ = host.GCR(ctx, A, host.GCR_Param(0, restart, 4000, 1e-12, False, L, None)).solve_host(rhs, np.zeros(n, dtype=np.complex128))
+    assert ith == it and relerr(xh, g[mode + "_x"]) < X_TOL
+
+
 def test_gcr_operator_call_starts_from_rand2(ctx, host, golden, c1):
     g = golden.gcr
     A = host.DiracOp(ctx, host.Sparse(ctx, c1["n"], c1["n"], c1["row"], c1["col"], c1["val"]), c1["k"])
