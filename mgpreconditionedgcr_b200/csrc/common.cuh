@@ -111,7 +111,8 @@ struct mgcr_ctx {
     void* nccl_comm = nullptr;
     void* p2p = nullptr;                    // peer-memory state (p2p.cu): mapped heaps of all ranks, NULL = NCCL for everything
     void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
-    int pdl = 1;                            // option "pdl" / MGCR_PDL: programmatic dependent launch of the solve's kernels (launch_pdl)
+    int pdl = 0;                            // option "pdl" / MGCR_PDL: programmatic dependent launch of the solve's kernels (launch_pdl);
+                                            // measured on B200: +4.7 us per launch (512^3 solve 1.234 -> 1.274 s, profiles/r02_knobs_pdl_blind.txt), so off
     int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,
                                             // the exchanges are latency- and skew-bound; profiles/r01_halo_overlap_n8.txt)
     std::vector<cudaEvent_t> depth_events;  // read-back event of each solver nesting depth (gcr.cu)

@@ -34,6 +34,17 @@ hopab)
         done
     done
     cat $O/${TAG}_hopab.txt ;;
+dist)
+    # multi-GPU parity + bench at N = $NGPU (gpurun --gpus N): tests for this world size, then the bench with the deferred halo wait on / off
+    N=${NGPU:-2}
+    timeout 1500 python -m pytest tests/test_gpu_dist.py -m gpu -q -k "test_distributed_against_single_gpu and ${N}-" > $O/${TAG}_pytest_dist${N}.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_dist${N}.log
+    grep -E "passed|failed|skipped|rc=" $O/${TAG}_pytest_dist${N}.log | tail -4
+    grep -E "^E  " $O/${TAG}_pytest_dist${N}.log | cut -c1-400 | head -20
+    for cfg in "MGCR_HALO_DEFER=1" "MGCR_HALO_DEFER=0" ${EXTRA_CFGS}; do
+        env $cfg timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29631 bench.py --gpus $N --steps 3 --warmup 2 --no-cpu-baseline \
+            > $O/${TAG}_bench_n${N}_${cfg//=/}.json 2> $O/${TAG}_bench_n${N}_${cfg//=/}.err; echo "== $cfg rc=$?"
+        python scripts/bench_brief.py $O/${TAG}_bench_n${N}_${cfg//=/}.json 2>&1 | head -24
+    done ;;
 knobs)
     # same box: programmatic dependent launch and blind preconditioned solves on / off
     : > $O/${TAG}_knobs.txt
