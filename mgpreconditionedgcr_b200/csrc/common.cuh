@@ -208,7 +208,7 @@ __device__ __forceinline__ void p2p_flag_wait(const uint32_t* flag, uint32_t seq
 int p2p_init(mgcr_ctx* ctx);
 void p2p_destroy(mgcr_ctx* ctx);
 bool p2p_enabled(mgcr_ctx* ctx);
-int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
+int p2p_allreduce_sum(mgcr_ctx* ctx, const double* d_in, double* d_out, int n);
 int p2p_halo_create(mgcr_ctx* ctx, int64_t n, PeerHalo* h);
 void p2p_halo_destroy(mgcr_ctx* ctx, PeerHalo* h);
 int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c128* send_hi, const c128** recv_lo, const c128** recv_hi, bool defer = false);
@@ -216,6 +216,8 @@ int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c12
 // distributed helpers (dist.cu)
 void dist_destroy(mgcr_ctx* ctx);
 int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n);
+// out[i] = sum over ranks of in[i]; `in` is left untouched (out may alias it), so repeating the call gives the same result
+int dist_allreduce_sum2(mgcr_ctx* ctx, const double* d_in, double* d_out, int n);
 int dist_sendrecv(mgcr_ctx* ctx, const void* d_send, size_t send_bytes, int send_peer, void* d_recv, size_t recv_bytes,
                   int recv_peer, cudaStream_t stream);
 bool dist_halo_overlap(mgcr_ctx* ctx);

@@ -118,16 +118,20 @@ extern "C" int mgcr_ctx_rank(mgcr_ctx* ctx, int* rank, int* nranks) {
     return MGCR_OK;
 }
 
-int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
-    if (ctx->nranks == 1) return MGCR_OK;
+int dist_allreduce_sum2(mgcr_ctx* ctx, const double* d_in, double* d_out, int n) {
+    if (ctx->nranks == 1) {
+        if (d_in != d_out) CUDA_TRY(cudaMemcpyAsync(d_out, d_in, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        return MGCR_OK;
+    }
     {
-        const int st = p2p_allreduce_sum(ctx, d_buf, n);
+        const int st = p2p_allreduce_sum(ctx, d_in, d_out, n);
         if (st != MGCR_ERR_UNSUPPORTED) return st;
     }
     ProfScope ps_(ctx, "nccl_allreduce", 8. * n);
-    NCCL_TRY(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat64_, ncclSum_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    NCCL_TRY(g_nccl.AllReduce(d_in, d_out, (size_t)n, ncclFloat64_, ncclSum_, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return MGCR_OK;
 }
+int dist_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) { return dist_allreduce_sum2(ctx, d_buf, d_buf, n); }
 
 extern "C" int mgcr_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
     ARG_CHECK(ctx && d_buf && n >= 0, "mgcr_allreduce_sum: bad argument");

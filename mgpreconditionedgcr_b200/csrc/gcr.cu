@@ -72,16 +72,16 @@ static int dot_hist(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* Ar, 
 template <int NH, int MINB>
 static void launch_update_p(mgcr_ctx* ctx, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                             int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
-                            int bden_off, double* scal, const double* guard, double tol2) {
+                            int bden_off, double* scal, double* red_anum, const double* guard, double tol2) {
     launch_pdl(ctx, k_gcr_update_p<NH, MINB>, grid, RED_THREADS, 0, n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
-               bden_off, scal, ctx->d_partials, ctx->d_ticket, guard, tol2);
+               bden_off, (const double*)scal, red_anum, ctx->d_partials, ctx->d_ticket, guard, tol2);
 }
 static void update_p(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                      int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj, int bden_off,
-                     double* scal, const double* guard, double tol2) {
+                     double* scal, double* red_anum, const double* guard, double tol2) {
     static const int minb_env = env_int("MGCR_UPD_MINB", 0);   // experiment knob
     const int minb = minb_env ? minb_env : 4;
-#define ARGS ctx, grid, n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, guard, tol2
+#define ARGS ctx, grid, n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red_anum, guard, tol2
 #define C(NH) case NH: if (minb >= 4) launch_update_p<NH, 4>(ARGS); else if (minb == 3) launch_update_p<NH, 3>(ARGS); else launch_update_p<NH, 2>(ARGS); break;
     switch (nh) {
         C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
@@ -145,6 +145,11 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     const int64_t stride = n + ring_pad;
     const int bden_off = S_BNUM + 2 * storage;
     const int nscal = bden_off + storage;
+    // Distributed solves keep this rank's PARTIAL sums in a second block of the same layout (`red`): the kernels reduce into it,
+    // the all-reduce reads it and writes the global sums into `scal`.  `scal` therefore only ever holds global values -- the
+    // device-side stopping tests of a blind solve decide the same thing on every rank -- and an all-reduce that is repeated after
+    // its producer kernel has been skipped (solve converged) reproduces the same sums instead of adding global values up again
+    // (round 1 reduced in place: with a loose smoother tolerance ||r||^2 doubled per skipped iteration and the solve resumed).
     int st = MGCR_OK;
     auto cleanup = [&]() {
         dev_free(ctx, r); dev_free(ctx, Ar); dev_free(ctx, z); dev_free(ctx, ps); dev_free(ctx, Aps);
@@ -183,8 +188,9 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
         return MGCR_OK;
     };
     if (storage > GCR_CHUNK) { GTRY(dev_alloc_t(ctx, (size_t)n, &acc_p)); GTRY(dev_alloc_t(ctx, (size_t)n, &acc_Ap)); }
-    GTRY(dev_alloc_t(ctx, (size_t)nscal, &scal));
-    GCUDA(cudaMemsetAsync(scal, 0, sizeof(double) * nscal, ctx->stream));
+    GTRY(dev_alloc_t(ctx, (size_t)nscal * (dist ? 2 : 1), &scal));
+    GCUDA(cudaMemsetAsync(scal, 0, sizeof(double) * nscal * (dist ? 2 : 1), ctx->stream));
+    double* const red = dist ? scal + nscal : scal;
 
     static const int grid_per_sm = getenv("MGCR_GRID_PER_SM") ? atoi(getenv("MGCR_GRID_PER_SM")) : 4;   // experiment knob
     const int grid = stream_grid(ctx, n, grid_per_sm, 2);
@@ -193,15 +199,15 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     // kernel in the pass that forms the first inner products
     if (right) GTRY(right->apply(rhs, ps));
     GTRY(A->apply(right ? ps : rhs, Aps));
-    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, n, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, scal)));
+    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, n, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red)));
     GCUDA(cudaGetLastError());
     if (left) {
         // r <- L(r) (GCR.h:201-204): the first alpha and the step-0 print use the preconditioned r with the UNpreconditioned Ap
         GTRY(left->apply(rhs, r));
-        GTRY(vec_dot_dev(ctx, n, std_conj ? Aps : r, std_conj ? r : Aps, scal + S_ANUM, false));   // <r,Ap> (or <Ap,r>), local part
-        GTRY(vec_norm2_dev(ctx, n, r, scal + S_RR, false));
+        GTRY(vec_dot_dev(ctx, n, std_conj ? Aps : r, std_conj ? r : Aps, red + S_ANUM, false));   // <r,Ap> (or <Ap,r>), local part
+        GTRY(vec_norm2_dev(ctx, n, r, red + S_RR, false));
     }
-    if (dist) GTRY(dist_allreduce_sum(ctx, scal, 5));
+    if (dist) GTRY(dist_allreduce_sum2(ctx, red, scal, 5));
     // Short solves nobody watches (the smoothers of the multigrid cycle): no read-back at all, the kernels carry the
     // stopping test themselves (gcr_converged) and the host enqueues max_iter iterations back to back.
     // A right preconditioner does not change that: its applies run whether or not the solve has converged (wasted work in the
@@ -234,12 +240,12 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
         KLAUNCH(ctx, "gcr_update_xr", 96. * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, n, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
-                                                                 scal, bden_off + cur, ctx->d_partials, ctx->d_ticket, guard, tol2)));
+                                                                 scal, red + S_RR, bden_off + cur, ctx->d_partials, ctx->d_ticket, guard, tol2)));
         GCUDA(cudaGetLastError());
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
-            KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, n, (const c128*)x, ctx->d_partials, ctx->d_ticket, scal + S_BB)));
+            KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, n, (const c128*)x, ctx->d_partials, ctx->d_ticket, red + S_BB)));
             GCUDA(cudaGetLastError());
-            if (dist) GTRY(dist_allreduce_sum(ctx, scal + S_BB, 1));
+            if (dist) GTRY(dist_allreduce_sum2(ctx, red + S_BB, scal + S_BB, 1));
         }
         const bool final_iter = (g >= prm->max_iter);   // nothing after the x update is observable on the last pass
         const c128* zz = r;
@@ -254,15 +260,14 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
                 const int cnt = std::min((int)GCR_CHUNK, lim - c0);
                 for (int k = 0; k < GCR_CHUNK; k++) hl.slot[k] = k < cnt ? c0 + k : 0;
                 ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + cnt));
-                // distributed: scal[S_RR] still holds this rank's PARTIAL ||r||^2 here (it is all-reduced together with the inner
-                // products below), so a device-side stopping test would compare a partial norm with the global ||rhs||^2 and
-                // ranks could disagree on whether this kernel runs; its output is unused once converged, so it runs unguarded
-                GTRY(dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, scal + S_BNUM + 2 * c0, dist ? nullptr : guard, tol2));
+                // (distributed: the stopping test sees the GLOBAL ||r||^2 of the previous iteration here -- this iteration's is all-reduced
+                // together with the inner products below --, identical on every rank; the output is unused once the solve has converged)
+                GTRY(dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, red + S_BNUM + 2 * c0, guard, tol2));
             }
             GCUDA(cudaGetLastError());
         }
         // (the last pass of a solve nobody watches leaves nothing to reduce: x is final, ||r||^2 is not read)
-        if (dist && !(blind && final_iter)) GTRY(dist_allreduce_sum(ctx, scal + S_RR, 1 + 2 * lim));
+        if (dist && !(blind && final_iter)) GTRY(dist_allreduce_sum2(ctx, red + S_RR, scal + S_RR, 1 + 2 * lim));
         if (!blind) {
             GCUDA(cudaMemcpyAsync(slot.h, scal + S_BB, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             GCUDA(cudaEventRecord(slot.ev, ctx->stream));
@@ -279,10 +284,10 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
                 for (int k = 0; k < GCR_CHUNK; k++) { bl.slot[k] = k < cnt ? c * GCR_CHUNK + k : 0; bl.num_index[k] = bl.slot[k]; }
                 int first = (c == 0), last = (c == nchunks - 1);
                 ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * cnt + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0)));
-                update_p(ctx, cnt, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, guard, tol2);
+                update_p(ctx, cnt, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red + S_ANUM, guard, tol2);
             }
             GCUDA(cudaGetLastError());
-            if (dist) GTRY(dist_allreduce_sum(ctx, scal + S_ANUM, 3));
+            if (dist) GTRY(dist_allreduce_sum2(ctx, red + S_ANUM, scal + S_ANUM, 3));
             iter = next_iter;
             cur = new_slot;
         }

@@ -114,7 +114,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, cons
 
 // x += alpha p ; r -= alpha Ap ; ||r||^2 -> scal[S_RR]      (GCR.h:230-233)
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n, const c128* __restrict__ p, const c128* __restrict__ Ap,
-                                                               c128* x, c128* r, double* scal, int bden_slot, double* partials,
+                                                               c128* x, c128* r, double* scal, double* rr_out, int bden_slot, double* partials,
                                                                unsigned int* ticket, const double* guard, double tol2) {
     PDL_ENTRY();
     if (gcr_converged(guard, tol2)) return;
@@ -144,7 +144,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n,
         st_stream(r + i, rv);
         v[0] += rv.x * rv.x + rv.y * rv.y;
     }
-    grid_reduce<1>(v, partials, ticket, scal + S_RR);
+    grid_reduce<1>(v, partials, ticket, rr_out);   // scal + S_RR, or this rank's partial block when the solve is distributed
 }
 
 // batched <Ar, Aps[slot]> for nh (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
@@ -358,8 +358,9 @@ struct BetaList { int slot[GCR_CHUNK]; int num_index[GCR_CHUNK]; };
 template <int NH, int MINB>
 static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps,
                                                                     c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
-                                                                    c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, double* scal,
-                                                                    double* partials, unsigned int* ticket, const double* guard, double tol2) {
+                                                                    c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, const double* scal,
+                                                                    double* anum_out, double* partials, unsigned int* ticket, const double* guard,
+                                                                    double tol2) {
     PDL_ENTRY();
     if (gcr_converged(guard, tol2)) return;
     constexpr int NHS = NH > 0 ? NH : 1;
@@ -418,7 +419,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64
         st_stream(Apout + i, Apc);
     }
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
-    if (last) grid_reduce<3>(v, partials, ticket, scal + S_ANUM);   // -> S_ANUM(2), S_ADEN
+    if (last) grid_reduce<3>(v, partials, ticket, anum_out);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
 }
 
 // out = a + sign * s * b with the complex scalar s in device memory (Gram-Schmidt updates: src/MG.h:116-118, 192-194)

@@ -713,16 +713,28 @@ static int level_setup(mgcr_mg* mg, int l, const c128* d_nearnull) {
         const int pgrid = stream_grid(ctx, (int64_t)plane_elems, 4);
         if (g.has_lo) { KLAUNCH(ctx, "mg_pack_P", 32. * plane_elems, (k_pack_P_plane<<<pgrid, RED_THREADS, 0, ctx->stream>>>(g, 0, L.d_site_block, L.d_site_off, L.d_P, send_lo))); CHECK_LAUNCH(); }
         if (g.has_hi) { KLAUNCH(ctx, "mg_pack_P", 32. * plane_elems, (k_pack_P_plane<<<pgrid, RED_THREADS, 0, ctx->stream>>>(g, L.nsite - g.plane_sites, L.d_site_block, L.d_site_off, L.d_P, send_hi))); CHECK_LAUNCH(); }
-        MGCR_TRY(dist_group_begin(ctx));
-        if (g.has_lo) {
-            MGCR_TRY(dist_send(ctx, send_lo, sizeof(c128) * plane_elems, ctx->rank - 1, ctx->stream));
-            MGCR_TRY(dist_recv(ctx, L.d_Pg, sizeof(c128) * plane_elems, ctx->rank - 1, ctx->stream));
+        // over peer memory when the planes fit the heap (a temporary receive area, handed back right away): the first NCCL
+        // send/recv of a process sets up its point-to-point channels, 0.6-1.5 s of the 2-GPU set-up in round 2's first measurement
+        PeerHalo tmp;
+        MGCR_TRY(p2p_halo_create(ctx, (int64_t)plane_elems, &tmp));
+        if (tmp.on) {
+            const c128 *recv_lo = nullptr, *recv_hi = nullptr;
+            MGCR_TRY(p2p_halo_exchange(ctx, &tmp, send_lo, send_hi, &recv_lo, &recv_hi));
+            if (g.has_lo) CUDA_TRY(cudaMemcpyAsync(L.d_Pg, recv_lo, sizeof(c128) * plane_elems, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (g.has_hi) CUDA_TRY(cudaMemcpyAsync(L.d_Pg + (g.has_lo ? plane_elems : 0), recv_hi, sizeof(c128) * plane_elems, cudaMemcpyDeviceToDevice, ctx->stream));
+            p2p_halo_destroy(ctx, &tmp);
+        } else {
+            MGCR_TRY(dist_group_begin(ctx));
+            if (g.has_lo) {
+                MGCR_TRY(dist_send(ctx, send_lo, sizeof(c128) * plane_elems, ctx->rank - 1, ctx->stream));
+                MGCR_TRY(dist_recv(ctx, L.d_Pg, sizeof(c128) * plane_elems, ctx->rank - 1, ctx->stream));
+            }
+            if (g.has_hi) {
+                MGCR_TRY(dist_send(ctx, send_hi, sizeof(c128) * plane_elems, ctx->rank + 1, ctx->stream));
+                MGCR_TRY(dist_recv(ctx, L.d_Pg + (g.has_lo ? plane_elems : 0), sizeof(c128) * plane_elems, ctx->rank + 1, ctx->stream));
+            }
+            MGCR_TRY(dist_group_end(ctx));
         }
-        if (g.has_hi) {
-            MGCR_TRY(dist_send(ctx, send_hi, sizeof(c128) * plane_elems, ctx->rank + 1, ctx->stream));
-            MGCR_TRY(dist_recv(ctx, L.d_Pg + (g.has_lo ? plane_elems : 0), sizeof(c128) * plane_elems, ctx->rank + 1, ctx->stream));
-        }
-        MGCR_TRY(dist_group_end(ctx));
         MGCR_TRY(dev_free(ctx, send_lo));
         MGCR_TRY(dev_free(ctx, send_hi));
     }

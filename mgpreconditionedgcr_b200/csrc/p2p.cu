@@ -168,16 +168,17 @@ struct SpinGuard {
 struct PeerPtrs { uint64_t* p[16]; };
 
 // slot layout of one parity: [source rank][2 * P2P_AR_MAX] words, word 2i / 2i+1 = {low / high half of element i, seq}
-static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, uint64_t* mine, int rank, int nranks, int n, uint32_t seq, double* buf) {
+static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, uint64_t* mine, int rank, int nranks, int n, uint32_t seq, const double* in,
+                                                              double* out) {
     PDL_ENTRY();
     const int words = 2 * n;
     for (int t = threadIdx.x; t < words * nranks; t += blockDim.x) {
         const int p = t / words, j = t - p * words;
-        const uint64_t bits = (uint64_t)__double_as_longlong(buf[j >> 1]);
+        const uint64_t bits = (uint64_t)__double_as_longlong(in[j >> 1]);
         const uint32_t half = (j & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
         st_volatile_u64(peers.p[p] + (size_t)rank * (2 * P2P_AR_MAX) + j, ((uint64_t)seq << 32) | half);
     }
-    __syncthreads();   // buf has been read by every thread before anybody overwrites it
+    __syncthreads();   // `in` has been read by every thread before anybody overwrites it (out may alias in)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double sum = 0.;
         for (int r = 0; r < nranks; r++) {
@@ -188,12 +189,12 @@ static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, ui
             while ((uint32_t)((hi = ld_volatile_u64(w + 1)) >> 32) != seq) guard.tick();
             sum += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
         }
-        buf[i] = sum;
+        out[i] = sum;
     }
 }
 
 // returns MGCR_ERR_UNSUPPORTED when the caller has to use NCCL (path off, too many values)
-int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
+int p2p_allreduce_sum(mgcr_ctx* ctx, const double* d_in, double* d_out, int n) {
     PeerState* s = state(ctx);
     if (!s || n > P2P_AR_MAX || ctx->nranks > 16) return MGCR_ERR_UNSUPPORTED;
     if (n <= 0) return MGCR_OK;
@@ -202,7 +203,7 @@ int p2p_allreduce_sum(mgcr_ctx* ctx, double* d_buf, int n) {
     const size_t par = (size_t)(s->ar_seq & 1) * (size_t)ctx->nranks * 2 * P2P_AR_MAX * sizeof(uint64_t);
     PeerPtrs pp;
     for (int r = 0; r < ctx->nranks; r++) pp.p[r] = (uint64_t*)(s->peer[(size_t)r] + s->ar_off + par);
-    KLAUNCH(ctx, "p2p_allreduce", 8. * n, (launch_pdl(ctx, k_p2p_allreduce, 1, 256, 0, pp, (uint64_t*)(s->heap + s->ar_off + par), ctx->rank, ctx->nranks, n, s->ar_seq, d_buf)));
+    KLAUNCH(ctx, "p2p_allreduce", 8. * n, (launch_pdl(ctx, k_p2p_allreduce, 1, 256, 0, pp, (uint64_t*)(s->heap + s->ar_off + par), ctx->rank, ctx->nranks, n, s->ar_seq, d_in, d_out)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }

@@ -101,7 +101,7 @@ bool glibc_rand_matches(int seed) {
 
 // elements [skip, skip+n) of Field::init_rand(seed) into a host buffer: element = complex((rand()%2000)/1000.-1, ...), the
 // IMAGINARY argument evaluated first (g++), SURVEY.md 8a row a9
-void fill_host(int seed, int64_t skip, int64_t n, c128* h, bool restated) {
+void fill_host(int seed, int64_t skip, int64_t n, c128* h, bool restated, int nthreads) {
     if (!restated) {
         srand(seed);
         for (int64_t i = 0; i < 2 * skip; i++) (void)rand();
@@ -117,7 +117,7 @@ void fill_host(int seed, int64_t skip, int64_t n, c128* h, bool restated) {
     const int64_t chunk = 1 << 16;
     const int64_t nchunks = (n + chunk - 1) / chunk;
     (void)jump_powers();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(std::max(1, std::min(omp_get_max_threads(), 16)))
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
     for (int64_t c = 0; c < nchunks; c++) {
         GlibcRand g = g0;
         const int64_t e0 = c * chunk, e1 = std::min(n, e0 + chunk);
@@ -135,7 +135,7 @@ void fill_host(int seed, int64_t skip, int64_t n, c128* h, bool restated) {
 // host-only entry point (no device needed): the stream itself, for callers that stage their own uploads and for the CPU tests
 extern "C" int mgcr_rand_stream(int seed, int64_t skip, int64_t n, mgcr_c128* h_out) {
     ARG_CHECK(skip >= 0 && n >= 0 && (n == 0 || h_out), "mgcr_rand_stream: bad argument");
-    fill_host(seed, skip, n, (c128*)h_out, glibc_rand_matches(seed));
+    fill_host(seed, skip, n, (c128*)h_out, glibc_rand_matches(seed), std::max(1, std::min(omp_get_num_procs(), 16)));
     return MGCR_OK;
 }
 
@@ -150,6 +150,8 @@ int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming));
     }
     const bool restated = glibc_rand_matches(seed);
+    // one process per GPU on one host: the ranks draw their slabs at the same time and share the cores
+    const int nthreads = std::max(1, std::min(omp_get_num_procs() / std::max(1, ctx->nranks), 16));
     c128* stage = (c128*)ctx->h_stage;
     int which = 0;
     for (int64_t e0 = 0; e0 < n; e0 += half, which ^= 1) {
@@ -163,7 +165,7 @@ int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d
                 h[i] = cmake(re, im);
             }
         } else {
-            fill_host(seed, skip + e0, cnt, stage + (size_t)which * half, restated);
+            fill_host(seed, skip + e0, cnt, stage + (size_t)which * half, restated, nthreads);
         }
         CUDA_TRY(cudaMemcpyAsync(d_out + e0, stage + (size_t)which * half, sizeof(c128) * (size_t)cnt, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaEventRecord(ctx->ev_stage[which], ctx->stream));
