@@ -15,8 +15,8 @@
 //          when the spinor extent is 4; MG_Param::n_level > 1 builds deeper levels (K-cycle) -- the reference stores
 //          n_level but never reads it.
 // The coarse and smoother solvers must be GCR objects (they are in every reference call site); their parameters are read
-// at initialise().  test_MG / test_by_value / recursive_solve (diagnostics; declared but unused or undefined in the
-// reference) are not provided.
+// at initialise().  test_MG (src/MG.h:432-512) prints the reference's diagnostics from device-resident operations; test_by_value
+// and recursive_solve (declared but unused / undefined in the reference) are not provided.
 #ifndef MGCR_DROPIN_MG_H
 #define MGCR_DROPIN_MG_H
 
@@ -203,6 +203,51 @@ public:
         if (!this->handle) MGCR_CALL(mgcr_mg_op_create(mgcr::context(), hierarchy, &this->handle));
         return this->handle;
     }
+
+    // The reference's diagnostic (src/MG.h:432-512), same prints in the same order.  The reference sums full-lattice copies of
+    // the prolongator columns (`large += prolongator[i][n]`); here sum_b prolongator[b][n] = expand(coarse vector that is 1 at
+    // b*ne + n for every aggregate b), everything else is the same chain of restrict / expand / operator applies on the device.
+    // The numbers are also kept (last_test_*) so that a caller can assert on them.
+    void test_MG(Operator<num_type>* M) {
+        const int n = 0;   /* test eigenvector 0 */
+        int64_t nb = 0, bl = 0; int ne = 0;
+        MGCR_CALL(mgcr_mg_level_info(hierarchy, 0, nullptr, &nb, &ne, &bl));
+        num_type cdim[1] = {m_coarse->get_dim()};
+        auto column_sum = [&](int col, bool all_blocks) {   // sum over aggregates (or aggregate 0 only) of prolongator[b][col]
+            std::vector<std::complex<double>> h((size_t)(nb * ne), std::complex<double>(0., 0.));
+            for (int64_t b = 0; b < (all_blocks ? nb : 1); b++) h[(size_t)(b * ne + col)] = 1.;
+            Field<num_type> sel(cdim, 1);
+            sel.upload(h.data());
+            return expand(sel);
+        };
+        Field<num_type> large = column_sum(n, true);
+        large.normalise();
+        Field<num_type> p01 = column_sum(1 < ne ? 1 : 0, false);
+        std::printf("eigen0.dot(eigen1) = %.5e\n", large.dot(p01).real());
+        large = (*M)(large);
+        std::printf("M (fine) norm = %f\n", large.norm());
+        Field<num_type> small = restrict(large);
+        Field<num_type> result = expand(small);
+        // m_coarse applied to sum over all eigenvectors and expand
+        Field<num_type> eigenbasis = column_sum(n, true);
+        eigenbasis.normalise();
+        Field<num_type> inter = restrict(eigenbasis);
+        Field<num_type> inter1 = (*m_coarse)(inter);
+        Field<num_type> result1 = expand(inter1);
+        std::printf("m (coarse) norm = %f\n", inter1.norm());
+        last_test_galerkin = (result - result1).norm() / result.norm();
+        std::printf("Relative Difference between TRM and TmR = %.5e\n", last_test_galerkin);
+        std::printf("LHS norm = %.5e\n", result.norm());
+        std::printf("RHS norm = %.5e\n", result1.norm());
+        std::printf("\n\nTest projector:\n");
+        std::printf("norm of eigenvector 0 = %f\n", eigenbasis.norm());
+        Field<num_type> r = restrict(eigenbasis);
+        std::printf("eigenvector 0 restrict:\n");
+        Field<num_type> e = expand(r);
+        last_test_projector = (e - eigenbasis).norm();
+        std::printf("\neigenvector 0 - expand(restrict(eigenvector 0)) = %.5e\n\n", last_test_projector);
+    }
+    double last_test_galerkin = -1., last_test_projector = -1.;   // additions: what test_MG printed
 
     // additions: structure export for parity checks
     mgcr_mg* device_hierarchy() const { return hierarchy; }

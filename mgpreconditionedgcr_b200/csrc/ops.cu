@@ -66,60 +66,8 @@ static int sell_launch(SellOp* op, const c128* x, c128* y, bool dirac, c128 k, c
 int SellOp::apply(const c128* x, c128* y) { return sell_launch(this, x, y, false, cmake(0., 0.), nullptr); }
 int SellOp::apply_dirac(const c128* x, c128* y, c128 k, const double* diag, const c128* bsub) { return sell_launch(this, x, y, true, k, diag, bsub); }
 
-// host CSR (int64) -> device sliced-ELL.  `ncol_local`: columns < ncol_local address x, the rest the ghost buffer.
-int sell_build(mgcr_ctx* ctx, int64_t nrow, int64_t ncol_addressable, const int64_t* row, const int64_t* col, const mgcr_c128* val, SellOp* op) {
-    ARG_CHECK(ncol_addressable < (int64_t)INT32_MAX, "CSR upload: %lld addressable columns exceed the int32 device index (shard the operator)", (long long)ncol_addressable);
-    int64_t nslices = (nrow + 31) / 32;
-    std::vector<int64_t> sp((size_t)nslices + 1, 0);
-    for (int64_t s = 0; s < nslices; s++) {
-        int64_t w = 0;
-        for (int64_t r = s * 32; r < std::min(nrow, s * 32 + 32); r++) {
-            ARG_CHECK(row[r + 1] >= row[r], "CSR upload: row offsets decrease at row %lld", (long long)r);
-            w = std::max(w, row[r + 1] - row[r]);
-        }
-        sp[s + 1] = sp[s] + 32 * w;
-    }
-    int64_t np = sp[nslices];
-    int32_t* hcol = nullptr; c128* hval = nullptr;
-    hcol = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
-    hval = (c128*)malloc(sizeof(c128) * (size_t)std::max<int64_t>(np, 1));
-    if (!hcol || !hval) { free(hcol); free(hval); mgcr_set_error("CSR upload: host staging allocation failed"); return MGCR_ERR_OOM; }
-    int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
-    for (int64_t s = 0; s < nslices; s++) {
-        int64_t w = (sp[s + 1] - sp[s]) / 32;
-        for (int l = 0; l < 32; l++) {
-            int64_t r = s * 32 + l;
-            int64_t b = r < nrow ? row[r] : 0, e = r < nrow ? row[r + 1] : 0;
-            for (int64_t j = 0; j < w; j++) {
-                int64_t dst = sp[s] + j * 32 + l;
-                if (b + j < e) {
-                    int64_t c = col[b + j];
-                    if (c < 0 || c >= ncol_addressable) { bad = 1; c = 0; }
-                    hcol[dst] = (int32_t)c;
-                    hval[dst] = cmake(val[b + j].re, val[b + j].im);
-                } else {
-                    hcol[dst] = 0;
-                    hval[dst] = cmake(0., 0.);
-                }
-            }
-        }
-    }
-    if (bad) { free(hcol); free(hval); mgcr_set_error("CSR upload: column index out of range (src/Operator.h:332 asserts f.field_size() == dim)"); return MGCR_ERR_ARG; }
-    op->nrow = nrow; op->nnz = row[nrow]; op->nnz_padded = np; op->nslices = nslices;
-    int st = dev_alloc_t(ctx, (size_t)nslices + 1, &op->d_slice_ptr);
-    if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)np, &op->d_col);
-    if (st == MGCR_OK) st = dev_alloc_t(ctx, (size_t)np, &op->d_val);
-    if (st == MGCR_OK) {
-        cudaError_t e = cudaMemcpyAsync(op->d_slice_ptr, sp.data(), sizeof(int64_t) * (nslices + 1), cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess && np) e = cudaMemcpyAsync(op->d_col, hcol, sizeof(int32_t) * np, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess && np) e = cudaMemcpyAsync(op->d_val, hval, sizeof(c128) * np, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { mgcr_set_error("CSR upload: %s", cudaGetErrorString(e)); st = MGCR_ERR_CUDA; }
-    }
-    free(hcol); free(hval);
-    return st;
-}
+int sell_build(mgcr_ctx* ctx, int64_t nrow, int64_t ncol_addressable, const int64_t* row, const int64_t* col, const mgcr_c128* val, SellOp* op);   // build.cu
+int device_exclusive_scan_i64(mgcr_ctx* ctx, int64_t* d_data, int64_t n, int64_t* d_total);
 
 extern "C" int mgcr_csr_create(mgcr_ctx* ctx, int64_t nrow, int64_t ncol, const int64_t* row, const int64_t* col, const mgcr_c128* val, mgcr_op** out) {
     ARG_CHECK(ctx && out && row && nrow >= 0 && ncol >= 0, "mgcr_csr_create: bad argument");
@@ -1065,7 +1013,9 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
     if (blockIdx.x == 0 && threadIdx.x == 0) ghost_ready();
 }
 
-static __global__ void __launch_bounds__(256) k_slice_width(int64_t nb, int64_t nslices, int S, const int32_t* __restrict__ brow, int64_t* __restrict__ width) {
+static __global__ void __launch_bounds__(256) k_slice_width(int64_t nb, int64_t nslices, int S, const int32_t* __restrict__ brow, int64_t* __restrict__ width,
+                                                            unsigned long long* __restrict__ wmax) {
+    int wm = 0;
     GRID_STRIDE(s, nslices) {
         int w = 0;
         for (int q = 0; q < S; q++) {
@@ -1073,7 +1023,9 @@ static __global__ void __launch_bounds__(256) k_slice_width(int64_t nb, int64_t 
             if (R < nb) w = max(w, brow[R + 1] - brow[R]);
         }
         width[s] = w;
+        wm = max(wm, w);
     }
+    if (wm) atomicMax(wmax, (unsigned long long)wm);
 }
 // one warp per slice copies its rows from the assembly layout [l][c][r] into the slice's blob; padding = zero blocks
 // whose column is the row's own block (always addressable)
@@ -1104,30 +1056,31 @@ int BlockCsrOp::build_sliced() {
     const int S = 32 / ne;
     const int slot = ne * 512 + S * 4;
     nslices = (nb + S - 1) / S;
-    int64_t* d_w = nullptr;
-    MGCR_TRY(dev_alloc_t(ctx, (size_t)nslices, &d_w));
-    k_slice_width<<<stream_grid(ctx, nslices, 8), RED_THREADS, 0, ctx->stream>>>(nb, nslices, S, d_brow, d_w);
+    // slice widths, their maximum and their exclusive scan stay on the device; 16 bytes come back (total slots, widest slice)
+    int64_t *d_tot = nullptr;
+    MGCR_TRY(dev_alloc_t(ctx, (size_t)nslices + 1, &d_sl_ptr));
+    MGCR_TRY(dev_alloc_t(ctx, 2, &d_tot));
+    CUDA_TRY(cudaMemsetAsync(d_tot, 0, 2 * sizeof(int64_t), ctx->stream));
+    k_slice_width<<<stream_grid(ctx, nslices, 8), RED_THREADS, 0, ctx->stream>>>(nb, nslices, S, d_brow, d_sl_ptr, (unsigned long long*)(d_tot + 1));
     CHECK_LAUNCH();
-    std::vector<int64_t> w((size_t)nslices), ptr((size_t)nslices + 1, 0);
-    CUDA_TRY(cudaMemcpyAsync(w.data(), d_w, sizeof(int64_t) * (size_t)nslices, cudaMemcpyDeviceToHost, ctx->stream));
+    MGCR_TRY(device_exclusive_scan_i64(ctx, d_sl_ptr, nslices, d_tot));
+    CUDA_TRY(cudaMemcpyAsync(d_sl_ptr + nslices, d_tot, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    int64_t tot[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(tot, d_tot, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, d_w);
-    int64_t wmax = 0;
-    for (int64_t s = 0; s < nslices; s++) { ptr[(size_t)s + 1] = ptr[(size_t)s] + w[(size_t)s]; wmax = std::max(wmax, w[(size_t)s]); }
-    sl_slots = ptr[(size_t)nslices];
+    dev_free(ctx, d_tot);
+    sl_slots = tot[0];
+    const int64_t wmax = tot[1];
     // ring: one stage (= the widest slice) per consumer warp, as many as fit 200 KB, at most 14 (26 for ne = 2)
     sl_stage_bytes = (int)(((wmax * slot + 127) / 128) * 128);
     static const int nst_env = getenv("MGCR_BLOCKCSR_STAGES") ? atoi(getenv("MGCR_BLOCKCSR_STAGES")) : 0;   // experiment knob
     const int max_stages = ne == 2 ? RingCfg<2>::MAX_STAGES : RingCfg<4>::MAX_STAGES;
     sl_stages = sl_stage_bytes ? (int)std::min<int64_t>(nst_env > 0 ? std::min(nst_env, max_stages) : max_stages, (200 * 1024) / sl_stage_bytes) : 0;
     // very ragged rows (> 25 % padding) or blobs too large for a useful ring: the assembly layout serves better
-    if ((double)sl_slots * S > 1.25 * (double)nnzb || sl_stages < 4) return MGCR_OK;
-    MGCR_TRY(dev_alloc_t(ctx, (size_t)nslices + 1, &d_sl_ptr));
+    if ((double)sl_slots * S > 1.25 * (double)nnzb || sl_stages < 4) { dev_free(ctx, d_sl_ptr); d_sl_ptr = nullptr; return MGCR_OK; }
     MGCR_TRY(dev_alloc(ctx, (size_t)std::max<int64_t>(sl_slots, 1) * slot, (void**)&d_sl_blob));
-    CUDA_TRY(cudaMemcpyAsync(d_sl_ptr, ptr.data(), sizeof(int64_t) * ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
     k_slice_fill<<<(unsigned)((nslices * 32 + 255) / 256), 256, 0, ctx->stream>>>(nb, nslices, ne, d_brow, d_bcol, d_bval, d_sl_ptr, d_sl_blob);
     CHECK_LAUNCH();
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // ptr (host vector) must outlive the copy
     sliced = 1;
     return MGCR_OK;
 }

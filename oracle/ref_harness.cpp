@@ -475,12 +475,32 @@ static int gcr_left(int argc, char** argv) {
     return 0;
 }
 
+// parse: the reference's own I/O pair on a MatrixMarket file: parse_data(<file>) writes ../../data/sample_matrix/parsed.txt
+// (src/Parse.cpp:39, relative to the working directory), read_data("parsed.txt") reads it back; the arrays are dumped to <outdir>.
+static int parse_mode(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: ref_oracle parse <file.mtx> <outdir>\n"); return 1; }
+    parse_data(argv[2]);
+    Sparse<long> m = read_data("parsed.txt");
+    g_out = argv[3];
+    long nrow = m.get_nrow(), nnz = m.get_nnz();
+    std::vector<long> row(nrow + 1), col(nnz);
+    std::vector<cplx> val(nnz);
+    for (long r = 0; r <= nrow; r++) row[r] = m.get_ROW(r);
+    for (long l = 0; l < nnz; l++) { col[l] = m.get_COL(l); val[l] = m.val_at(l); }
+    dump_i64("row", row);
+    dump_i64("col", col);
+    FILE* f = fopen((std::string(argv[3]) + "/val.bin").c_str(), "wb"); fwrite(val.data(), 16, val.size(), f); fclose(f);
+    printf("PARSED %ld %ld %ld\n", nrow, (long)m.get_dim(), nnz);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: ref_oracle golden <outdir> | bench ... | gcr-file ...\n"); return 1; }
     std::string cmd = argv[1];
     if (cmd == "bench") return bench(argc, argv);
     if (cmd == "gcr-file") return gcr_file(argc, argv);
     if (cmd == "gcr-left") return gcr_left(argc, argv);
+    if (cmd == "parse") return parse_mode(argc, argv);
     if (cmd == "golden") {
         g_out = argv[2];
         golden_rand();

@@ -42,6 +42,7 @@ def test_examples_compile_without_a_gpu():
     """the headers are plain C++17 over the C ABI: they build with g++ alone (this test has no gpu marker)"""
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
     assert os.path.exists(BIN) and os.path.exists(BIN2)
+    assert os.path.exists(os.path.join(ROOT, "examples", "_build", "test_mg_property"))   # src/main.cpp:877-918, 541-570 unchanged
 
 
 @pytest.mark.gpu
@@ -127,3 +128,25 @@ def test_stencil_operator_through_the_cpp_classes(data_dir, tmp_path):
     d, off_x, off_y = (float(v) for v in kv["VAL_AT"])
     assert d > 0.5 and -1.4 < off_x < -0.6 and -0.014 < off_y < -0.006
     assert float(kv["TRUE_RESIDUAL"][0]) < 1.2e-10
+
+
+@pytest.mark.gpu
+def test_reference_diagnostics_compile_and_hold(data_dir, tmp_path):
+    """examples/test_mg_property.cpp = the reference's test_MG_property() (src/main.cpp:877-918, with MG::test_MG of src/MG.h:432-512)
+    and test_hermiticity() (src/main.cpp:541-570) compiled unchanged against the drop-in headers, on the shipped 4^4 data"""
+    out = run(os.path.join(ROOT, "examples", "_build", "test_mg_property"), data_dir, str(tmp_path))
+    kv = {ln.split()[0]: ln.split()[1:] for ln in out.splitlines() if ln.startswith(("KV_", "DONE"))}
+    assert "DONE" in kv
+    # the prints of MG::test_MG, in the reference's order
+    want = ["eigen0.dot(eigen1) =", "M (fine) norm =", "m (coarse) norm =", "Relative Difference between TRM and TmR =", "LHS norm =", "RHS norm =",
+            "Test projector:", "norm of eigenvector 0 =", "eigenvector 0 restrict:", "eigenvector 0 - expand(restrict(eigenvector 0)) =",
+            "RT - Id identity test difference =", "TR TR - TR projector test difference ="]
+    pos = [out.find(w) for w in want]
+    assert all(p >= 0 for p in pos) and pos == sorted(pos)
+    assert float(kv["KV_TEST_MG_GALERKIN"][0]) < 1e-12          # T R M v = T m R v for v in the range of T (src/MG.h:449-475)
+    assert float(kv["KV_TEST_MG_PROJECTOR"][0]) < 1e-12         # v = T R v for v in the range of T
+    assert float(kv["KV_RT_IDENTITY"][0]) < 1e-12 and float(kv["KV_TR_PROJECTOR"][0]) < 1e-12   # src/main.cpp:899-909
+    # the hopping matrix of the sample is not Hermitian (the reference's probe prints so) but gamma5-Hermitian
+    assert "Matrix is NOT Hermitian!" in out
+    assert abs(float(kv["KV_HERMITICITY_DEFECT"][0])) > 1e-6
+    assert float(kv["KV_GAMMA5_HERMITICITY_DEFECT"][0]) < 1e-12
