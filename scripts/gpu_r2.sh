@@ -54,6 +54,9 @@ knobs)
         python scripts/bench_brief.py $O/knob_tmp.json | head -2 >> $O/${TAG}_knobs.txt
     done
     cat $O/${TAG}_knobs.txt ;;
+kbt)
+    # standalone layout comparison for restrict / prolong (scripts/kbench_transfer.cu, built into build/kbt)
+    for n in 256 512; do timeout 120 build/kbt $n; done > $O/${TAG}_kbench_transfer.txt 2>&1; cat $O/${TAG}_kbench_transfer.txt ;;
 bench)
     timeout 900 python bench.py > $O/${TAG}_bench_default_n1.json 2> $O/${TAG}_bench_default_n1.err; echo "bench rc=$?"
     python scripts/bench_brief.py $O/${TAG}_bench_default_n1.json ;;
