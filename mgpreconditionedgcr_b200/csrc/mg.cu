@@ -430,21 +430,29 @@ static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
     if (g.nb == 0) return MGCR_OK;
     const double bytes = 16. * L.n * (1 + g.ne) + 16. * L.nc;
     const AggGeom ag = agg_geom(g);
-    const int64_t resident = (int64_t)ctx->num_sms * 8;       // CTAs of 256 threads the machine holds
+    const int32_t* qo = L.d_q_off;
+    const c128* P = L.d_P;
+    // persistent grids: exactly the CTAs that are resident at once (or fewer when there is less work)
+#define RESTRICT_LAUNCH(KERNEL, lanes_per_agg)                                                                                              \
+    do {                                                                                                                                    \
+        const int64_t need = (g.nb * (lanes_per_agg) + 255) / 256;                                                                          \
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, (const void*)KERNEL, 256), need));         \
+        launch_pdl(ctx, KERNEL, grid, 256, 0, g, ag, qo, P, xf, xc);                                                                        \
+    } while (0)
     if (g.bl <= 256) {
         ProfScope ps_(ctx, "mg_restrict", bytes);
-        const unsigned grid = (unsigned)std::min<int64_t>(resident, (g.nb * 32 + 255) / 256);
-        if (g.bl <= 8) launch_pdl(ctx, k_restrict_sub<8>, (unsigned)std::min<int64_t>(resident, (g.nb * 8 + 255) / 256), 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
-        else if (g.bl <= 16) launch_pdl(ctx, k_restrict_sub<16>, (unsigned)std::min<int64_t>(resident, (g.nb * 16 + 255) / 256), 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
-        else if (g.bl <= 64) launch_pdl(ctx, k_restrict_warp<2>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
-        else if (g.bl <= 128) launch_pdl(ctx, k_restrict_warp<4>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
-        else launch_pdl(ctx, k_restrict_warp<8>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc);
+        if (g.bl <= 8) RESTRICT_LAUNCH(k_restrict_sub<8>, 8);
+        else if (g.bl <= 16) RESTRICT_LAUNCH(k_restrict_sub<16>, 16);
+        else if (g.bl <= 64) RESTRICT_LAUNCH(k_restrict_warp<2>, 32);
+        else if (g.bl <= 128) RESTRICT_LAUNCH(k_restrict_warp<4>, 32);
+        else RESTRICT_LAUNCH(k_restrict_warp<8>, 32);
     } else {
         int threads = 32 * (int)std::min<int64_t>(8, std::max<int64_t>(1, g.ne));
         size_t smem = sizeof(c128) * (size_t)g.bl;
         const unsigned grid = (unsigned)std::min<int64_t>(g.nb, (int64_t)ctx->num_sms * 4);
-        KLAUNCH(ctx, "mg_restrict", bytes, (launch_pdl(ctx, k_restrict, grid, threads, smem, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xf, xc)));
+        KLAUNCH(ctx, "mg_restrict", bytes, (launch_pdl(ctx, k_restrict, grid, threads, smem, g, ag, qo, P, xf, xc)));
     }
+#undef RESTRICT_LAUNCH
     CHECK_LAUNCH();
     return MGCR_OK;
 }
@@ -452,7 +460,7 @@ static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
 static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf, bool add = false) {
     const LevelGeom& g = L.g;
     if (L.n == 0) return MGCR_OK;
-    const unsigned grid = (unsigned)std::min<int64_t>((int64_t)ctx->num_sms * 8, (g.nb * 32 + 255) / 256);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, (const void*)k_prolong, 256), (g.nb * 32 + 255) / 256));
     KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc, (launch_pdl(ctx, k_prolong, grid, 256, 0, g, agg_geom(g), (const int32_t*)L.d_q_off, (const c128*)L.d_P, xc, xf, add ? 1 : 0)));
     CHECK_LAUNCH();
     return MGCR_OK;
