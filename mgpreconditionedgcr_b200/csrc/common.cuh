@@ -111,6 +111,7 @@ struct mgcr_ctx {
     void* nccl_comm = nullptr;
     void* p2p = nullptr;                    // peer-memory state (p2p.cu): mapped heaps of all ranks, NULL = NCCL for everything
     void* nccl_comm_halo = nullptr;         // second communicator: halo exchanges on the auxiliary stream
+    int red_vslabs = 8;                     // option "red_vslabs" / MGCR_RED_VSLABS: 8 = GPU-count-independent reduction shape (red_geom), 1 = plain
     int pdl = 0;                            // option "pdl" / MGCR_PDL: programmatic dependent launch of the solve's kernels (launch_pdl);
                                             // measured on B200: +4.7 us per launch (512^3 solve 1.234 -> 1.274 s, profiles/r02_knobs_pdl_blind.txt), so off
     int halo_overlap = 0;                   // option: overlap halo exchange with interior rows (measured: no gain at 2 and 8 GPUs,
@@ -125,8 +126,19 @@ struct mgcr_ctx {
     std::vector<ProfPending> prof_pending;
 };
 
-enum { MAX_RED_BLOCKS = 2048, MAX_RED_VALUES = 32, RED_THREADS = 256 };
+enum { MAX_RED_BLOCKS = 8192, MAX_RED_VALUES = 32, RED_THREADS = 256 };
 
+// Shape of a reduction over a (possibly slab-partitioned) vector that does NOT depend on the number of GPUs: the GLOBAL vector is
+// cut into RED_VSLABS equal virtual slabs; a rank that holds `nvs` of them launches nvs * G CTAs, CTA (v, c) strides over virtual
+// slab v only, with a stride and a CTA count G that depend on the slab length L alone.  The per-slab sums are combined by a
+// balanced binary tree over the slab index -- inside a rank over its own slabs, across ranks (which own aligned subtrees when
+// their number is a power of two) by the same tree in the all-reduce (p2p.cu).  One GPU therefore forms exactly the partial sums
+// and additions that 2, 4 or 8 GPUs form: residual histories are identical bit for bit at every GPU count.
+// nvs = 1, G = gridDim.x, L = n is the plain grid-stride shape (vectors that do not divide, small levels).
+enum { RED_VSLABS = 8 };
+struct RedGeom { int G; int nvs; int64_t L; };
+
+static inline RedGeom red_geom(const mgcr_ctx* ctx, int64_t n_local, int64_t n_global, int per_sm, int items_per_thread);
 // grid for a grid-stride streaming kernel over n items, `per_sm` resident blocks of RED_THREADS per SM
 static inline int stream_grid(const mgcr_ctx* ctx, int64_t n, int per_sm, int items_per_thread = 1) {
     int64_t need = (n + (int64_t)RED_THREADS * items_per_thread - 1) / ((int64_t)RED_THREADS * items_per_thread);
@@ -134,6 +146,22 @@ static inline int stream_grid(const mgcr_ctx* ctx, int64_t n, int per_sm, int it
     if (cap > MAX_RED_BLOCKS) cap = MAX_RED_BLOCKS;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+// virtual-slab reduction shape for a vector of n_local elements on this rank out of n_global (= n_local when replicated)
+static inline RedGeom red_geom(const mgcr_ctx* ctx, int64_t n_local, int64_t n_global, int per_sm, int items_per_thread) {
+    RedGeom rg;
+    const int nranks = n_global == n_local ? 1 : ctx->nranks;
+    const bool ok = ctx->red_vslabs == RED_VSLABS && nranks >= 1 && RED_VSLABS % nranks == 0 && n_global % RED_VSLABS == 0 &&
+                    n_local * nranks == n_global && n_global / RED_VSLABS >= ((int64_t)1 << 16);
+    if (!ok) { rg.nvs = 1; rg.L = n_local; rg.G = stream_grid(ctx, n_local, per_sm, items_per_thread); return rg; }
+    rg.nvs = RED_VSLABS / nranks;
+    rg.L = n_global / RED_VSLABS;
+    // G depends on the slab length and on per-launch constants only (148 SMs on every B200): the same on every GPU count
+    const int64_t need = (rg.L + (int64_t)RED_THREADS * items_per_thread - 1) / ((int64_t)RED_THREADS * items_per_thread);
+    const int64_t cap = std::min<int64_t>((int64_t)148 * per_sm, MAX_RED_BLOCKS / RED_VSLABS);
+    rg.G = (int)std::max<int64_t>(1, std::min(need, cap));
+    return rg;
 }
 
 // profile-aware launch bookkeeping: KLAUNCH(ctx, "name", bytes, kernel<<<...>>>(...)).  With profiling on, every
@@ -290,10 +318,31 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// blockDim.x must be RED_THREADS.  Returns true in every thread of the last block (after results are final).
+// the last CTA's part: value q summed over the CTA partials of every virtual slab (lanes stride over the slab's G CTAs, shuffle
+// tree), then the slab sums by a balanced binary tree over the slab index.  Called by whole warps; every lane returns the sum.
+__device__ __forceinline__ double combine_partials(const double* __restrict__ partials, int stride_vals, int q, const RedGeom& rg, int lane) {
+    double segs[RED_VSLABS];
+#pragma unroll
+    for (int v = 0; v < RED_VSLABS; v++) {
+        double acc = 0.;
+        if (v < rg.nvs) {
+            for (int b = lane; b < rg.G; b += 32) acc += __ldcg(&partials[(size_t)(v * rg.G + b) * stride_vals + q]);
+            acc = warp_sum(acc);
+        }
+        segs[v] = acc;
+    }
+#pragma unroll
+    for (int w = 1; w < RED_VSLABS; w <<= 1)
+#pragma unroll
+        for (int i = 0; i + w < RED_VSLABS; i += 2 * w)
+            if (i + w < rg.nvs) segs[i] += segs[i + w];
+    return segs[0];
+}
+
+// blockDim.x must be RED_THREADS, gridDim.x = rg.nvs * rg.G.  Returns true in every thread of the last block (after results are final).
 template <int NV>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
-                                            double* __restrict__ result, int nwrite = NV) {
+                                            double* __restrict__ result, const RedGeom& rg, int nwrite = NV) {
     constexpr int NW = RED_THREADS / 32;
     __shared__ double sm[NW][NV];
     __shared__ bool is_last;
@@ -319,26 +368,10 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict_
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    // last block: thread t sums partials of blocks t, t+RED_THREADS, ... (fixed), then the fixed tree above
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; k++) acc[k] = 0.;
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS) {
-#pragma unroll
-        for (int k = 0; k < NV; k++) acc[k] += __ldcg(&partials[(size_t)b * NV + k]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        double s = warp_sum(acc[k]);
-        if (lane == 0) sm[warp][k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double s = 0.;
-#pragma unroll
-        for (int w = 0; w < NW; w++) s += sm[w][threadIdx.x];
-        if ((int)threadIdx.x < nwrite) result[threadIdx.x] = s;
+    // last block: warp w combines values w, w + NW, ... in a fixed order (combine_partials)
+    for (int q = warp; q < NV; q += NW) {
+        const double s = combine_partials(partials, NV, q, rg, lane);
+        if (lane == 0 && q < nwrite) result[q] = s;
     }
     return true;
 }

@@ -108,6 +108,7 @@ extern "C" int mgcr_ctx_create(int device, mgcr_ctx** out) {
     if (getenv("MGCR_HOPPING_TMA_ROWS")) c->hopping_tma_rows = atoll(getenv("MGCR_HOPPING_TMA_ROWS"));
     if (getenv("MGCR_HALO_OVERLAP")) c->halo_overlap = atoi(getenv("MGCR_HALO_OVERLAP"));
     if (getenv("MGCR_PDL")) c->pdl = atoi(getenv("MGCR_PDL"));
+    if (getenv("MGCR_RED_VSLABS")) c->red_vslabs = atoi(getenv("MGCR_RED_VSLABS"));
     *out = c;
     return MGCR_OK;
 }
@@ -122,6 +123,7 @@ extern "C" int mgcr_ctx_set_option(mgcr_ctx* c, const char* key, int64_t value) 
     else if (!strcmp(key, "blockcsr_ring_rows")) c->blockcsr_ring_rows = value;
     else if (!strcmp(key, "halo_overlap")) c->halo_overlap = (int)value;
     else if (!strcmp(key, "pdl")) c->pdl = (int)value;
+    else if (!strcmp(key, "red_vslabs")) c->red_vslabs = (int)value;
     else { mgcr_set_error("mgcr_ctx_set_option: unknown option '%s'", key); return MGCR_ERR_ARG; }
     return MGCR_OK;
 }

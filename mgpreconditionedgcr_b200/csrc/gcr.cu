@@ -8,9 +8,9 @@
 #include "kernels_blas.cuh"
 #include "ops.cuh"
 
-int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist);
-int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist);
-int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist);
+int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist, int64_t n_global = 0);
+int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist, int64_t n_global = 0);
+int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist, int64_t n_global = 0);
 
 int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, const c128* rhs, c128* x, double* hist,
                  int hist_cap, int* iters_out);
@@ -31,37 +31,39 @@ struct GcrOp : mgcr_op {
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 template <int NK, int KS>
-static void launch_dot_hist(mgcr_ctx* ctx, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int nh,
+static void launch_dot_hist(mgcr_ctx* ctx, const RedGeom& rg, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int nh,
                             int std_conj, double* out, const double* guard, double tol2) {
-    launch_pdl(ctx, k_gcr_dot_hist<NK, KS>, grid, RED_THREADS, 0, n, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2);
+    launch_pdl(ctx, k_gcr_dot_hist<NK, KS>, rg.nvs * rg.G, RED_THREADS, 0, rg, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2);
 }
 template <int NH>
-static int launch_dot_hist_tma(mgcr_ctx* ctx, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int std_conj,
+static int launch_dot_hist_tma(mgcr_ctx* ctx, const RedGeom& rg0, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int std_conj,
                                double* out, const double* guard, double tol2) {
     MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_gcr_dot_hist_tma<NH>, 200 * 1024));
     // tile = 256*ept elements of each of the 1+NH vectors; ring of `stages` tiles in ~150 KB (measured: scripts/kbench_dot5.cu)
     const int ept = NH <= 3 ? 4 : NH <= 7 ? 2 : 1;
     const size_t stage_bytes = (size_t)(1 + NH) * RED_THREADS * ept * sizeof(c128);
     const int stages = (int)std::max<size_t>(2, std::min<size_t>(4, (150 * 1024) / stage_bytes));
-    const int64_t tiles = (n + (int64_t)RED_THREADS * ept - 1) / ((int64_t)RED_THREADS * ept);
-    const int grid = (int)std::min<int64_t>(ctx->num_sms, tiles);
-    launch_pdl(ctx, k_gcr_dot_hist_tma<NH>, grid, RED_THREADS, stages * stage_bytes, n, Ar, Aps, stride, hl, std_conj, ept, stages, out,
+    // one CTA per SM and virtual slab (the ring takes the SM's shared memory); the slab's tiles are dealt over its CTAs
+    RedGeom rg = rg0;
+    const int64_t tiles = (rg.L + (int64_t)RED_THREADS * ept - 1) / ((int64_t)RED_THREADS * ept);
+    rg.G = (int)std::min<int64_t>(148, tiles);
+    launch_pdl(ctx, k_gcr_dot_hist_tma<NH>, rg.nvs * rg.G, RED_THREADS, stages * stage_bytes, rg, Ar, Aps, stride, hl, std_conj, ept, stages, out,
                ctx->d_partials, ctx->d_ticket, guard, tol2);
     return MGCR_OK;
 }
 
 // history length -> kernel.  Short histories (and short vectors): register-staged kernel, KS thread groups per CTA with
 // <= NK vectors each; nh >= 3 on long vectors: TMA-staged ring (measured on B200, profiles/r01_kbench_dot.txt).
-static int dot_hist(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
+static int dot_hist(mgcr_ctx* ctx, int nh, const RedGeom& rg, int64_t n_global, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
                     int std_conj, double* out, const double* guard, double tol2) {
-    if (ctx->dot_tma && nh >= 3 && n >= ((int64_t)1 << 20)) {
+    if (ctx->dot_tma && nh >= 3 && n_global >= ((int64_t)1 << 23) && rg.L >= ((int64_t)1 << 17)) {   // (the GLOBAL length decides: the same kernel at every GPU count)
         switch (nh) {
-#define C(NH) case NH: return launch_dot_hist_tma<NH>(ctx, n, Ar, Aps, stride, hl, std_conj, out, guard, tol2);
+#define C(NH) case NH: return launch_dot_hist_tma<NH>(ctx, rg, Ar, Aps, stride, hl, std_conj, out, guard, tol2);
             C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
 #undef C
         }
     }
-#define GO(NK, KS) launch_dot_hist<NK, KS>(ctx, grid, n, Ar, Aps, stride, hl, nh, std_conj, out, guard, tol2)
+#define GO(NK, KS) launch_dot_hist<NK, KS>(ctx, rg, Ar, Aps, stride, hl, nh, std_conj, out, guard, tol2)
     if (nh <= 3) GO(3, 1);
     else if (nh <= 8) GO(4, 2);
     else GO(4, 4);
@@ -70,18 +72,18 @@ static int dot_hist(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* Ar, 
 }
 
 template <int NH, int MINB>
-static void launch_update_p(mgcr_ctx* ctx, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
+static void launch_update_p(mgcr_ctx* ctx, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                             int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
                             int bden_off, double* scal, double* red_anum, const double* guard, double tol2) {
-    launch_pdl(ctx, k_gcr_update_p<NH, MINB>, grid, RED_THREADS, 0, n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
+    launch_pdl(ctx, k_gcr_update_p<NH, MINB>, rg.nvs * rg.G, RED_THREADS, 0, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
                bden_off, (const double*)scal, red_anum, ctx->d_partials, ctx->d_ticket, guard, tol2);
 }
-static void update_p(mgcr_ctx* ctx, int nh, int grid, int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
+static void update_p(mgcr_ctx* ctx, int nh, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                      int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj, int bden_off,
                      double* scal, double* red_anum, const double* guard, double tol2) {
     static const int minb_env = env_int("MGCR_UPD_MINB", 0);   // experiment knob
     const int minb = minb_env ? minb_env : 4;
-#define ARGS ctx, grid, n, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red_anum, guard, tol2
+#define ARGS ctx, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red_anum, guard, tol2
 #define C(NH) case NH: if (minb >= 4) launch_update_p<NH, 4>(ARGS); else if (minb == 3) launch_update_p<NH, 3>(ARGS); else launch_update_p<NH, 2>(ARGS); break;
     switch (nh) {
         C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
@@ -193,19 +195,21 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     double* const red = dist ? scal + nscal : scal;
 
     static const int grid_per_sm = getenv("MGCR_GRID_PER_SM") ? atoi(getenv("MGCR_GRID_PER_SM")) : 4;   // experiment knob
-    const int grid = stream_grid(ctx, n, grid_per_sm, 2);
+    // reduction / streaming shape of every kernel of this solve: independent of the number of GPUs (common.cuh, RedGeom)
+    const RedGeom rg = red_geom(ctx, n, dist ? A->n_global : n, grid_per_sm, 2);
+    const int grid = rg.nvs * rg.G;
     // r = rhs ; p = z = R(r) or r ; Ap = A p                                                   (GCR.h:189-192)
     // the operator / preconditioner read rhs directly; r (and p when there is no preconditioner) are written by the init
     // kernel in the pass that forms the first inner products
     if (right) GTRY(right->apply(rhs, ps));
     GTRY(A->apply(right ? ps : rhs, Aps));
-    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, n, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red)));
+    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red)));
     GCUDA(cudaGetLastError());
     if (left) {
         // r <- L(r) (GCR.h:201-204): the first alpha and the step-0 print use the preconditioned r with the UNpreconditioned Ap
         GTRY(left->apply(rhs, r));
-        GTRY(vec_dot_dev(ctx, n, std_conj ? Aps : r, std_conj ? r : Aps, red + S_ANUM, false));   // <r,Ap> (or <Ap,r>), local part
-        GTRY(vec_norm2_dev(ctx, n, r, red + S_RR, false));
+        GTRY(vec_dot_dev(ctx, n, std_conj ? Aps : r, std_conj ? r : Aps, red + S_ANUM, false, dist ? A->n_global : n));   // <r,Ap> (or <Ap,r>), local part
+        GTRY(vec_norm2_dev(ctx, n, r, red + S_RR, false, dist ? A->n_global : n));
     }
     if (dist) GTRY(dist_allreduce_sum2(ctx, red, scal, 5));
     // Short solves nobody watches (the smoothers of the multigrid cycle): no read-back at all, the kernels carry the
@@ -239,11 +243,11 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     do {
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
-        KLAUNCH(ctx, "gcr_update_xr", 96. * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, n, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
+        KLAUNCH(ctx, "gcr_update_xr", 96. * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
                                                                  scal, red + S_RR, bden_off + cur, ctx->d_partials, ctx->d_ticket, guard, tol2)));
         GCUDA(cudaGetLastError());
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
-            KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, n, (const c128*)x, ctx->d_partials, ctx->d_ticket, red + S_BB)));
+            KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, rg, (const c128*)x, ctx->d_partials, ctx->d_ticket, red + S_BB)));
             GCUDA(cudaGetLastError());
             if (dist) GTRY(dist_allreduce_sum2(ctx, red + S_BB, scal + S_BB, 1));
         }
@@ -262,7 +266,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
                 ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + cnt));
                 // (distributed: the stopping test sees the GLOBAL ||r||^2 of the previous iteration here -- this iteration's is all-reduced
                 // together with the inner products below --, identical on every rank; the output is unused once the solve has converged)
-                GTRY(dot_hist(ctx, cnt, grid, n, Ar, Aps, stride, hl, std_conj, red + S_BNUM + 2 * c0, guard, tol2));
+                GTRY(dot_hist(ctx, cnt, rg, dist ? A->n_global : n, Ar, Aps, stride, hl, std_conj, red + S_BNUM + 2 * c0, guard, tol2));
             }
             GCUDA(cudaGetLastError());
         }
@@ -284,7 +288,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
                 for (int k = 0; k < GCR_CHUNK; k++) { bl.slot[k] = k < cnt ? c * GCR_CHUNK + k : 0; bl.num_index[k] = bl.slot[k]; }
                 int first = (c == 0), last = (c == nchunks - 1);
                 ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * cnt + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0)));
-                update_p(ctx, cnt, grid, n, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red + S_ANUM, guard, tol2);
+                update_p(ctx, cnt, rg, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red + S_ANUM, guard, tol2);
             }
             GCUDA(cudaGetLastError());
             if (dist) GTRY(dist_allreduce_sum2(ctx, red + S_ANUM, scal + S_ANUM, 3));
@@ -405,7 +409,7 @@ int arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* ep, int n_vec, c128
     p.verbose = 0;
     for (int i = 0; i < 10; i++) {                                        // MG.h:100-104
         MGCR_TRY(gcr_solve(ctx, A, &p, nullptr, b, b, nullptr, 0, nullptr));
-        MGCR_TRY(vec_normalise(ctx, n, b, dist));
+        MGCR_TRY(vec_normalise(ctx, n, b, dist, A->n_global));
     }
     const int grid = stream_grid(ctx, n, 8);
     for (int c = 1; c < n_vec; c++) {                                     // MG.h:110-121
@@ -414,13 +418,13 @@ int arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* ep, int n_vec, c128
         MGCR_TRY(gcr_solve(ctx, A, &p, nullptr, vecs + (int64_t)(c - 1) * n, tmp, nullptr, 0, nullptr));
         for (int j = 0; j < c; j++) {
             const c128* ej = vecs + (int64_t)j * n;
-            MGCR_TRY(vec_dot_dev(ctx, n, ej, tmp, ctx->d_scratch + 16, dist));
+            MGCR_TRY(vec_dot_dev(ctx, n, ej, tmp, ctx->d_scratch + 16, dist, A->n_global));
             if (n) {
                 KLAUNCH(ctx, "vec_axpy", 48. * n, (k_axpy_devscal<<<grid, RED_THREADS, 0, ctx->stream>>>(n, ctx->d_scratch + 16, -1., ej, tmp, tmp)));
                 CHECK_LAUNCH();
             }
         }
-        MGCR_TRY(vec_normalise(ctx, n, tmp, dist));
+        MGCR_TRY(vec_normalise(ctx, n, tmp, dist, A->n_global));
     }
     return MGCR_OK;
 }

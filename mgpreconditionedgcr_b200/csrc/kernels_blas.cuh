@@ -5,6 +5,12 @@
 #include "common.cuh"
 
 #define GRID_STRIDE(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+// the same over the virtual slab of this CTA (RedGeom, common.cuh): CTA (v, c) = (blockIdx.x / G, blockIdx.x % G) strides over
+// elements [v L, (v + 1) L) with stride G * blockDim.x; nvs = 1, G = gridDim.x, L = n is exactly GRID_STRIDE
+#define SLAB_STRIDE(i, rg)                                                                                                                  \
+    for (int64_t i = (int64_t)(blockIdx.x / (rg).G) * (rg).L + (int64_t)(blockIdx.x % (rg).G) * blockDim.x + threadIdx.x,                  \
+                 slab_end__ = (int64_t)(blockIdx.x / (rg).G + 1) * (rg).L;                                                                  \
+         i < slab_end__; i += (int64_t)(rg).G * blockDim.x)
 
 static __global__ void __launch_bounds__(RED_THREADS) k_fill(int64_t n, c128 v, c128* __restrict__ out) {
     PDL_ENTRY();
@@ -36,26 +42,26 @@ static __global__ void __launch_bounds__(RED_THREADS) k_scale_inv_sqrt(int64_t n
     }
 }
 
-static __global__ void __launch_bounds__(RED_THREADS) k_dot(int64_t n, const c128* __restrict__ a, const c128* __restrict__ b,
+static __global__ void __launch_bounds__(RED_THREADS) k_dot(RedGeom rg, const c128* __restrict__ a, const c128* __restrict__ b,
                                                      double* partials, unsigned int* ticket, double* out) {
     PDL_ENTRY();
     double v[2] = {0., 0.};
-    GRID_STRIDE(i, n) {
+    SLAB_STRIDE(i, rg) {
         c128 t = cmulc(ld_stream(a + i), ld_stream(b + i));
         v[0] += t.x; v[1] += t.y;
     }
-    grid_reduce<2>(v, partials, ticket, out);
+    grid_reduce<2>(v, partials, ticket, out, rg);
 }
 
-static __global__ void __launch_bounds__(RED_THREADS) k_norm2(int64_t n, const c128* __restrict__ a, double* partials,
+static __global__ void __launch_bounds__(RED_THREADS) k_norm2(RedGeom rg, const c128* __restrict__ a, double* partials,
                                                        unsigned int* ticket, double* out) {
     PDL_ENTRY();
     double v[1] = {0.};
-    GRID_STRIDE(i, n) {
+    SLAB_STRIDE(i, rg) {
         c128 t = ld_stream(a + i);
         v[0] += t.x * t.x + t.y * t.y;
     }
-    grid_reduce<1>(v, partials, ticket, out);
+    grid_reduce<1>(v, partials, ticket, out, rg);
 }
 
 // gamma5 permutation along an axis of extent axis_dim with `inner` elements below it (src/Fields.h:310-339):
@@ -93,12 +99,12 @@ __device__ __forceinline__ bool gcr_converged(const double* guard, double tol2) 
 
 // init: <r,Ap>, <Ap,Ap>, ||rhs||^2 (r = rhs at start) in one pass -> S_ANUM(2), S_ADEN, S_BB, S_RR (= ||rhs||^2)
 // The same pass also makes the solver's working copies r = rhs and (without a preconditioner) p = r  (GCR.h:189-190).
-static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, const c128* __restrict__ r, const c128* __restrict__ Ap,
+static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, const c128* __restrict__ r, const c128* __restrict__ Ap,
                                                           int std_conj, c128* __restrict__ r_out, c128* __restrict__ p_out,
                                                           double* partials, unsigned int* ticket, double* out5) {
     PDL_ENTRY();
     double v[5] = {0., 0., 0., 0., 0.};
-    GRID_STRIDE(i, n) {
+    SLAB_STRIDE(i, rg) {
         c128 rv = ld_stream(r + i), av = ld_stream(Ap + i);
         if (r_out) st_stream(r_out + i, rv);
         if (p_out) st_stream(p_out + i, rv);
@@ -109,11 +115,11 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(int64_t n, cons
     }
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
     v[4] = v[3];
-    grid_reduce<5>(v, partials, ticket, out5);
+    grid_reduce<5>(v, partials, ticket, out5, rg);
 }
 
 // x += alpha p ; r -= alpha Ap ; ||r||^2 -> scal[S_RR]      (GCR.h:230-233)
-static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n, const c128* __restrict__ p, const c128* __restrict__ Ap,
+static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg, const c128* __restrict__ p, const c128* __restrict__ Ap,
                                                                c128* x, c128* r, double* scal, double* rr_out, int bden_slot, double* partials,
                                                                unsigned int* ticket, const double* guard, double tol2) {
     PDL_ENTRY();
@@ -124,8 +130,9 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n,
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[bden_slot] = aden;
     double v[1] = {0.};
     // two elements per trip: 8 independent 128-bit loads in flight per thread
-    const int64_t T = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t T = (int64_t)rg.G * blockDim.x;
+    const int64_t n = (int64_t)(blockIdx.x / rg.G + 1) * rg.L;            // end of this CTA's virtual slab
+    int64_t i = (int64_t)(blockIdx.x / rg.G) * rg.L + (int64_t)(blockIdx.x % rg.G) * blockDim.x + threadIdx.x;
     for (; i + T < n; i += 2 * T) {
         const c128 p0 = ld_stream(p + i), a0 = ld_stream(Ap + i), p1 = ld_stream(p + i + T), a1 = ld_stream(Ap + i + T);
         c128 x0 = ld_plain(x + i), r0 = ld_plain(r + i), x1 = ld_plain(x + i + T), r1 = ld_plain(r + i + T);
@@ -144,7 +151,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(int64_t n,
         st_stream(r + i, rv);
         v[0] += rv.x * rv.x + rv.y * rv.y;
     }
-    grid_reduce<1>(v, partials, ticket, rr_out);   // scal + S_RR, or this rank's partial block when the solve is distributed
+    grid_reduce<1>(v, partials, ticket, rr_out, rg);   // scal + S_RR, or this rank's partial block when the solve is distributed
 }
 
 // batched <Ar, Aps[slot]> for nh (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
@@ -185,7 +192,7 @@ __device__ __forceinline__ void dot_hist_group(int64_t n, int64_t i0, int64_t T,
 }
 
 template <int NK, int KS>
-static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
+static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(RedGeom rg, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                               int64_t stride, HistList hl, int nh, int std_conj, double* out /* 2*nh */,
                                                               double* partials, unsigned int* ticket, const double* guard, double tol2) {
     PDL_ENTRY();
@@ -200,8 +207,9 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, 
     double v[2 * NK];
 #pragma unroll
     for (int k = 0; k < 2 * NK; k++) v[k] = 0.;
-    const int64_t T = (int64_t)gridDim.x * GT;
-    const int64_t i0 = blockIdx.x * (int64_t)GT + tl;
+    const int64_t T = (int64_t)rg.G * GT;
+    const int64_t n = (int64_t)(blockIdx.x / rg.G + 1) * rg.L;            // end of this CTA's virtual slab
+    const int64_t i0 = (int64_t)(blockIdx.x / rg.G) * rg.L + (int64_t)(blockIdx.x % rg.G) * GT + tl;
     switch (cnt) {
         case 1: dot_hist_group<1, 4, NK>(n, i0, T, Ar, hp, v); break;
         case 2: if constexpr (NK >= 2) dot_hist_group<2, 2, NK>(n, i0, T, Ar, hp, v); break;
@@ -243,11 +251,9 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(int64_t n, 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // last CTA: warp w sums value q = w, w + 8, ... over all CTAs in a fixed order (lanes stride over CTAs, then the tree)
+    // last CTA: warp w combines value q = w, w + 8, ... over all CTAs in a fixed order (combine_partials)
     for (int q = warp; q < nv; q += RED_THREADS / 32) {
-        double acc = 0.;
-        for (unsigned int bidx = lane; bidx < gridDim.x; bidx += 32) acc += __ldcg(&partials[(size_t)bidx * MAX_RED_VALUES + q]);
-        acc = warp_sum(acc);
+        const double acc = combine_partials(partials, MAX_RED_VALUES, q, rg, lane);
         if (lane == 0) out[q] = acc;
     }
 }
@@ -284,7 +290,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 enum { DOT_TMA_MAX_STAGES = 16 };
 
 template <int NH>
-static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int64_t n, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
+static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedGeom rg, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                                      int64_t stride, HistList hl, int std_conj, int ept, int stages,
                                                                      double* out /* 2*NH */, double* partials, unsigned int* ticket,
                                                                      const double* guard, double tol2) {
@@ -295,14 +301,17 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int6
     const int te = RED_THREADS * ept;                         // elements per tile
     const size_t stage_elems = (size_t)(1 + NH) * te;
     c128* ring = (c128*)dot_smem;
-    const int64_t tiles = (n + te - 1) / te;
+    // tiles of this CTA's virtual slab, dealt round-robin over the slab's G CTAs
+    const int64_t slab0 = (int64_t)(blockIdx.x / rg.G) * rg.L, n = slab0 + rg.L;
+    const int cta = blockIdx.x % rg.G;
+    const int64_t tiles = (rg.L + te - 1) / te;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     auto issue = [&](int64_t tile, int s) {                   // thread 0 only
-        const int64_t e0 = tile * te;
+        const int64_t e0 = slab0 + tile * te;
         const uint32_t cnt = (uint32_t)min((int64_t)te, n - e0);
         c128* dst = ring + (size_t)s * stage_elems;
         mbar_expect_tx(&full[s], cnt * 16u * (1 + NH));
@@ -312,17 +321,17 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int6
     };
     if (threadIdx.x == 0)
         for (int s = 0; s < stages; s++) {
-            const int64_t tile = blockIdx.x + (int64_t)s * gridDim.x;
+            const int64_t tile = cta + (int64_t)s * rg.G;
             if (tile < tiles) issue(tile, s);
         }
     double v[2 * NH];
 #pragma unroll
     for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
     int s = 0; uint32_t parity = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int64_t tile = cta; tile < tiles; tile += rg.G) {
         mbar_wait(&full[s], parity);
         const c128* st = ring + (size_t)s * stage_elems;
-        const int64_t left = n - tile * te;
+        const int64_t left = rg.L - tile * te;
         for (int q = 0; q < ept; q++) {
             const int e = q * RED_THREADS + threadIdx.x;
             if (e < left) {
@@ -335,7 +344,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int6
             }
         }
         __syncthreads();                                      // every thread is done with stage s
-        const int64_t next = tile + (int64_t)stages * gridDim.x;
+        const int64_t next = tile + (int64_t)stages * rg.G;
         if (threadIdx.x == 0 && next < tiles) issue(next, s);
         if (++s == stages) { s = 0; parity ^= 1; }
     }
@@ -343,7 +352,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int6
 #pragma unroll
         for (int k = 0; k < NH; k++) v[2 * k + 1] = -v[2 * k + 1];
     }
-    grid_reduce<2 * NH>(v, partials, ticket, out);
+    grid_reduce<2 * NH>(v, partials, ticket, out, rg);
 }
 
 // p_new = z + sum_i(-beta_i ps[i]) ; Ap_new = Ar + sum_i(-beta_i Aps[i]) written into ring slot `cur`, with the next
@@ -356,7 +365,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(int6
 struct BetaList { int slot[GCR_CHUNK]; int num_index[GCR_CHUNK]; };
 
 template <int NH, int MINB>
-static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64_t n, const c128* z, const c128* Ar, const c128* r, c128* ps,
+static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGeom rg, const c128* z, const c128* Ar, const c128* r, c128* ps,
                                                                     c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
                                                                     c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, const double* scal,
                                                                     double* anum_out, double* partials, unsigned int* ticket, const double* guard,
@@ -375,7 +384,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64
     double v[3] = {0., 0., 0.};
     constexpr int CH = 4;                    // history vectors loaded per batch: 2*CH 128-bit loads in flight per thread
     constexpr int NFULL = (NH / CH) * CH;
-    GRID_STRIDE(i, n) {
+    SLAB_STRIDE(i, rg) {
         c128 pc = first ? cmake(0., 0.) : ld_plain(acc_p + i);
         c128 Apc = first ? cmake(0., 0.) : ld_plain(acc_Ap + i);
 #pragma unroll 1
@@ -419,7 +428,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(int64
         st_stream(Apout + i, Apc);
     }
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
-    if (last) grid_reduce<3>(v, partials, ticket, anum_out);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
+    if (last) grid_reduce<3>(v, partials, ticket, anum_out, rg);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
 }
 
 // out = a + sign * s * b with the complex scalar s in device memory (Gram-Schmidt updates: src/MG.h:116-118, 192-194)

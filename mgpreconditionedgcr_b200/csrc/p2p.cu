@@ -180,16 +180,21 @@ static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, ui
     }
     __syncthreads();   // `in` has been read by every thread before anybody overwrites it (out may alias in)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double sum = 0.;
+        double part[16];
         for (int r = 0; r < nranks; r++) {
             const uint64_t* w = mine + (size_t)r * (2 * P2P_AR_MAX) + 2 * i;
             uint64_t lo, hi;
             SpinGuard guard;
             while ((uint32_t)((lo = ld_volatile_u64(w)) >> 32) != seq) guard.tick();
             while ((uint32_t)((hi = ld_volatile_u64(w + 1)) >> 32) != seq) guard.tick();
-            sum += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+            part[r] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
         }
-        out[i] = sum;
+        // balanced binary tree over the rank index: with a power-of-two number of ranks this continues the tree each rank summed
+        // its own virtual slabs with (common.cuh, RedGeom), so 1, 2, 4 and 8 GPUs perform the same additions; identical bits on
+        // every rank in any case
+        for (int w = 1; w < nranks; w <<= 1)
+            for (int r = 0; r + w < nranks; r += 2 * w) part[r] += part[r + w];
+        out[i] = part[0];
     }
 }
 

@@ -72,15 +72,19 @@ extern "C" int mgcr_vec_scale(mgcr_ctx* ctx, int64_t n, double s_re, double s_im
 }
 
 // device-resident result: d_out[0..1] = sum conj(a) b (this rank's part, then all-reduced)
-int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist) {
-    KLAUNCH(ctx, "vec_dot", 32. * n, (launch_pdl(ctx, k_dot, stream_grid(ctx, n, 4, 2), RED_THREADS, 0, n, a, b, ctx->d_partials, ctx->d_ticket, d_out)));
+// n_global: the length of the whole (slab-partitioned) vector when known -- the reduction then has the GPU-count-independent
+// shape of red_geom; 0 = unknown (plain shape)
+int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist, int64_t n_global = 0) {
+    const RedGeom rg = red_geom(ctx, n, n_global > 0 ? n_global : (dist ? 0 : n), 4, 2);
+    KLAUNCH(ctx, "vec_dot", 32. * n, (launch_pdl(ctx, k_dot, rg.nvs * rg.G, RED_THREADS, 0, rg, a, b, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
     if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 2));
     return MGCR_OK;
 }
 
-int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist) {
-    KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, stream_grid(ctx, n, 4, 2), RED_THREADS, 0, n, a, ctx->d_partials, ctx->d_ticket, d_out)));
+int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist, int64_t n_global = 0) {
+    const RedGeom rg = red_geom(ctx, n, n_global > 0 ? n_global : (dist ? 0 : n), 4, 2);
+    KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, rg.nvs * rg.G, RED_THREADS, 0, rg, a, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
     if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 1));
     return MGCR_OK;
@@ -106,8 +110,8 @@ extern "C" int mgcr_vec_squarednorm(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a
 }
 
 // a *= 1/sqrt(sum |a|^2), scalar never leaves the device (src/Fields.h:237-243)
-int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist) {
-    MGCR_TRY(vec_norm2_dev(ctx, n, a, ctx->d_scratch + 8, dist));
+int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist, int64_t n_global = 0) {
+    MGCR_TRY(vec_norm2_dev(ctx, n, a, ctx->d_scratch + 8, dist, n_global));
     KLAUNCH(ctx, "vec_normalise", 32. * n, (launch_pdl(ctx, k_scale_inv_sqrt, stream_grid(ctx, n, 8), RED_THREADS, 0, n, (const double*)(ctx->d_scratch + 8), a)));
     CHECK_LAUNCH();
     return MGCR_OK;

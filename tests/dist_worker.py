@@ -163,6 +163,30 @@ def main(rank, world, port, gather_dofs, mode="unit"):
     out["mg_loose_x_rel"] = float(np.linalg.norm(yl.numpy() - y1.numpy()[sl]) / np.linalg.norm(y1.numpy()[sl]))
     rl = rhsl - A(yl)
     out["mg_loose_true_res"] = rl.norm() / rhsl.norm()
+    # GPU-count-independent reduction shape (csrc/common.cuh, RedGeom): on a lattice whose length divides into the 8 virtual slabs
+    # (>= 2^16 elements each) the distributed solve performs the same additions as the one-GPU solve -- histories and solutions are
+    # IDENTICAL, bit for bit, for unpreconditioned GCR and for the MG-preconditioned solve (inverse iteration, hierarchy, cycle)
+    if mode == "unit":
+        dims_b = [64, 64, 128]
+        Vb = int(np.prod(dims_b))
+        pb = dims_b[1] * dims_b[2]
+        bb, eb = host.slab_range(dims_b[0], 16, rank, world)
+        Ab, Ab1 = host.DiracOp(ctx, host.Hopping(ctx, dims_b), 1. / 6.3), host.DiracOp(single, host.Hopping(single, dims_b), 1. / 6.3)
+        rb1 = single.init_rand(0, Vb)
+        rbl = ctx.init_rand(0, Ab.get_dim(), skip=bb * pb)
+        pg = host.GCR_Param(0, 5, 60, 1e-10, False, None, None)
+        xb1, xbl = single.field(Vb).set_zero(), ctx.field(Ab.get_dim()).set_zero()
+        ib1, hb1 = host.GCR(single, Ab1, pg).solve(rb1, xb1)
+        ibl, hbl = host.GCR(ctx, Ab, pg).solve(rbl, xbl)
+        out["bits_gcr"] = bool(ib1 == ibl and np.array_equal(hb1, hbl) and np.array_equal(xbl.numpy(), xb1.numpy()[bb * pb:eb * pb]))
+        lvb = [dict(site_dims=[1] + dims_b, sub=[1, 4, 4, 4], n_spin=1, n_col=1, n_eigen=4)]
+        mgb = host.MG(ctx, Ab, lvb, eig, host.GCR_Param(0, 10, 2, 1e-2), host.GCR_Param(0, 4, 2, 1e-8))
+        mgb1 = host.MG(single, Ab1, lvb, eig, host.GCR_Param(0, 10, 2, 1e-2), host.GCR_Param(0, 4, 2, 1e-8))
+        xb1.set_zero(); xbl.set_zero()
+        jb1, gb1 = host.GCR(single, Ab1, host.GCR_Param(0, 3, 100, 1e-10, False, None, mgb1)).solve(rb1, xb1)
+        jbl, gbl = host.GCR(ctx, Ab, host.GCR_Param(0, 3, 100, 1e-10, False, None, mgb)).solve(rbl, xbl)
+        out["bits_mg"] = bool(jb1 == jbl and np.array_equal(gb1, gbl) and np.array_equal(xbl.numpy(), xb1.numpy()[bb * pb:eb * pb]))
+        out["bits_mg_hist_rel"] = float(np.max(np.abs(gbl[:min(len(gbl), len(gb1))] - gb1[:min(len(gbl), len(gb1))]) / gb1[:min(len(gbl), len(gb1))]))
     res = [None] * world
     dist.all_gather_object(res, out)
     if rank == 0:
