@@ -97,36 +97,41 @@ struct RowSlots { int K; int slot[9]; int64_t col[9]; };
 // neighbour's plane first); at the global boundary of the partitioned dimension there is no neighbour (the reference's
 // periodic wrap-around block, MG.h:229-231, would couple the first and the last GPU; it is structurally zero for the
 // Dirichlet operators the distributed configurations use).
+// Blocks of a row are ordered by their GLOBAL column: the lower neighbour rank's aggregates come before every local one, the upper
+// neighbour's after (slabs are contiguous in the slowest dimension), although their local ghost ids are >= nb.  A slab-partitioned
+// coarse operator then adds up the blocks of a row in exactly the order the one-GPU operator does (bit-identical applies).
 __host__ __device__ inline void row_slots(const LevelGeom& g, int64_t B, RowSlots* rs) {
     int64_t bi[4], rem = B;
     for (int c = 3; c >= 0; c--) { bi[c] = rem % g.bd[c]; rem /= g.bd[c]; }
+    int64_t key[9];   // sort key: global order
+    const int64_t LO = -1, HI = (int64_t)1 << 62;
     int K = 0;
-    rs->slot[K] = 0; rs->col[K] = B; K++;
+    rs->slot[K] = 0; rs->col[K] = B; key[K] = B; K++;
     for (int d = 0; d < 4; d++) {
         int64_t stride = 1;
         for (int c = 3; c > d; c--) stride *= g.bd[c];
         if (g.dist && d == g.pd) {
             const int64_t in_plane = B - bi[d] * stride;   // dims before pd have extent 1
-            if (bi[d] > 0) { rs->slot[K] = 2 * d + 1; rs->col[K] = B - stride; K++; }
-            else if (g.has_lo) { rs->slot[K] = 2 * d + 1; rs->col[K] = g.nb + in_plane; K++; }
-            if (bi[d] + 1 < g.bd[d]) { rs->slot[K] = 2 * d + 2; rs->col[K] = B + stride; K++; }
-            else if (g.has_hi) { rs->slot[K] = 2 * d + 2; rs->col[K] = g.nb + (g.has_lo ? g.plane_blocks : 0) + in_plane; K++; }
+            if (bi[d] > 0) { rs->slot[K] = 2 * d + 1; rs->col[K] = B - stride; key[K] = B - stride; K++; }
+            else if (g.has_lo) { rs->slot[K] = 2 * d + 1; rs->col[K] = g.nb + in_plane; key[K] = LO; K++; }
+            if (bi[d] + 1 < g.bd[d]) { rs->slot[K] = 2 * d + 2; rs->col[K] = B + stride; key[K] = B + stride; K++; }
+            else if (g.has_hi) { rs->slot[K] = 2 * d + 2; rs->col[K] = g.nb + (g.has_lo ? g.plane_blocks : 0) + in_plane; key[K] = HI; K++; }
             continue;
         }
         if (g.bd[d] >= 2) {
             int64_t m = (bi[d] - 1 + g.bd[d]) % g.bd[d];
-            rs->slot[K] = 2 * d + 1; rs->col[K] = B + (m - bi[d]) * stride; K++;
+            rs->slot[K] = 2 * d + 1; rs->col[K] = B + (m - bi[d]) * stride; key[K] = rs->col[K]; K++;
         }
         if (g.bd[d] >= 3) {
             int64_t p = (bi[d] + 1) % g.bd[d];
-            rs->slot[K] = 2 * d + 2; rs->col[K] = B + (p - bi[d]) * stride; K++;
+            rs->slot[K] = 2 * d + 2; rs->col[K] = B + (p - bi[d]) * stride; key[K] = rs->col[K]; K++;
         }
     }
-    // ascending column order, ties (none structurally) by slot: insertion sort
+    // ascending global column order, ties (none structurally) by slot: insertion sort
     for (int a = 1; a < K; a++) {
-        int s = rs->slot[a]; int64_t c = rs->col[a]; int q = a;
-        while (q > 0 && (rs->col[q - 1] > c || (rs->col[q - 1] == c && rs->slot[q - 1] > s))) { rs->slot[q] = rs->slot[q - 1]; rs->col[q] = rs->col[q - 1]; q--; }
-        rs->slot[q] = s; rs->col[q] = c;
+        int s = rs->slot[a]; int64_t c = rs->col[a], k = key[a]; int q = a;
+        while (q > 0 && (key[q - 1] > k || (key[q - 1] == k && rs->slot[q - 1] > s))) { rs->slot[q] = rs->slot[q - 1]; rs->col[q] = rs->col[q - 1]; key[q] = key[q - 1]; q--; }
+        rs->slot[q] = s; rs->col[q] = c; key[q] = k;
     }
     rs->K = K;
 }

@@ -48,10 +48,10 @@ dist)
 knobs)
     # same box: programmatic dependent launch and blind preconditioned solves on / off
     : > $O/${TAG}_knobs.txt
-    for cfg in "MGCR_PDL=1 MGCR_BLIND_PRECOND=1" "MGCR_PDL=0 MGCR_BLIND_PRECOND=1" "MGCR_PDL=1 MGCR_BLIND_PRECOND=0" "MGCR_PDL=0 MGCR_BLIND_PRECOND=0" "MGCR_PDL=1 MGCR_BLIND_PRECOND=1"; do
+    for cfg in ${KNOB_CFGS:-"MGCR_PDL=1 MGCR_BLIND_PRECOND=1" "MGCR_PDL=0 MGCR_BLIND_PRECOND=1" "MGCR_PDL=1 MGCR_BLIND_PRECOND=0" "MGCR_PDL=0 MGCR_BLIND_PRECOND=0" "MGCR_PDL=1 MGCR_BLIND_PRECOND=1"}; do
         echo "== $cfg" >> $O/${TAG}_knobs.txt
         env $cfg timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-others 2>/dev/null | tail -1 > $O/knob_tmp.json
-        python scripts/bench_brief.py $O/knob_tmp.json | head -2 >> $O/${TAG}_knobs.txt
+        python scripts/bench_brief.py $O/knob_tmp.json 2>/dev/null | head -${KNOB_LINES:-2} >> $O/${TAG}_knobs.txt
     done
     cat $O/${TAG}_knobs.txt ;;
 kbt)
