@@ -126,11 +126,12 @@ struct mgcr_ctx {
     std::vector<ProfPending> prof_pending;
 };
 
-enum { MAX_RED_BLOCKS = 8192, MAX_RED_VALUES = 32, RED_THREADS = 256 };
+enum { MAX_RED_BLOCKS = 8192, MAX_RED_VALUES = 32, RED_THREADS = 256 };   // MAX_RED_BLOCKS: partial slots = CTAs x virtual slabs
 
 // Shape of a reduction over a (possibly slab-partitioned) vector that does NOT depend on the number of GPUs: the GLOBAL vector is
-// cut into RED_VSLABS equal virtual slabs; a rank that holds `nvs` of them launches nvs * G CTAs, CTA (v, c) strides over virtual
-// slab v only, with a stride and a CTA count G that depend on the slab length L alone.  The per-slab sums are combined by a
+// cut into RED_VSLABS equal virtual slabs; a rank that holds `nvs` of them launches G CTAs, and CTA c plays the virtual CTA (v, c) of
+// every slab v in turn: it strides over slab v only, with a stride and a CTA count G that depend on the slab length L alone, and
+// leaves one partial per (v, c).  The per-slab sums are combined by a
 // balanced binary tree over the slab index -- inside a rank over its own slabs, across ranks (which own aligned subtrees when
 // their number is a power of two) by the same tree in the all-reduce (p2p.cu).  One GPU therefore forms exactly the partial sums
 // and additions that 2, 4 or 8 GPUs form: residual histories are identical bit for bit at every GPU count.
@@ -159,7 +160,7 @@ static inline RedGeom red_geom(const mgcr_ctx* ctx, int64_t n_local, int64_t n_g
     rg.L = n_global / RED_VSLABS;
     // G depends on the slab length and on per-launch constants only (148 SMs on every B200): the same on every GPU count
     const int64_t need = (rg.L + (int64_t)RED_THREADS * items_per_thread - 1) / ((int64_t)RED_THREADS * items_per_thread);
-    const int64_t cap = std::min<int64_t>((int64_t)148 * per_sm, MAX_RED_BLOCKS / RED_VSLABS);
+    const int64_t cap = std::min<int64_t>((int64_t)148 * per_sm, MAX_RED_BLOCKS / RED_VSLABS);   // 148 SMs on every B200
     rg.G = (int)std::max<int64_t>(1, std::min(need, cap));
     return rg;
 }
@@ -339,14 +340,15 @@ __device__ __forceinline__ double combine_partials(const double* __restrict__ pa
     return segs[0];
 }
 
-// blockDim.x must be RED_THREADS, gridDim.x = rg.nvs * rg.G.  Returns true in every thread of the last block (after results are final).
+// blockDim.x must be RED_THREADS, gridDim.x = rg.G.  Two steps:
+//   cta_partial<NV>(v, partials, vslab, rg)   after the pass over virtual slab `vslab`: this CTA's partial of the NV running sums
+//   grid_finish<NV>(partials, ticket, result, rg)   once, after the last slab: the last CTA to arrive combines all partials
 template <int NV>
-__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
-                                            double* __restrict__ result, const RedGeom& rg, int nwrite = NV) {
+__device__ __forceinline__ void cta_partial(const double (&v)[NV], double* __restrict__ partials, int vslab, const RedGeom& rg) {
     constexpr int NW = RED_THREADS / 32;
     __shared__ double sm[NW][NV];
-    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                              // the previous slab's sums have been read out of sm
 #pragma unroll
     for (int k = 0; k < NV; k++) {
         double s = warp_sum(v[k]);
@@ -357,9 +359,16 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict_
         double s = 0.;
 #pragma unroll
         for (int w = 0; w < NW; w++) s += sm[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * NV + threadIdx.x] = s;
-        __threadfence();
+        partials[(size_t)(vslab * rg.G + blockIdx.x) * NV + threadIdx.x] = s;
     }
+}
+template <int NV>
+__device__ __forceinline__ bool grid_finish(double* __restrict__ partials, unsigned int* ticket, double* __restrict__ result, const RedGeom& rg,
+                                            int nwrite = NV) {
+    constexpr int NW = RED_THREADS / 32;
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __threadfence();                              // this CTA's partials are visible before its ticket is
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int t = atomicInc(ticket, gridDim.x - 1);   // wraps back to 0 after the last block: self-resetting

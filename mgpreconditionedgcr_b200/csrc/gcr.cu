@@ -33,7 +33,7 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 template <int NK, int KS>
 static void launch_dot_hist(mgcr_ctx* ctx, const RedGeom& rg, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int nh,
                             int std_conj, double* out, const double* guard, double tol2) {
-    launch_pdl(ctx, k_gcr_dot_hist<NK, KS>, rg.nvs * rg.G, RED_THREADS, 0, rg, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2);
+    launch_pdl(ctx, k_gcr_dot_hist<NK, KS>, rg.G, RED_THREADS, 0, rg, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2);
 }
 template <int NH>
 static int launch_dot_hist_tma(mgcr_ctx* ctx, const RedGeom& rg0, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int std_conj,
@@ -43,11 +43,11 @@ static int launch_dot_hist_tma(mgcr_ctx* ctx, const RedGeom& rg0, const c128* Ar
     const int ept = NH <= 3 ? 4 : NH <= 7 ? 2 : 1;
     const size_t stage_bytes = (size_t)(1 + NH) * RED_THREADS * ept * sizeof(c128);
     const int stages = (int)std::max<size_t>(2, std::min<size_t>(4, (150 * 1024) / stage_bytes));
-    // one CTA per SM and virtual slab (the ring takes the SM's shared memory); the slab's tiles are dealt over its CTAs
+    // one CTA per SM (the ring takes the SM's shared memory); each slab's tiles are dealt over the G CTAs
     RedGeom rg = rg0;
     const int64_t tiles = (rg.L + (int64_t)RED_THREADS * ept - 1) / ((int64_t)RED_THREADS * ept);
     rg.G = (int)std::min<int64_t>(148, tiles);
-    launch_pdl(ctx, k_gcr_dot_hist_tma<NH>, rg.nvs * rg.G, RED_THREADS, stages * stage_bytes, rg, Ar, Aps, stride, hl, std_conj, ept, stages, out,
+    launch_pdl(ctx, k_gcr_dot_hist_tma<NH>, rg.G, RED_THREADS, stages * stage_bytes, rg, Ar, Aps, stride, hl, std_conj, ept, stages, out,
                ctx->d_partials, ctx->d_ticket, guard, tol2);
     return MGCR_OK;
 }
@@ -75,7 +75,7 @@ template <int NH, int MINB>
 static void launch_update_p(mgcr_ctx* ctx, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                             int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
                             int bden_off, double* scal, double* red_anum, const double* guard, double tol2) {
-    launch_pdl(ctx, k_gcr_update_p<NH, MINB>, rg.nvs * rg.G, RED_THREADS, 0, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
+    launch_pdl(ctx, k_gcr_update_p<NH, MINB>, rg.G, RED_THREADS, 0, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
                bden_off, (const double*)scal, red_anum, ctx->d_partials, ctx->d_ticket, guard, tol2);
 }
 static void update_p(mgcr_ctx* ctx, int nh, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
@@ -197,7 +197,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     static const int grid_per_sm = getenv("MGCR_GRID_PER_SM") ? atoi(getenv("MGCR_GRID_PER_SM")) : 4;   // experiment knob
     // reduction / streaming shape of every kernel of this solve: independent of the number of GPUs (common.cuh, RedGeom)
     const RedGeom rg = red_geom(ctx, n, dist ? A->n_global : n, grid_per_sm, 2);
-    const int grid = rg.nvs * rg.G;
+    const int grid = rg.G;   // every CTA plays its part in each of the rank's virtual slabs in turn
     // r = rhs ; p = z = R(r) or r ; Ap = A p                                                   (GCR.h:189-192)
     // the operator / preconditioner read rhs directly; r (and p when there is no preconditioner) are written by the init
     // kernel in the pass that forms the first inner products

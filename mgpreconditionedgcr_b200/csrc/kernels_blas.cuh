@@ -5,11 +5,10 @@
 #include "common.cuh"
 
 #define GRID_STRIDE(i, n) for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
-// the same over the virtual slab of this CTA (RedGeom, common.cuh): CTA (v, c) = (blockIdx.x / G, blockIdx.x % G) strides over
-// elements [v L, (v + 1) L) with stride G * blockDim.x; nvs = 1, G = gridDim.x, L = n is exactly GRID_STRIDE
-#define SLAB_STRIDE(i, rg)                                                                                                                  \
-    for (int64_t i = (int64_t)(blockIdx.x / (rg).G) * (rg).L + (int64_t)(blockIdx.x % (rg).G) * blockDim.x + threadIdx.x,                  \
-                 slab_end__ = (int64_t)(blockIdx.x / (rg).G + 1) * (rg).L;                                                                  \
+// the same over virtual slab vs of the vector (RedGeom, common.cuh): this CTA (gridDim.x = G) strides over the elements
+// [vs L, (vs + 1) L) with stride G * blockDim.x; nvs = 1, G = gridDim.x, L = n is exactly GRID_STRIDE
+#define SLAB_STRIDE(i, rg, vs)                                                                                                              \
+    for (int64_t i = (int64_t)(vs) * (rg).L + (int64_t)blockIdx.x * blockDim.x + threadIdx.x, slab_end__ = (int64_t)((vs) + 1) * (rg).L;   \
          i < slab_end__; i += (int64_t)(rg).G * blockDim.x)
 
 static __global__ void __launch_bounds__(RED_THREADS) k_fill(int64_t n, c128 v, c128* __restrict__ out) {
@@ -45,23 +44,29 @@ static __global__ void __launch_bounds__(RED_THREADS) k_scale_inv_sqrt(int64_t n
 static __global__ void __launch_bounds__(RED_THREADS) k_dot(RedGeom rg, const c128* __restrict__ a, const c128* __restrict__ b,
                                                      double* partials, unsigned int* ticket, double* out) {
     PDL_ENTRY();
-    double v[2] = {0., 0.};
-    SLAB_STRIDE(i, rg) {
-        c128 t = cmulc(ld_stream(a + i), ld_stream(b + i));
-        v[0] += t.x; v[1] += t.y;
+    for (int vs = 0; vs < rg.nvs; vs++) {
+        double v[2] = {0., 0.};
+        SLAB_STRIDE(i, rg, vs) {
+            c128 t = cmulc(ld_stream(a + i), ld_stream(b + i));
+            v[0] += t.x; v[1] += t.y;
+        }
+        cta_partial<2>(v, partials, vs, rg);
     }
-    grid_reduce<2>(v, partials, ticket, out, rg);
+    grid_finish<2>(partials, ticket, out, rg);
 }
 
 static __global__ void __launch_bounds__(RED_THREADS) k_norm2(RedGeom rg, const c128* __restrict__ a, double* partials,
                                                        unsigned int* ticket, double* out) {
     PDL_ENTRY();
-    double v[1] = {0.};
-    SLAB_STRIDE(i, rg) {
-        c128 t = ld_stream(a + i);
-        v[0] += t.x * t.x + t.y * t.y;
+    for (int vs = 0; vs < rg.nvs; vs++) {
+        double v[1] = {0.};
+        SLAB_STRIDE(i, rg, vs) {
+            c128 t = ld_stream(a + i);
+            v[0] += t.x * t.x + t.y * t.y;
+        }
+        cta_partial<1>(v, partials, vs, rg);
     }
-    grid_reduce<1>(v, partials, ticket, out, rg);
+    grid_finish<1>(partials, ticket, out, rg);
 }
 
 // gamma5 permutation along an axis of extent axis_dim with `inner` elements below it (src/Fields.h:310-339):
@@ -103,19 +108,22 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, con
                                                           int std_conj, c128* __restrict__ r_out, c128* __restrict__ p_out,
                                                           double* partials, unsigned int* ticket, double* out5) {
     PDL_ENTRY();
-    double v[5] = {0., 0., 0., 0., 0.};
-    SLAB_STRIDE(i, rg) {
-        c128 rv = ld_stream(r + i), av = ld_stream(Ap + i);
-        if (r_out) st_stream(r_out + i, rv);
-        if (p_out) st_stream(p_out + i, rv);
-        c128 t = cmulc(rv, av);
-        v[0] += t.x; v[1] += t.y;
-        v[2] += av.x * av.x + av.y * av.y;
-        v[3] += rv.x * rv.x + rv.y * rv.y;
+    for (int vs = 0; vs < rg.nvs; vs++) {
+        double v[5] = {0., 0., 0., 0., 0.};
+        SLAB_STRIDE(i, rg, vs) {
+            c128 rv = ld_stream(r + i), av = ld_stream(Ap + i);
+            if (r_out) st_stream(r_out + i, rv);
+            if (p_out) st_stream(p_out + i, rv);
+            c128 t = cmulc(rv, av);
+            v[0] += t.x; v[1] += t.y;
+            v[2] += av.x * av.x + av.y * av.y;
+            v[3] += rv.x * rv.x + rv.y * rv.y;
+        }
+        if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
+        v[4] = v[3];
+        cta_partial<5>(v, partials, vs, rg);
     }
-    if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
-    v[4] = v[3];
-    grid_reduce<5>(v, partials, ticket, out5, rg);
+    grid_finish<5>(partials, ticket, out5, rg);
 }
 
 // x += alpha p ; r -= alpha Ap ; ||r||^2 -> scal[S_RR]      (GCR.h:230-233)
@@ -128,30 +136,33 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg
     const c128 alpha = cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
     // ||Aps[cur]||^2 never changes while the slot lives: cache it for the beta denominators (GCR.h:258 recomputes it)
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[bden_slot] = aden;
-    double v[1] = {0.};
     // two elements per trip: 8 independent 128-bit loads in flight per thread
     const int64_t T = (int64_t)rg.G * blockDim.x;
-    const int64_t n = (int64_t)(blockIdx.x / rg.G + 1) * rg.L;            // end of this CTA's virtual slab
-    int64_t i = (int64_t)(blockIdx.x / rg.G) * rg.L + (int64_t)(blockIdx.x % rg.G) * blockDim.x + threadIdx.x;
-    for (; i + T < n; i += 2 * T) {
-        const c128 p0 = ld_stream(p + i), a0 = ld_stream(Ap + i), p1 = ld_stream(p + i + T), a1 = ld_stream(Ap + i + T);
-        c128 x0 = ld_plain(x + i), r0 = ld_plain(r + i), x1 = ld_plain(x + i + T), r1 = ld_plain(r + i + T);
-        x0 = cadd(x0, cmul(alpha, p0)); r0 = csub(r0, cmul(alpha, a0));
-        x1 = cadd(x1, cmul(alpha, p1)); r1 = csub(r1, cmul(alpha, a1));
-        st_stream(x + i, x0); st_stream(r + i, r0); st_stream(x + i + T, x1); st_stream(r + i + T, r1);
-        v[0] += r0.x * r0.x + r0.y * r0.y;
-        v[0] += r1.x * r1.x + r1.y * r1.y;
+    for (int vs = 0; vs < rg.nvs; vs++) {
+        double v[1] = {0.};
+        const int64_t n = (int64_t)(vs + 1) * rg.L;                        // end of this virtual slab
+        int64_t i = (int64_t)vs * rg.L + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + T < n; i += 2 * T) {
+            const c128 p0 = ld_stream(p + i), a0 = ld_stream(Ap + i), p1 = ld_stream(p + i + T), a1 = ld_stream(Ap + i + T);
+            c128 x0 = ld_plain(x + i), r0 = ld_plain(r + i), x1 = ld_plain(x + i + T), r1 = ld_plain(r + i + T);
+            x0 = cadd(x0, cmul(alpha, p0)); r0 = csub(r0, cmul(alpha, a0));
+            x1 = cadd(x1, cmul(alpha, p1)); r1 = csub(r1, cmul(alpha, a1));
+            st_stream(x + i, x0); st_stream(r + i, r0); st_stream(x + i + T, x1); st_stream(r + i + T, r1);
+            v[0] += r0.x * r0.x + r0.y * r0.y;
+            v[0] += r1.x * r1.x + r1.y * r1.y;
+        }
+        for (; i < n; i += T) {
+            c128 pv = ld_stream(p + i), av = ld_stream(Ap + i);
+            c128 xv = ld_plain(x + i), rv = ld_plain(r + i);
+            xv = cadd(xv, cmul(alpha, pv));
+            rv = csub(rv, cmul(alpha, av));
+            st_stream(x + i, xv);
+            st_stream(r + i, rv);
+            v[0] += rv.x * rv.x + rv.y * rv.y;
+        }
+        cta_partial<1>(v, partials, vs, rg);
     }
-    for (; i < n; i += T) {
-        c128 pv = ld_stream(p + i), av = ld_stream(Ap + i);
-        c128 xv = ld_plain(x + i), rv = ld_plain(r + i);
-        xv = cadd(xv, cmul(alpha, pv));
-        rv = csub(rv, cmul(alpha, av));
-        st_stream(x + i, xv);
-        st_stream(r + i, rv);
-        v[0] += rv.x * rv.x + rv.y * rv.y;
-    }
-    grid_reduce<1>(v, partials, ticket, rr_out, rg);   // scal + S_RR, or this rank's partial block when the solve is distributed
+    grid_finish<1>(partials, ticket, rr_out, rg);   // scal + S_RR, or this rank's partial block when the solve is distributed
 }
 
 // batched <Ar, Aps[slot]> for nh (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
@@ -204,45 +215,48 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(RedGeom rg,
     const c128* hp[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) hp[k] = Aps + (int64_t)hl.slot[k < cnt ? g + k * KS : 0] * stride;
-    double v[2 * NK];
-#pragma unroll
-    for (int k = 0; k < 2 * NK; k++) v[k] = 0.;
     const int64_t T = (int64_t)rg.G * GT;
-    const int64_t n = (int64_t)(blockIdx.x / rg.G + 1) * rg.L;            // end of this CTA's virtual slab
-    const int64_t i0 = (int64_t)(blockIdx.x / rg.G) * rg.L + (int64_t)(blockIdx.x % rg.G) * GT + tl;
-    switch (cnt) {
-        case 1: dot_hist_group<1, 4, NK>(n, i0, T, Ar, hp, v); break;
-        case 2: if constexpr (NK >= 2) dot_hist_group<2, 2, NK>(n, i0, T, Ar, hp, v); break;
-        case 3: if constexpr (NK >= 3) dot_hist_group<3, 2, NK>(n, i0, T, Ar, hp, v); break;
-        case 4: if constexpr (NK >= 4) dot_hist_group<4, 1, NK>(n, i0, T, Ar, hp, v); break;
-        default: break;
-    }
-    // <h, a> = conj(<a, h>) term by term and exactly (the products commute, the difference changes sign): the textbook
-    // convention only flips the sign of the imaginary sums
-    if (std_conj) {
-#pragma unroll
-        for (int k = 0; k < NK; k++) v[2 * k + 1] = -v[2 * k + 1];
-    }
     // CTA partials: value q = 2*kk + c of history vector kk = g + k*KS lives in the warps of group g
     __shared__ double sm[RED_THREADS / 32][2 * NK];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 2 * NK; k++) {
-        double s = warp_sum(v[k]);
-        if (lane == 0) sm[warp][k] = s;
-    }
-    __syncthreads();
     const int nv = 2 * nh;
-    if ((int)threadIdx.x < nv) {
-        const int kk = threadIdx.x >> 1, c = threadIdx.x & 1;
-        const int gg = kk % KS, k = kk / KS;
-        double s = 0.;
+    for (int vs = 0; vs < rg.nvs; vs++) {
+        double v[2 * NK];
 #pragma unroll
-        for (int w = 0; w < GW; w++) s += sm[gg * GW + w][2 * k + c];
-        partials[(size_t)blockIdx.x * MAX_RED_VALUES + threadIdx.x] = s;
-        __threadfence();
+        for (int k = 0; k < 2 * NK; k++) v[k] = 0.;
+        const int64_t n = (int64_t)(vs + 1) * rg.L;                        // end of this virtual slab
+        const int64_t i0 = (int64_t)vs * rg.L + (int64_t)blockIdx.x * GT + tl;
+        switch (cnt) {
+            case 1: dot_hist_group<1, 4, NK>(n, i0, T, Ar, hp, v); break;
+            case 2: if constexpr (NK >= 2) dot_hist_group<2, 2, NK>(n, i0, T, Ar, hp, v); break;
+            case 3: if constexpr (NK >= 3) dot_hist_group<3, 2, NK>(n, i0, T, Ar, hp, v); break;
+            case 4: if constexpr (NK >= 4) dot_hist_group<4, 1, NK>(n, i0, T, Ar, hp, v); break;
+            default: break;
+        }
+        // <h, a> = conj(<a, h>) term by term and exactly (the products commute, the difference changes sign): the textbook
+        // convention only flips the sign of the imaginary sums
+        if (std_conj) {
+#pragma unroll
+            for (int k = 0; k < NK; k++) v[2 * k + 1] = -v[2 * k + 1];
+        }
+        __syncthreads();                              // the previous slab's sums have been read out of sm
+#pragma unroll
+        for (int k = 0; k < 2 * NK; k++) {
+            double s = warp_sum(v[k]);
+            if (lane == 0) sm[warp][k] = s;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nv) {
+            const int kk = threadIdx.x >> 1, c = threadIdx.x & 1;
+            const int gg = kk % KS, k = kk / KS;
+            double s = 0.;
+#pragma unroll
+            for (int w = 0; w < GW; w++) s += sm[gg * GW + w][2 * k + c];
+            partials[(size_t)(vs * rg.G + blockIdx.x) * MAX_RED_VALUES + threadIdx.x] = s;
+        }
     }
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int t = atomicInc(ticket, gridDim.x - 1);
@@ -301,18 +315,20 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
     const int te = RED_THREADS * ept;                         // elements per tile
     const size_t stage_elems = (size_t)(1 + NH) * te;
     c128* ring = (c128*)dot_smem;
-    // tiles of this CTA's virtual slab, dealt round-robin over the slab's G CTAs
-    const int64_t slab0 = (int64_t)(blockIdx.x / rg.G) * rg.L, n = slab0 + rg.L;
-    const int cta = blockIdx.x % rg.G;
-    const int64_t tiles = (rg.L + te - 1) / te;
+    // The tiles of a virtual slab are dealt round-robin over the G CTAs; this CTA works through its tiles of slab 0, then of
+    // slab 1, ... as ONE stream of work items, so the ring stays full across the slab boundaries.
+    const int64_t tiles = (rg.L + te - 1) / te;                              // per slab
+    const int64_t tpc = blockIdx.x < tiles ? (tiles - blockIdx.x + rg.G - 1) / rg.G : 0;   // tiles of one slab that are this CTA's
+    const int64_t items = tpc * rg.nvs;
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; s++) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int64_t tile, int s) {                   // thread 0 only
-        const int64_t e0 = slab0 + tile * te;
-        const uint32_t cnt = (uint32_t)min((int64_t)te, n - e0);
+    auto issue = [&](int64_t item, int s) {                   // thread 0 only
+        const int64_t vs = item / tpc, tile = blockIdx.x + (item - vs * tpc) * rg.G;
+        const int64_t e0 = vs * rg.L + tile * te;
+        const uint32_t cnt = (uint32_t)min((int64_t)te, (vs + 1) * rg.L - e0);
         c128* dst = ring + (size_t)s * stage_elems;
         mbar_expect_tx(&full[s], cnt * 16u * (1 + NH));
         tma_load_1d(dst, Ar + e0, cnt * 16u, &full[s]);
@@ -320,39 +336,44 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
         for (int k = 0; k < NH; k++) tma_load_1d(dst + (size_t)(1 + k) * te, Aps + (int64_t)hl.slot[k] * stride + e0, cnt * 16u, &full[s]);
     };
     if (threadIdx.x == 0)
-        for (int s = 0; s < stages; s++) {
-            const int64_t tile = cta + (int64_t)s * rg.G;
-            if (tile < tiles) issue(tile, s);
-        }
+        for (int s = 0; s < stages; s++)
+            if (s < items) issue(s, s);
     double v[2 * NH];
 #pragma unroll
     for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
     int s = 0; uint32_t parity = 0;
-    for (int64_t tile = cta; tile < tiles; tile += rg.G) {
+    for (int64_t item = 0; item < items; item++) {
+        const int64_t vs = item / tpc, t = item - vs * tpc;
         mbar_wait(&full[s], parity);
         const c128* st = ring + (size_t)s * stage_elems;
-        const int64_t left = rg.L - tile * te;
+        const int64_t left = rg.L - (blockIdx.x + t * rg.G) * te;
         for (int q = 0; q < ept; q++) {
             const int e = q * RED_THREADS + threadIdx.x;
             if (e < left) {
                 const c128 a = st[e];
 #pragma unroll
                 for (int k = 0; k < NH; k++) {
-                    c128 t = cmulc(a, st[(size_t)(1 + k) * te + e]);
-                    v[2 * k] += t.x; v[2 * k + 1] += t.y;
+                    c128 tt = cmulc(a, st[(size_t)(1 + k) * te + e]);
+                    v[2 * k] += tt.x; v[2 * k + 1] += tt.y;
                 }
             }
         }
         __syncthreads();                                      // every thread is done with stage s
-        const int64_t next = tile + (int64_t)stages * rg.G;
-        if (threadIdx.x == 0 && next < tiles) issue(next, s);
+        if (threadIdx.x == 0 && item + stages < items) issue(item + stages, s);
         if (++s == stages) { s = 0; parity ^= 1; }
-    }
-    if (std_conj) {
+        if (t == tpc - 1) {                                   // this CTA's last tile of slab vs: its partial, fresh accumulators
+            if (std_conj) {
 #pragma unroll
-        for (int k = 0; k < NH; k++) v[2 * k + 1] = -v[2 * k + 1];
+                for (int k = 0; k < NH; k++) v[2 * k + 1] = -v[2 * k + 1];
+            }
+            cta_partial<2 * NH>(v, partials, (int)vs, rg);
+#pragma unroll
+            for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
+        }
     }
-    grid_reduce<2 * NH>(v, partials, ticket, out, rg);
+    if (tpc == 0)                                             // (more CTAs than tiles cannot happen: G <= tiles; kept for safety)
+        for (int vs = 0; vs < rg.nvs; vs++) cta_partial<2 * NH>(v, partials, vs, rg);
+    grid_finish<2 * NH>(partials, ticket, out, rg);
 }
 
 // p_new = z + sum_i(-beta_i ps[i]) ; Ap_new = Ar + sum_i(-beta_i Aps[i]) written into ring slot `cur`, with the next
@@ -381,10 +402,11 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
     __syncthreads();
     c128* pout = last ? ps + (int64_t)cur * stride : acc_p;
     c128* Apout = last ? Aps + (int64_t)cur * stride : acc_Ap;
-    double v[3] = {0., 0., 0.};
     constexpr int CH = 4;                    // history vectors loaded per batch: 2*CH 128-bit loads in flight per thread
     constexpr int NFULL = (NH / CH) * CH;
-    SLAB_STRIDE(i, rg) {
+    for (int vs = 0; vs < rg.nvs; vs++) {
+    double v[3] = {0., 0., 0.};
+    SLAB_STRIDE(i, rg, vs) {
         c128 pc = first ? cmake(0., 0.) : ld_plain(acc_p + i);
         c128 Apc = first ? cmake(0., 0.) : ld_plain(acc_Ap + i);
 #pragma unroll 1
@@ -428,7 +450,9 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
         st_stream(Apout + i, Apc);
     }
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
-    if (last) grid_reduce<3>(v, partials, ticket, anum_out, rg);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
+    if (last) cta_partial<3>(v, partials, vs, rg);
+    }
+    if (last) grid_finish<3>(partials, ticket, anum_out, rg);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
 }
 
 // out = a + sign * s * b with the complex scalar s in device memory (Gram-Schmidt updates: src/MG.h:116-118, 192-194)

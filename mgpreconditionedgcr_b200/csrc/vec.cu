@@ -76,7 +76,7 @@ extern "C" int mgcr_vec_scale(mgcr_ctx* ctx, int64_t n, double s_re, double s_im
 // shape of red_geom; 0 = unknown (plain shape)
 int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* d_out, bool dist, int64_t n_global = 0) {
     const RedGeom rg = red_geom(ctx, n, n_global > 0 ? n_global : (dist ? 0 : n), 4, 2);
-    KLAUNCH(ctx, "vec_dot", 32. * n, (launch_pdl(ctx, k_dot, rg.nvs * rg.G, RED_THREADS, 0, rg, a, b, ctx->d_partials, ctx->d_ticket, d_out)));
+    KLAUNCH(ctx, "vec_dot", 32. * n, (launch_pdl(ctx, k_dot, rg.G, RED_THREADS, 0, rg, a, b, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
     if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 2));
     return MGCR_OK;
@@ -84,7 +84,7 @@ int vec_dot_dev(mgcr_ctx* ctx, int64_t n, const c128* a, const c128* b, double* 
 
 int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool dist, int64_t n_global = 0) {
     const RedGeom rg = red_geom(ctx, n, n_global > 0 ? n_global : (dist ? 0 : n), 4, 2);
-    KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, rg.nvs * rg.G, RED_THREADS, 0, rg, a, ctx->d_partials, ctx->d_ticket, d_out)));
+    KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, rg.G, RED_THREADS, 0, rg, a, ctx->d_partials, ctx->d_ticket, d_out)));
     CHECK_LAUNCH();
     if (dist) MGCR_TRY(dist_allreduce_sum(ctx, d_out, 1));
     return MGCR_OK;
