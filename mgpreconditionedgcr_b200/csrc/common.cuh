@@ -119,6 +119,7 @@ struct mgcr_ctx {
     std::vector<cudaEvent_t> depth_events;  // read-back event of each solver nesting depth (gcr.cu)
     std::map<const void*, int> dyn_smem;    // kernels whose dynamic shared-memory limit has been raised on THIS device
     std::map<const void*, int> resident;    // kernel -> CTAs resident on the whole device (resident_ctas)
+    std::map<int64_t, int64_t> global_len;  // slab length -> length of the whole vector when all ranks hold equal slabs (vec.cu)
     // profiling
     bool profile = false;
     std::map<std::string, ProfEntry> prof;

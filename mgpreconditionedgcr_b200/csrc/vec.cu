@@ -97,15 +97,31 @@ static int read_scalars(mgcr_ctx* ctx, const double* d, int n, double* h) {
     return MGCR_OK;
 }
 
+// length of the whole vector a slab of n elements belongs to, when every rank holds a slab of the same length (0 otherwise):
+// lets the Field-level inner products use the GPU-count-independent reduction shape.  One host all-gather per distinct n.
+static int64_t global_len(mgcr_ctx* ctx, int64_t n) {
+    if (ctx->nranks == 1) return n;
+    auto it = ctx->global_len.find(n);
+    if (it != ctx->global_len.end()) return it->second;
+    std::vector<int64_t> all;
+    int64_t g = 0;
+    if (dist_allgather_host_i64(ctx, n, all) == MGCR_OK) {
+        g = n * ctx->nranks;
+        for (int64_t v : all) if (v != n) g = 0;
+    }
+    ctx->global_len[n] = g;
+    return g;
+}
+
 extern "C" int mgcr_vec_dot(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, const mgcr_c128* b, double out[2]) {
     ARG_CHECK(ctx && out && (n == 0 || (a && b)), "mgcr_vec_dot: NULL buffer");
-    MGCR_TRY(vec_dot_dev(ctx, n, (const c128*)a, (const c128*)b, ctx->d_scratch, ctx->nranks > 1));
+    MGCR_TRY(vec_dot_dev(ctx, n, (const c128*)a, (const c128*)b, ctx->d_scratch, ctx->nranks > 1, global_len(ctx, n)));
     return read_scalars(ctx, ctx->d_scratch, 2, out);
 }
 
 extern "C" int mgcr_vec_squarednorm(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, double* out) {
     ARG_CHECK(ctx && out && (n == 0 || a), "mgcr_vec_squarednorm: NULL buffer");
-    MGCR_TRY(vec_norm2_dev(ctx, n, (const c128*)a, ctx->d_scratch, ctx->nranks > 1));
+    MGCR_TRY(vec_norm2_dev(ctx, n, (const c128*)a, ctx->d_scratch, ctx->nranks > 1, global_len(ctx, n)));
     return read_scalars(ctx, ctx->d_scratch, 1, out);
 }
 
@@ -119,7 +135,7 @@ int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist, int64_t n_global
 
 extern "C" int mgcr_vec_normalise(mgcr_ctx* ctx, int64_t n, mgcr_c128* a) {
     ARG_CHECK(ctx && (n == 0 || a), "mgcr_vec_normalise: NULL buffer");
-    return vec_normalise(ctx, n, (c128*)a, ctx->nranks > 1);
+    return vec_normalise(ctx, n, (c128*)a, ctx->nranks > 1, global_len(ctx, n));
 }
 
 int vec_gamma5(mgcr_ctx* ctx, int64_t n, int64_t inner, int64_t axis_dim, const c128* in, c128* out) {
