@@ -55,6 +55,9 @@ def test_distributed_against_single_gpu(world, gather, mode, p2p):
         if mode == "unit" and p2p == "1":
             # the reduction shape does not depend on the number of GPUs: identical bits (csrc/common.cuh, RedGeom)
             assert o["bits_gcr"], "GCR history / solution differ from the one-GPU run"
-            assert o["bits_mg"], "MG-GCR history / solution differ from the one-GPU run (max rel %.3e)" % o["bits_mg_hist_rel"]
+            if gather == "default":   # (gather_dofs = 0 keeps a 2^16-dof level distributed: below the virtual-slab length, and the one-GPU
+                #                       run solves that level with the persistent small-system kernel -- equal to rounding only)
+                assert o["bits_mg"], "MG-GCR history / solution differ from the one-GPU run (max rel %.3e)" % o["bits_mg_hist_rel"]
+            assert o["bits_mg_hist_rel"] < 1e-9
         # loose inner tolerances (device-side stopping tests decide from all-reduced norms): same solve as on one GPU
         assert abs(o["mg_loose_iters"][0] - o["mg_loose_iters"][1]) <= 2 and o["mg_loose_true_res"] < 1.2e-10 and o["mg_loose_x_rel"] < 1e-8
