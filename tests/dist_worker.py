@@ -167,7 +167,7 @@ def main(rank, world, port, gather_dofs, mode="unit"):
     # (>= 2^16 elements each) the distributed solve performs the same additions as the one-GPU solve -- histories and solutions are
     # IDENTICAL, bit for bit, for unpreconditioned GCR and for the MG-preconditioned solve (inverse iteration, hierarchy, cycle)
     if mode == "unit":
-        dims_b = [64, 64, 256]   # 2^20 sites: above the persistent small-solve kernel's range (2^19), 8 virtual slabs of 2^17
+        dims_b = [max(64, 16 * world), 64, 256]   # >= 2^20 sites: above the persistent small-solve kernel's range (2^19), 8 virtual slabs of >= 2^17
         Vb = int(np.prod(dims_b))
         pb = dims_b[1] * dims_b[2]
         bb, eb = host.slab_range(dims_b[0], 16, rank, world)
