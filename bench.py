@@ -390,10 +390,11 @@ def kernel_classes(prof):
     return classes, dom, host_side
 
 
-def secondary_workload(host, torch, ctx, name, operator, local_rank, peak):
-    """one more of BASELINE.json's configurations, one warm-up + one timed solve + one profiled solve on this GPU"""
+def secondary_workload(host, torch, ctx, name, operator, local_rank, peak, world=1, rank=0, dist=None):
+    """one more of BASELINE.json's configurations, one warm-up + one timed solve + one profiled solve (on every rank when the run
+    is distributed: device time is the maximum over the ranks)"""
     wl = dict(WORKLOADS[name])
-    A, rhs, x, V = build_problem(host, torch, ctx, wl, operator, 1, 0, local_rank)
+    A, rhs, x, V = build_problem(host, torch, ctx, wl, operator, world, rank, local_rank)
     mg, setup = (None, None)
     if wl.get("mg"):
         mg, setup = build_mg(host, ctx, A, wl)
@@ -408,6 +409,10 @@ def secondary_workload(host, torch, ctx, name, operator, local_rank, peak):
     e1.record(stream)
     ctx.sync(); torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) / 1e3
+    if dist is not None:
+        t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
     r = rhs - A(x)
     final_rel = r.norm() / rhs.norm()
     ctx.set_profile(True)
@@ -415,7 +420,7 @@ def secondary_workload(host, torch, ctx, name, operator, local_rank, peak):
     ctx.sync()
     classes, dom, _ = kernel_classes(ctx.profile())
     ctx.set_profile(False)
-    out = {"desc": wl["desc"], "operator": operator, "rows": V, "value": sec, "unit": "s", "iterations": it, "final_true_rel_residual": final_rel,
+    out = {"desc": wl["desc"], "operator": operator, "rows": V, "n_gpus": world, "value": sec, "unit": "s", "iterations": it, "final_true_rel_residual": final_rel,
            "dominant_kernel": dom, "dominant_GBps": classes[dom]["GBps"], "dominant_frac": classes[dom]["GBps"] / peak,
            "kernels": {k: {"share": round(v["share"], 4), "GBps": v["GBps"]} for k, v in classes.items()}}
     op = [k for k in classes if k.startswith(("sell", "hopping"))]
@@ -691,6 +696,12 @@ def main():
                 others["c1_sample"] = c1_sample_workload(host, torch, ctx, local_rank)
             except Exception as ex:
                 others["c1_sample"] = {"error": repr(ex)[:300]}
+        if world == 8:   # BASELINE configs[4]: the anisotropic 1024x512x512 five-level solve is quoted at 8 GPUs
+            try:
+                set_align(WORKLOADS["mg3d_aniso"])
+                others["mg3d_aniso"] = secondary_workload(host, torch, ctx, "mg3d_aniso", "stencil", local_rank, peak, world, rank, dist)
+            except Exception as ex:
+                others["mg3d_aniso"] = {"error": repr(ex)[:300]}
         if rank == 0:
             line["other_workloads"] = others
     if rank == 0:

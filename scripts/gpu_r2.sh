@@ -40,8 +40,10 @@ dist)
     timeout 1500 python -m pytest tests/test_gpu_dist.py -m gpu -q -k "test_distributed_against_single_gpu and ${N}-" > $O/${TAG}_pytest_dist${N}.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_dist${N}.log
     grep -E "passed|failed|skipped|rc=" $O/${TAG}_pytest_dist${N}.log | tail -4
     grep -E "^E  " $O/${TAG}_pytest_dist${N}.log | cut -c1-400 | head -20
+    first=1
     for cfg in ${DIST_CFGS-"MGCR_HALO_DEFER=1" "MGCR_HALO_DEFER=0"}; do
-        env $cfg timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29631 bench.py --gpus $N --steps 3 --warmup 2 --no-cpu-baseline \
+        extra="--no-others"; [ $first = 1 ] && extra=""; first=0     # the first configuration is the driver's command (secondary workloads included)
+        env $cfg timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29631 bench.py --gpus $N --steps 3 --warmup 2 --no-cpu-baseline $extra \
             > $O/${TAG}_bench_n${N}_${cfg//=/}.json 2> $O/${TAG}_bench_n${N}_${cfg//=/}.err; echo "== $cfg rc=$?"
         python scripts/bench_brief.py $O/${TAG}_bench_n${N}_${cfg//=/}.json 2>&1 | head -24
     done ;;
