@@ -342,33 +342,37 @@ __device__ __forceinline__ double combine_partials(const double* __restrict__ pa
 }
 
 // blockDim.x must be RED_THREADS, gridDim.x = rg.G.  Two steps:
-//   cta_partial<NV>(v, partials, vslab, rg)   after the pass over virtual slab `vslab`: this CTA's partial of the NV running sums
-//   grid_finish<NV>(partials, ticket, result, rg)   once, after the last slab: the last CTA to arrive combines all partials
+//   slab_partial<NV>(v, vslab)                        after the pass over virtual slab `vslab`: every WARP leaves the sum of its lanes
+//                                                     in shared memory -- no block barrier, the warps of a CTA drift from slab to
+//                                                     slab independently and the loads keep flowing (a barrier per slab cost 14 % of
+//                                                     update_xr at 256^3: 14 elements per thread and slab);
+//   grid_finish<NV>(partials, ticket, result, rg)     once: the CTA's partial of every slab = its warp sums added in warp order, then
+//                                                     the last CTA to arrive combines all partials (combine_partials).
+template <int NV> struct SlabSums { double w[RED_VSLABS][RED_THREADS / 32][NV]; };
+
 template <int NV>
-__device__ __forceinline__ void cta_partial(const double (&v)[NV], double* __restrict__ partials, int vslab, const RedGeom& rg) {
-    constexpr int NW = RED_THREADS / 32;
-    __shared__ double sm[NW][NV];
+__device__ __forceinline__ void slab_partial(const double (&v)[NV], SlabSums<NV>& sm, int vslab) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();                              // the previous slab's sums have been read out of sm
 #pragma unroll
     for (int k = 0; k < NV; k++) {
         double s = warp_sum(v[k]);
-        if (lane == 0) sm[warp][k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double s = 0.;
-#pragma unroll
-        for (int w = 0; w < NW; w++) s += sm[w][threadIdx.x];
-        partials[(size_t)(vslab * rg.G + blockIdx.x) * NV + threadIdx.x] = s;
+        if (lane == 0) sm.w[vslab][warp][k] = s;
     }
 }
 template <int NV>
-__device__ __forceinline__ bool grid_finish(double* __restrict__ partials, unsigned int* ticket, double* __restrict__ result, const RedGeom& rg,
-                                            int nwrite = NV) {
+__device__ __forceinline__ bool grid_finish(SlabSums<NV>& sm, double* __restrict__ partials, unsigned int* ticket, double* __restrict__ result,
+                                            const RedGeom& rg, int nwrite = NV) {
     constexpr int NW = RED_THREADS / 32;
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    for (int t = threadIdx.x; t < rg.nvs * NV; t += RED_THREADS) {
+        const int vs = t / NV, k = t - vs * NV;
+        double s = 0.;
+#pragma unroll
+        for (int w = 0; w < NW; w++) s += sm.w[vs][w][k];
+        partials[(size_t)(vs * rg.G + blockIdx.x) * NV + k] = s;
+    }
     __threadfence();                              // this CTA's partials are visible before its ticket is
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -44,29 +44,31 @@ static __global__ void __launch_bounds__(RED_THREADS) k_scale_inv_sqrt(int64_t n
 static __global__ void __launch_bounds__(RED_THREADS) k_dot(RedGeom rg, const c128* __restrict__ a, const c128* __restrict__ b,
                                                      double* partials, unsigned int* ticket, double* out) {
     PDL_ENTRY();
+    __shared__ SlabSums<2> sums;
     for (int vs = 0; vs < rg.nvs; vs++) {
         double v[2] = {0., 0.};
         SLAB_STRIDE(i, rg, vs) {
             c128 t = cmulc(ld_stream(a + i), ld_stream(b + i));
             v[0] += t.x; v[1] += t.y;
         }
-        cta_partial<2>(v, partials, vs, rg);
+        slab_partial<2>(v, sums, vs);
     }
-    grid_finish<2>(partials, ticket, out, rg);
+    grid_finish<2>(sums, partials, ticket, out, rg);
 }
 
 static __global__ void __launch_bounds__(RED_THREADS) k_norm2(RedGeom rg, const c128* __restrict__ a, double* partials,
                                                        unsigned int* ticket, double* out) {
     PDL_ENTRY();
+    __shared__ SlabSums<1> sums;
     for (int vs = 0; vs < rg.nvs; vs++) {
         double v[1] = {0.};
         SLAB_STRIDE(i, rg, vs) {
             c128 t = ld_stream(a + i);
             v[0] += t.x * t.x + t.y * t.y;
         }
-        cta_partial<1>(v, partials, vs, rg);
+        slab_partial<1>(v, sums, vs);
     }
-    grid_finish<1>(partials, ticket, out, rg);
+    grid_finish<1>(sums, partials, ticket, out, rg);
 }
 
 // gamma5 permutation along an axis of extent axis_dim with `inner` elements below it (src/Fields.h:310-339):
@@ -108,6 +110,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, con
                                                           int std_conj, c128* __restrict__ r_out, c128* __restrict__ p_out,
                                                           double* partials, unsigned int* ticket, double* out5) {
     PDL_ENTRY();
+    __shared__ SlabSums<5> sums;
     for (int vs = 0; vs < rg.nvs; vs++) {
         double v[5] = {0., 0., 0., 0., 0.};
         SLAB_STRIDE(i, rg, vs) {
@@ -121,9 +124,9 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, con
         }
         if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
         v[4] = v[3];
-        cta_partial<5>(v, partials, vs, rg);
+        slab_partial<5>(v, sums, vs);
     }
-    grid_finish<5>(partials, ticket, out5, rg);
+    grid_finish<5>(sums, partials, ticket, out5, rg);
 }
 
 // x += alpha p ; r -= alpha Ap ; ||r||^2 -> scal[S_RR]      (GCR.h:230-233)
@@ -131,6 +134,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg
                                                                c128* x, c128* r, double* scal, double* rr_out, int bden_slot, double* partials,
                                                                unsigned int* ticket, const double* guard, double tol2) {
     PDL_ENTRY();
+    __shared__ SlabSums<1> sums;
     if (gcr_converged(guard, tol2)) return;
     const double aden = scal[S_ADEN];
     const c128 alpha = cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
@@ -160,9 +164,9 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg
             st_stream(r + i, rv);
             v[0] += rv.x * rv.x + rv.y * rv.y;
         }
-        cta_partial<1>(v, partials, vs, rg);
+        slab_partial<1>(v, sums, vs);
     }
-    grid_finish<1>(partials, ticket, rr_out, rg);   // scal + S_RR, or this rank's partial block when the solve is distributed
+    grid_finish<1>(sums, partials, ticket, rr_out, rg);   // scal + S_RR, or this rank's partial block when the solve is distributed
 }
 
 // batched <Ar, Aps[slot]> for nh (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
@@ -216,8 +220,9 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(RedGeom rg,
 #pragma unroll
     for (int k = 0; k < NK; k++) hp[k] = Aps + (int64_t)hl.slot[k < cnt ? g + k * KS : 0] * stride;
     const int64_t T = (int64_t)rg.G * GT;
-    // CTA partials: value q = 2*kk + c of history vector kk = g + k*KS lives in the warps of group g
-    __shared__ double sm[RED_THREADS / 32][2 * NK];
+    // warp sums per virtual slab (no block barrier between slabs); value q = 2*kk + c of history vector kk = g + k*KS lives in
+    // the warps of group g
+    __shared__ double sm[RED_VSLABS][RED_THREADS / 32][2 * NK];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nv = 2 * nh;
@@ -240,21 +245,21 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(RedGeom rg,
 #pragma unroll
             for (int k = 0; k < NK; k++) v[2 * k + 1] = -v[2 * k + 1];
         }
-        __syncthreads();                              // the previous slab's sums have been read out of sm
 #pragma unroll
         for (int k = 0; k < 2 * NK; k++) {
             double s = warp_sum(v[k]);
-            if (lane == 0) sm[warp][k] = s;
+            if (lane == 0) sm[vs][warp][k] = s;
         }
-        __syncthreads();
-        if ((int)threadIdx.x < nv) {
-            const int kk = threadIdx.x >> 1, c = threadIdx.x & 1;
-            const int gg = kk % KS, k = kk / KS;
-            double s = 0.;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < rg.nvs * nv; t += RED_THREADS) {
+        const int vs = t / nv, q = t - vs * nv;
+        const int kk = q >> 1, c = q & 1;
+        const int gg = kk % KS, k = kk / KS;
+        double s = 0.;
 #pragma unroll
-            for (int w = 0; w < GW; w++) s += sm[gg * GW + w][2 * k + c];
-            partials[(size_t)(vs * rg.G + blockIdx.x) * MAX_RED_VALUES + threadIdx.x] = s;
-        }
+        for (int w = 0; w < GW; w++) s += sm[vs][gg * GW + w][2 * k + c];
+        partials[(size_t)(vs * rg.G + blockIdx.x) * MAX_RED_VALUES + q] = s;
     }
     __threadfence();
     __syncthreads();
@@ -309,6 +314,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
                                                                      double* out /* 2*NH */, double* partials, unsigned int* ticket,
                                                                      const double* guard, double tol2) {
     PDL_ENTRY();
+    __shared__ SlabSums<2 * NH> sums;
     if (gcr_converged(guard, tol2)) return;
     extern __shared__ __align__(128) unsigned char dot_smem[];
     __shared__ __align__(8) uint64_t full[DOT_TMA_MAX_STAGES];
@@ -366,14 +372,14 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
 #pragma unroll
                 for (int k = 0; k < NH; k++) v[2 * k + 1] = -v[2 * k + 1];
             }
-            cta_partial<2 * NH>(v, partials, (int)vs, rg);
+            slab_partial<2 * NH>(v, sums, (int)vs);
 #pragma unroll
             for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
         }
     }
     if (tpc == 0)                                             // (more CTAs than tiles cannot happen: G <= tiles; kept for safety)
-        for (int vs = 0; vs < rg.nvs; vs++) cta_partial<2 * NH>(v, partials, vs, rg);
-    grid_finish<2 * NH>(partials, ticket, out, rg);
+        for (int vs = 0; vs < rg.nvs; vs++) slab_partial<2 * NH>(v, sums, vs);
+    grid_finish<2 * NH>(sums, partials, ticket, out, rg);
 }
 
 // p_new = z + sum_i(-beta_i ps[i]) ; Ap_new = Ar + sum_i(-beta_i Aps[i]) written into ring slot `cur`, with the next
@@ -392,6 +398,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
                                                                     double* anum_out, double* partials, unsigned int* ticket, const double* guard,
                                                                     double tol2) {
     PDL_ENTRY();
+    __shared__ SlabSums<3> sums;
     if (gcr_converged(guard, tol2)) return;
     constexpr int NHS = NH > 0 ? NH : 1;
     __shared__ c128 beta[NHS];
@@ -450,9 +457,9 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
         st_stream(Apout + i, Apc);
     }
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
-    if (last) cta_partial<3>(v, partials, vs, rg);
+    if (last) slab_partial<3>(v, sums, vs);
     }
-    if (last) grid_finish<3>(partials, ticket, anum_out, rg);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
+    if (last) grid_finish<3>(sums, partials, ticket, anum_out, rg);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
 }
 
 // out = a + sign * s * b with the complex scalar s in device memory (Gram-Schmidt updates: src/MG.h:116-118, 192-194)

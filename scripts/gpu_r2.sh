@@ -47,6 +47,24 @@ dist)
             > $O/${TAG}_bench_n${N}_${cfg//=/}.json 2> $O/${TAG}_bench_n${N}_${cfg//=/}.err; echo "== $cfg rc=$?"
         python scripts/bench_brief.py $O/${TAG}_bench_n${N}_${cfg//=/}.json 2>&1 | head -24
     done ;;
+q256)
+    # the 1/8-size problem (the per-GPU sizes of the 8-GPU run) on one GPU, virtual slabs on / off
+    : > $O/${TAG}_q256.txt
+    for cfg in "MGCR_RED_VSLABS=8" "MGCR_RED_VSLABS=1"; do
+        echo "== $cfg" >> $O/${TAG}_q256.txt
+        env $cfg timeout 200 python bench.py --workload mg3d_256 --operator stencil --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | tail -1 > $O/knob_tmp.json
+        python scripts/bench_brief.py $O/knob_tmp.json 2>/dev/null | head -13 >> $O/${TAG}_q256.txt
+    done
+    cat $O/${TAG}_q256.txt ;;
+small)
+    # persistent small-system solver: CTAs per SM x rows per CTA (the replicated coarse solves are 9 % of the 8-GPU solve)
+    : > $O/${TAG}_small_sweep.txt
+    for ps in 1 2 3; do for rows in 128 256 512 1024; do
+        echo "== per_sm=$ps rows_per_cta=$rows" >> $O/${TAG}_small_sweep.txt
+        MGCR_SMALL_GRID_PER_SM=$ps MGCR_SMALL_ROWS_PER_CTA=$rows timeout 200 python bench.py --workload mg3d_256 --operator stencil --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | tail -1 > $O/knob_tmp.json
+        python scripts/bench_brief.py $O/knob_tmp.json 2>/dev/null | grep -E "^N=|gcr_small|blockcsr" >> $O/${TAG}_small_sweep.txt
+    done; done
+    cat $O/${TAG}_small_sweep.txt ;;
 knobs)
     # same box: programmatic dependent launch and blind preconditioned solves on / off
     : > $O/${TAG}_knobs.txt
