@@ -294,8 +294,7 @@ int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline void launch_pdl(mgcr_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

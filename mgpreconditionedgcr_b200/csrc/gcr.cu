@@ -13,9 +13,9 @@ int vec_norm2_dev(mgcr_ctx* ctx, int64_t n, const c128* a, double* d_out, bool d
 int vec_normalise(mgcr_ctx* ctx, int64_t n, c128* a, bool dist, int64_t n_global = 0);
 
 int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, const c128* rhs, c128* x, double* hist,
-                 int hist_cap, int* iters_out);
+                 int hist_cap, int* iters_out, bool x_zero = false);
 int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const c128* rhs, c128* x, double* hist, int hist_cap,
-                    int* iters_out, int storage, int restart, int* handled);
+                    int* iters_out, int storage, int restart, int* handled, bool x_zero);
 
 struct GcrOp : mgcr_op {
     mgcr_op* A = nullptr;
@@ -109,9 +109,14 @@ static int acquire_slot(mgcr_ctx* ctx, int depth, SolveSlot* s) {
 static thread_local int g_depth = 0;
 struct DepthGuard { DepthGuard() { g_depth++; } ~DepthGuard() { g_depth--; } };
 
+// x_zero: the caller's start vector is zero and x need not hold it -- the first x += alpha p WRITES alpha p (0 + t = t exactly),
+// so neither a memset of x nor the first read of it happens (the multigrid cycle starts every smoother / coarse solve that way:
+// a 2.1 GB memset and a 2.1 GB read per level-0 cycle at 512^3)
 int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* right, const c128* rhs, c128* x, double* hist,
-              int hist_cap, int* iters_out) {
-    return gcr_solve_lr(ctx, A, prm, nullptr, right, rhs, x, hist, hist_cap, iters_out);
+              int hist_cap, int* iters_out, bool x_zero = false);
+int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* right, const c128* rhs, c128* x, double* hist,
+              int hist_cap, int* iters_out, bool x_zero) {
+    return gcr_solve_lr(ctx, A, prm, nullptr, right, rhs, x, hist, hist_cap, iters_out, x_zero);
 }
 
 // `left`: the reference's left preconditioner, replicated operation for operation (src/GCR.h:201-204, 245-247): r <- L(r) ONCE,
@@ -119,7 +124,7 @@ int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* rig
 // direction is therefore unpreconditioned and what the loop reduces (and prints) is L(rhs) - sum alpha Ap, not a residual of
 // the original system -- the reference's behaviour, kept because it is deterministic (SURVEY.md Appendix B, Q4 for the right side).
 int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, const c128* rhs, c128* x, double* hist,
-                 int hist_cap, int* iters_out) {
+                 int hist_cap, int* iters_out, bool x_zero) {
     const int64_t n = A->n_local;
     ARG_CHECK(prm->truncation == 0 || prm->restart == 0, "Do not support concurrent restarting and truncation. (src/GCR.h:165)");
     ARG_CHECK(prm->truncation >= 0 && prm->restart >= 0 && prm->max_iter >= 0, "GCR: negative parameter");
@@ -134,7 +139,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     const bool dist = A->distributed;   // vectors are row slabs: partial inner products are all-reduced (NCCL)
     if (!right && !left) {   // small operators: the whole solve as one persistent cooperative kernel (gcr_small.cu)
         int handled = 0;
-        MGCR_TRY(gcr_solve_small(ctx, A, prm, rhs, x, hist, hist_cap, iters_out, storage, restart, &handled));
+        MGCR_TRY(gcr_solve_small(ctx, A, prm, rhs, x, hist, hist_cap, iters_out, storage, restart, &handled, x_zero && rhs != x));
         if (handled) return MGCR_OK;
     }
     DepthGuard dg;
@@ -243,8 +248,8 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     do {
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
-        KLAUNCH(ctx, "gcr_update_xr", 96. * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
-                                                                 scal, red + S_RR, bden_off + cur, ctx->d_partials, ctx->d_ticket, guard, tol2)));
+        KLAUNCH(ctx, "gcr_update_xr", ((x_zero && !aliased && g == 1) ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
+                                                                 scal, red + S_RR, bden_off + cur, (x_zero && !aliased && g == 1) ? 1 : 0, ctx->d_partials, ctx->d_ticket, guard, tol2)));
         GCUDA(cudaGetLastError());
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
             KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, rg, (const c128*)x, ctx->d_partials, ctx->d_ticket, red + S_BB)));
@@ -355,7 +360,7 @@ int vec_init_rand_slab(mgcr_ctx* ctx, int seed, int64_t skip, int64_t n, c128* d
 int GcrOp::apply(const c128* x, c128* y) {
     ARG_CHECK(x != y, "operator apply: input and output alias");
     if (prm.zero_guess) {
-        CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(c128) * n_local, ctx->stream));
+        // (no memset: the solve is told that its start vector is zero)
     } else {
         if (!d_rand2) {
             MGCR_TRY(dev_alloc_t(ctx, (size_t)n_local, &d_rand2));
@@ -371,7 +376,7 @@ int GcrOp::apply(const c128* x, c128* y) {
     }
     mgcr_gcr_param p = prm;
     p.verbose = prm.verbose;
-    return gcr_solve_lr(ctx, A, &p, left, right, x, y, nullptr, 0, nullptr);
+    return gcr_solve_lr(ctx, A, &p, left, right, x, y, nullptr, 0, nullptr, prm.zero_guess != 0);
 }
 
 extern "C" int mgcr_gcr_op_create(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* left, mgcr_op* right, mgcr_op** out) {

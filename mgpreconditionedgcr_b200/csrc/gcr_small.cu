@@ -35,6 +35,7 @@ struct SmallGcrArgs {
     double* out;                 // [0] iterations, [1] ||r||^2, [2] ||rhs||^2
     double* hist;                // optional device array of hist_cap doubles
     int hist_cap;
+    int x_zero;                  // the start vector is zero and x does not hold it: the first update writes x
 };
 
 // CTA partial of NV running sums -> partials[buf][block][k]
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_gcr_small(Rows M, SmallGcrArgs a
             const c128* Ap = a.Aps + (int64_t)cur * n;
             double v[1] = {0.};
             for (int64_t i = t0; i < n; i += T) {
-                c128 xv = cadd(a.x[i], cmul(alpha, p[i]));
+                c128 xv = cadd((a.x_zero && g == 1) ? cmake(0., 0.) : a.x[i], cmul(alpha, p[i]));
                 c128 rv = csub(a.r[i], cmul(alpha, Ap[i]));
                 a.x[i] = xv; a.r[i] = rv;
                 v[0] += rv.x * rv.x + rv.y * rv.y;
@@ -226,7 +227,7 @@ static int launch_small(mgcr_ctx* ctx, const Rows& rows, SmallGcrArgs& a, int* g
 // Returns MGCR_OK and sets *handled = 1 when the solve was enqueued as one persistent kernel; *handled = 0 when the
 // caller must run the host-driven loop (operator has no row access, solve too large, history too long, verbose...).
 int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const c128* rhs, c128* x, double* hist, int hist_cap,
-                    int* iters_out, int storage, int restart, int* handled) {
+                    int* iters_out, int storage, int restart, int* handled, bool x_zero) {
     *handled = 0;
     const int64_t n = A->n_local;
     if (n == 0 || n > ctx->small_gcr_rows || storage > SG_MAXH || prm->verbose || rhs == x || A->distributed) return MGCR_OK;
@@ -238,7 +239,7 @@ int gcr_solve_small(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, const 
         SmallGcrArgs a;
         a.n = n; a.storage = storage; a.restart = restart; a.max_iter = prm->max_iter; a.std_conj = prm->std_conj;
         a.tol2 = prm->tol * prm->tol;
-        a.rhs = rhs; a.x = x;
+        a.rhs = rhs; a.x = x; a.x_zero = x_zero ? 1 : 0;
         int grid = 1;
         MGCR_TRY(launch_small(ctx, rows, a, &grid));
         MGCR_TRY(dev_alloc_t(ctx, (size_t)n * (2 + 2 * (size_t)storage), &work));

@@ -131,11 +131,17 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, con
 
 // x += alpha p ; r -= alpha Ap ; ||r||^2 -> scal[S_RR]      (GCR.h:230-233)
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg, const c128* __restrict__ p, const c128* __restrict__ Ap,
-                                                               c128* x, c128* r, double* scal, double* rr_out, int bden_slot, double* partials,
-                                                               unsigned int* ticket, const double* guard, double tol2) {
+                                                               c128* x, c128* r, double* scal, double* rr_out, int bden_slot, int x_zero,
+                                                               double* partials, unsigned int* ticket, const double* guard, double tol2) {
     PDL_ENTRY();
     __shared__ SlabSums<1> sums;
-    if (gcr_converged(guard, tol2)) return;
+    if (gcr_converged(guard, tol2)) {
+        // x_zero: x has never been written (the caller skipped the memset).  A solve that counts as converged before its first
+        // iteration (a zero right-hand side) must still return the zero vector
+        if (x_zero)
+            for (int vs = 0; vs < rg.nvs; vs++) SLAB_STRIDE(i, rg, vs) st_stream(x + i, cmake(0., 0.));
+        return;
+    }
     const double aden = scal[S_ADEN];
     const c128 alpha = cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
     // ||Aps[cur]||^2 never changes while the slot lives: cache it for the beta denominators (GCR.h:258 recomputes it)
@@ -148,7 +154,9 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg
         int64_t i = (int64_t)vs * rg.L + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         for (; i + T < n; i += 2 * T) {
             const c128 p0 = ld_stream(p + i), a0 = ld_stream(Ap + i), p1 = ld_stream(p + i + T), a1 = ld_stream(Ap + i + T);
-            c128 x0 = ld_plain(x + i), r0 = ld_plain(r + i), x1 = ld_plain(x + i + T), r1 = ld_plain(r + i + T);
+            c128 x0 = cmake(0., 0.), x1 = cmake(0., 0.);
+            if (!x_zero) { x0 = ld_plain(x + i); x1 = ld_plain(x + i + T); }
+            c128 r0 = ld_plain(r + i), r1 = ld_plain(r + i + T);
             x0 = cadd(x0, cmul(alpha, p0)); r0 = csub(r0, cmul(alpha, a0));
             x1 = cadd(x1, cmul(alpha, p1)); r1 = csub(r1, cmul(alpha, a1));
             st_stream(x + i, x0); st_stream(r + i, r0); st_stream(x + i + T, x1); st_stream(r + i + T, r1);
@@ -157,7 +165,7 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg
         }
         for (; i < n; i += T) {
             c128 pv = ld_stream(p + i), av = ld_stream(Ap + i);
-            c128 xv = ld_plain(x + i), rv = ld_plain(r + i);
+            c128 xv = x_zero ? cmake(0., 0.) : ld_plain(x + i), rv = ld_plain(r + i);
             xv = cadd(xv, cmul(alpha, pv));
             rv = csub(rv, cmul(alpha, av));
             st_stream(x + i, xv);
@@ -331,25 +339,28 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int64_t item, int s) {                   // thread 0 only
-        const int64_t vs = item / tpc, tile = blockIdx.x + (item - vs * tpc) * rg.G;
-        const int64_t e0 = vs * rg.L + tile * te;
-        const uint32_t cnt = (uint32_t)min((int64_t)te, (vs + 1) * rg.L - e0);
+    // (slab, tile-of-slab) of a work item advance by counting: no 64-bit divisions in the loop
+    int64_t iss_vs = 0, iss_t = 0;                            // next item to issue (thread 0)
+    auto issue = [&](int s) {                                 // thread 0 only
+        const int64_t tile = blockIdx.x + iss_t * rg.G;
+        const int64_t e0 = iss_vs * rg.L + tile * te;
+        const uint32_t cnt = (uint32_t)min((int64_t)te, (iss_vs + 1) * rg.L - e0);
         c128* dst = ring + (size_t)s * stage_elems;
         mbar_expect_tx(&full[s], cnt * 16u * (1 + NH));
         tma_load_1d(dst, Ar + e0, cnt * 16u, &full[s]);
 #pragma unroll
         for (int k = 0; k < NH; k++) tma_load_1d(dst + (size_t)(1 + k) * te, Aps + (int64_t)hl.slot[k] * stride + e0, cnt * 16u, &full[s]);
+        if (++iss_t == tpc) { iss_t = 0; iss_vs++; }
     };
     if (threadIdx.x == 0)
         for (int s = 0; s < stages; s++)
-            if (s < items) issue(s, s);
+            if (s < items) issue(s);
     double v[2 * NH];
 #pragma unroll
     for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
     int s = 0; uint32_t parity = 0;
+    int vs = 0; int64_t t = 0;
     for (int64_t item = 0; item < items; item++) {
-        const int64_t vs = item / tpc, t = item - vs * tpc;
         mbar_wait(&full[s], parity);
         const c128* st = ring + (size_t)s * stage_elems;
         const int64_t left = rg.L - (blockIdx.x + t * rg.G) * te;
@@ -365,16 +376,17 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
             }
         }
         __syncthreads();                                      // every thread is done with stage s
-        if (threadIdx.x == 0 && item + stages < items) issue(item + stages, s);
+        if (threadIdx.x == 0 && item + stages < items) issue(s);
         if (++s == stages) { s = 0; parity ^= 1; }
-        if (t == tpc - 1) {                                   // this CTA's last tile of slab vs: its partial, fresh accumulators
+        if (++t == tpc) {                                     // this CTA's last tile of slab vs: its warp sums, fresh accumulators
             if (std_conj) {
 #pragma unroll
                 for (int k = 0; k < NH; k++) v[2 * k + 1] = -v[2 * k + 1];
             }
-            slab_partial<2 * NH>(v, sums, (int)vs);
+            slab_partial<2 * NH>(v, sums, vs);
 #pragma unroll
             for (int k = 0; k < 2 * NH; k++) v[k] = 0.;
+            t = 0; vs++;
         }
     }
     if (tpc == 0)                                             // (more CTAs than tiles cannot happen: G <= tiles; kept for safety)

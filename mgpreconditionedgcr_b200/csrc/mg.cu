@@ -489,16 +489,15 @@ struct MgOp : mgcr_op {
 static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x) {
     mgcr_ctx* ctx = mg->ctx;
     MgLevel& L = mg->lv[l];
-    const int64_t n = L.n, nc = L.nc;
+    const int64_t nc = L.nc;
+    (void)nc;
     ARG_CHECK(b != x, "MG cycle: input and output alias");
-    CUDA_TRY(cudaMemsetAsync(x, 0, sizeof(c128) * n, ctx->stream));
-    MGCR_TRY(gcr_solve(ctx, L.A, &mg->smooth, nullptr, b, x, nullptr, 0, nullptr));
+    MGCR_TRY(gcr_solve(ctx, L.A, &mg->smooth, nullptr, b, x, nullptr, 0, nullptr, true));      // x = S b from a zero start: x is written, never read
     MGCR_TRY(L.A->apply_residual(x, b, L.d_r));                            // r = b - A x, one kernel
     MGCR_TRY(mg_restrict(ctx, L, L.d_r, L.d_rc));
     const c128* xc = L.d_xc;
     if (!L.gather) {
-        CUDA_TRY(cudaMemsetAsync(L.d_xc, 0, sizeof(c128) * nc, ctx->stream));
-        MGCR_TRY(gcr_solve(ctx, L.Ac, &mg->coarse, L.deeper, L.d_rc, L.d_xc, nullptr, 0, nullptr));
+        MGCR_TRY(gcr_solve(ctx, L.Ac, &mg->coarse, L.deeper, L.d_rc, L.d_xc, nullptr, 0, nullptr, true));
     } else {
         // coarse-level gather: every rank assembles the whole coarse right-hand side, solves the
         // replicated coarse system (identical arithmetic on every GPU, no further communication) and keeps its slice
@@ -516,8 +515,7 @@ static int mg_cycle(mgcr_mg* mg, int l, const c128* b, c128* x) {
                 off += L.nc_counts[r];
             }
         }
-        CUDA_TRY(cudaMemsetAsync(L.d_xc_full, 0, sizeof(c128) * L.nc_global, ctx->stream));
-        MGCR_TRY(gcr_solve(ctx, L.Ac_full, &mg->coarse, L.deeper, L.d_rc_full, L.d_xc_full, nullptr, 0, nullptr));
+        MGCR_TRY(gcr_solve(ctx, L.Ac_full, &mg->coarse, L.deeper, L.d_rc_full, L.d_xc_full, nullptr, 0, nullptr, true));
         xc = L.d_xc_full + L.nc_offset;
     }
     MGCR_TRY(mg_prolong(ctx, L, xc, x, true));                             // x += P xc, one kernel

@@ -63,7 +63,7 @@ struct SetupStage {
 };
 
 int gcr_solve(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* right, const c128* rhs, c128* x, double* hist,
-              int hist_cap, int* iters_out);
+              int hist_cap, int* iters_out, bool x_zero = false);
 int arnoldi(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* ep, int n_vec, c128* vecs);
 int blocking_device(mgcr_ctx* ctx, const int64_t sd[4], const int64_t sub[4], int64_t bd[4], int64_t* d_block_map,
                     int32_t* d_site_block, int32_t* d_site_off);
