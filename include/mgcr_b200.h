@@ -16,7 +16,9 @@
  *   - all work is enqueued on the context's stream; functions that return host-visible numbers synchronise that
  *     stream, the others are asynchronous.  One context = one GPU = one host thread.
  *   - multi-GPU: one process (context) per GPU.  After mgcr_ctx_init_dist every vector is the caller's LOCAL row
- *     slab, inner products are all-reduced (NCCL) and operator applies exchange halos (NCCL send/recv).
+ *     slab; inner products are all-reduced and operator applies exchange halos with hand-written kernels over NVLink
+ *     peer memory (CUDA IPC; csrc/p2p.cu), NCCL being the bootstrap, the set-up transport and the fallback (MGCR_P2P=0).
+ *     Reductions have a GPU-count-independent shape: 1, 2, 4 and 8 GPUs produce identical bits (csrc/common.cuh, RedGeom).
  *   - there is NO CPU fallback: with no usable CUDA device every call fails with MGCR_ERR_CUDA.
  */
 #ifndef MGCR_B200_H
@@ -99,11 +101,15 @@ int mgcr_vec_set_constant(mgcr_ctx* ctx, int64_t n, double re, double im, mgcr_c
 int mgcr_vec_axpy(mgcr_ctx* ctx, int64_t n, double s_re, double s_im, const mgcr_c128* d_b, const mgcr_c128* d_a, mgcr_c128* d_out);
 /* out = s * a  (Field operator*(complex): Fields.h:245-253; product formed as s * field[i]) */
 int mgcr_vec_scale(mgcr_ctx* ctx, int64_t n, double s_re, double s_im, const mgcr_c128* d_a, mgcr_c128* d_out);
-/* sum_i conj(a_i) b_i (Fields.h:216-226), all-reduced over ranks */
+/* sum_i conj(a_i) b_i (Fields.h:216-226).  In a distributed context the vectors are this rank's ROW SLABS: the result is
+ * all-reduced over the ranks and the call is COLLECTIVE (every rank must make it). */
 int mgcr_vec_dot(mgcr_ctx* ctx, int64_t n, const mgcr_c128* d_a, const mgcr_c128* d_b, double h_out[2]);
-/* sum_i |a_i|^2 (Fields.h:228-235), all-reduced over ranks */
+/* sum_i |a_i|^2 (Fields.h:228-235); row slabs, all-reduced, collective like mgcr_vec_dot */
 int mgcr_vec_squarednorm(mgcr_ctx* ctx, int64_t n, const mgcr_c128* d_a, double* h_out);
-/* a *= 1/||a|| (Fields.h:237-243) */
+/* the same for vectors that are NOT row slabs (replicated coarse-level fields, a rank's own scratch): no all-reduce, not collective */
+int mgcr_vec_dot_local(mgcr_ctx* ctx, int64_t n, const mgcr_c128* d_a, const mgcr_c128* d_b, double h_out[2]);
+int mgcr_vec_squarednorm_local(mgcr_ctx* ctx, int64_t n, const mgcr_c128* d_a, double* h_out);
+/* a *= 1/||a|| (Fields.h:237-243); row slabs, collective like mgcr_vec_dot */
 int mgcr_vec_normalise(mgcr_ctx* ctx, int64_t n, mgcr_c128* d_a);
 /* permutation 0<->2, 1<->3 along `axis` of a row-major ndim mesh (Fields.h:310-339) */
 int mgcr_vec_gamma5(mgcr_ctx* ctx, int ndim, const int64_t* h_dims, int axis, const mgcr_c128* d_in, mgcr_c128* d_out);

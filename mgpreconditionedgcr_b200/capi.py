@@ -70,6 +70,8 @@ SIGNATURES = {
     "mgcr_vec_scale": [_vp, _i64, _dbl, _dbl, _vp, _vp],
     "mgcr_vec_dot": [_vp, _i64, _vp, _vp, _pdbl],
     "mgcr_vec_squarednorm": [_vp, _i64, _vp, _pdbl],
+    "mgcr_vec_dot_local": [_vp, _i64, _vp, _vp, _pdbl],
+    "mgcr_vec_squarednorm_local": [_vp, _i64, _vp, _pdbl],
     "mgcr_vec_normalise": [_vp, _i64, _vp],
     "mgcr_vec_gamma5": [_vp, _int, _pi64, _int, _vp, _vp],
     "mgcr_vec_init_rand": [_vp, _int, _i64, _vp],

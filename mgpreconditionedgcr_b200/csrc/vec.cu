@@ -119,6 +119,18 @@ extern "C" int mgcr_vec_dot(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, const 
     return read_scalars(ctx, ctx->d_scratch, 2, out);
 }
 
+// the same on vectors that are NOT row slabs (replicated coarse-level fields, per-rank scratch): no all-reduce, not collective
+extern "C" int mgcr_vec_dot_local(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, const mgcr_c128* b, double out[2]) {
+    ARG_CHECK(ctx && out && (n == 0 || (a && b)), "mgcr_vec_dot_local: NULL buffer");
+    MGCR_TRY(vec_dot_dev(ctx, n, (const c128*)a, (const c128*)b, ctx->d_scratch, false, n));
+    return read_scalars(ctx, ctx->d_scratch, 2, out);
+}
+extern "C" int mgcr_vec_squarednorm_local(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, double* out) {
+    ARG_CHECK(ctx && out && (n == 0 || a), "mgcr_vec_squarednorm_local: NULL buffer");
+    MGCR_TRY(vec_norm2_dev(ctx, n, (const c128*)a, ctx->d_scratch, false, n));
+    return read_scalars(ctx, ctx->d_scratch, 1, out);
+}
+
 extern "C" int mgcr_vec_squarednorm(mgcr_ctx* ctx, int64_t n, const mgcr_c128* a, double* out) {
     ARG_CHECK(ctx && out && (n == 0 || a), "mgcr_vec_squarednorm: NULL buffer");
     MGCR_TRY(vec_norm2_dev(ctx, n, (const c128*)a, ctx->d_scratch, ctx->nranks > 1, global_len(ctx, n)));
