@@ -228,8 +228,18 @@ static __global__ void __launch_bounds__(256) k_p2p_halo(const c128* __restrict_
                                                          uint32_t seq, unsigned int* ticket, const uint32_t* my_flag_lo, const uint32_t* my_flag_hi) {
     PDL_ENTRY();
     __shared__ bool is_last;
+    // four elements per thread and direction in flight (posted 16-byte stores over NVLink): with 64 CTAs of one store per thread
+    // the 4.2 MB plane of the 512^3 lattice left at ~130 GB/s (22 us per exchange at every GPU count, profiles/r02_bench_*_n{2,4,8}.json)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        c128 a0, a1, a2, a3, b0, b1, b2, b3;
+        if (dst_lo) { a0 = ld_stream(src_lo + i); a1 = ld_stream(src_lo + i + stride); a2 = ld_stream(src_lo + i + 2 * stride); a3 = ld_stream(src_lo + i + 3 * stride); }
+        if (dst_hi) { b0 = ld_stream(src_hi + i); b1 = ld_stream(src_hi + i + stride); b2 = ld_stream(src_hi + i + 2 * stride); b3 = ld_stream(src_hi + i + 3 * stride); }
+        if (dst_lo) { dst_lo[i] = a0; dst_lo[i + stride] = a1; dst_lo[i + 2 * stride] = a2; dst_lo[i + 3 * stride] = a3; }
+        if (dst_hi) { dst_hi[i] = b0; dst_hi[i + stride] = b1; dst_hi[i + 2 * stride] = b2; dst_hi[i + 3 * stride] = b3; }
+    }
+    for (; i < n; i += stride) {
         if (dst_lo) dst_lo[i] = ld_stream(src_lo + i);
         if (dst_hi) dst_hi[i] = ld_stream(src_hi + i);
     }
@@ -306,7 +316,7 @@ int p2p_halo_exchange(mgcr_ctx* ctx, PeerHalo* h, const c128* send_lo, const c12
     const uint32_t* my_hi = has_hi ? (const uint32_t*)(s->heap + h->flag_off + 128) : nullptr;
     h->wait_lo = defer ? my_lo : nullptr; h->wait_hi = defer ? my_hi : nullptr;
     if (defer) { my_lo = nullptr; my_hi = nullptr; }
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(64, (h->n + 255) / 256));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 2, (h->n + 1023) / 1024));
     KLAUNCH(ctx, "p2p_halo", 32. * h->n * ((has_lo ? 1 : 0) + (has_hi ? 1 : 0)),
             (launch_pdl(ctx, k_p2p_halo, grid, 256, 0, send_lo, dst_lo, flag_at_lo, send_hi, dst_hi, flag_at_hi, h->n, h->seq, s->d_ticket, my_lo, my_hi)));
     CHECK_LAUNCH();
