@@ -32,12 +32,12 @@ static int env_int(const char* name, int dflt) { const char* e = getenv(name); r
 
 template <int NK, int KS>
 static void launch_dot_hist(mgcr_ctx* ctx, const RedGeom& rg, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int nh,
-                            int std_conj, double* out, const double* guard, double tol2) {
-    launch_pdl(ctx, k_gcr_dot_hist<NK, KS>, rg.G, RED_THREADS, 0, rg, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2);
+                            int std_conj, double* out, const double* guard, double tol2, const ArPush& push) {
+    launch_pdl(ctx, k_gcr_dot_hist<NK, KS>, rg.G, RED_THREADS, 0, rg, Ar, Aps, stride, hl, nh, std_conj, out, ctx->d_partials, ctx->d_ticket, guard, tol2, push);
 }
 template <int NH>
 static int launch_dot_hist_tma(mgcr_ctx* ctx, const RedGeom& rg0, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl, int std_conj,
-                               double* out, const double* guard, double tol2) {
+                               double* out, const double* guard, double tol2, const ArPush& push) {
     MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_gcr_dot_hist_tma<NH>, 200 * 1024));
     // tile = 256*ept elements of each of the 1+NH vectors; ring of `stages` tiles in ~150 KB (measured: scripts/kbench_dot5.cu)
     const int ept = NH <= 3 ? 4 : NH <= 7 ? 2 : 1;
@@ -48,22 +48,22 @@ static int launch_dot_hist_tma(mgcr_ctx* ctx, const RedGeom& rg0, const c128* Ar
     const int64_t tiles = (rg.L + (int64_t)RED_THREADS * ept - 1) / ((int64_t)RED_THREADS * ept);
     rg.G = (int)std::min<int64_t>(148, tiles);
     launch_pdl(ctx, k_gcr_dot_hist_tma<NH>, rg.G, RED_THREADS, stages * stage_bytes, rg, Ar, Aps, stride, hl, std_conj, ept, stages, out,
-               ctx->d_partials, ctx->d_ticket, guard, tol2);
+               ctx->d_partials, ctx->d_ticket, guard, tol2, push);
     return MGCR_OK;
 }
 
 // history length -> kernel.  Short histories (and short vectors): register-staged kernel, KS thread groups per CTA with
 // <= NK vectors each; nh >= 3 on long vectors: TMA-staged ring (measured on B200, profiles/r01_kbench_dot.txt).
 static int dot_hist(mgcr_ctx* ctx, int nh, const RedGeom& rg, int64_t n_global, const c128* Ar, const c128* Aps, int64_t stride, const HistList& hl,
-                    int std_conj, double* out, const double* guard, double tol2) {
+                    int std_conj, double* out, const double* guard, double tol2, const ArPush& push) {
     if (ctx->dot_tma && nh >= 3 && n_global >= ((int64_t)1 << 23) && rg.L >= ((int64_t)1 << 17)) {   // (the GLOBAL length decides: the same kernel at every GPU count)
         switch (nh) {
-#define C(NH) case NH: return launch_dot_hist_tma<NH>(ctx, rg, Ar, Aps, stride, hl, std_conj, out, guard, tol2);
+#define C(NH) case NH: return launch_dot_hist_tma<NH>(ctx, rg, Ar, Aps, stride, hl, std_conj, out, guard, tol2, push);
             C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
 #undef C
         }
     }
-#define GO(NK, KS) launch_dot_hist<NK, KS>(ctx, rg, Ar, Aps, stride, hl, nh, std_conj, out, guard, tol2)
+#define GO(NK, KS) launch_dot_hist<NK, KS>(ctx, rg, Ar, Aps, stride, hl, nh, std_conj, out, guard, tol2, push)
     if (nh <= 3) GO(3, 1);
     else if (nh <= 8) GO(4, 2);
     else GO(4, 4);
@@ -74,16 +74,16 @@ static int dot_hist(mgcr_ctx* ctx, int nh, const RedGeom& rg, int64_t n_global, 
 template <int NH, int MINB>
 static void launch_update_p(mgcr_ctx* ctx, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                             int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
-                            int bden_off, double* scal, double* red_anum, const double* guard, double tol2) {
+                            int bden_off, double* scal, double* red_anum, const double* guard, double tol2, const ArWait& aw, const ArPush& push) {
     launch_pdl(ctx, k_gcr_update_p<NH, MINB>, rg.G, RED_THREADS, 0, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
-               bden_off, (const double*)scal, red_anum, ctx->d_partials, ctx->d_ticket, guard, tol2);
+               bden_off, (const double*)scal, red_anum, ctx->d_partials, ctx->d_ticket, guard, tol2, aw, push);
 }
 static void update_p(mgcr_ctx* ctx, int nh, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                      int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj, int bden_off,
-                     double* scal, double* red_anum, const double* guard, double tol2) {
+                     double* scal, double* red_anum, const double* guard, double tol2, const ArWait& aw, const ArPush& push) {
     static const int minb_env = env_int("MGCR_UPD_MINB", 0);   // experiment knob
     const int minb = minb_env ? minb_env : 4;
-#define ARGS ctx, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red_anum, guard, tol2
+#define ARGS ctx, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red_anum, guard, tol2, aw, push
 #define C(NH) case NH: if (minb >= 4) launch_update_p<NH, 4>(ARGS); else if (minb == 3) launch_update_p<NH, 3>(ARGS); else launch_update_p<NH, 2>(ARGS); break;
     switch (nh) {
         C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
@@ -208,15 +208,6 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     // kernel in the pass that forms the first inner products
     if (right) GTRY(right->apply(rhs, ps));
     GTRY(A->apply(right ? ps : rhs, Aps));
-    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red)));
-    GCUDA(cudaGetLastError());
-    if (left) {
-        // r <- L(r) (GCR.h:201-204): the first alpha and the step-0 print use the preconditioned r with the UNpreconditioned Ap
-        GTRY(left->apply(rhs, r));
-        GTRY(vec_dot_dev(ctx, n, std_conj ? Aps : r, std_conj ? r : Aps, red + S_ANUM, false, dist ? A->n_global : n));   // <r,Ap> (or <Ap,r>), local part
-        GTRY(vec_norm2_dev(ctx, n, r, red + S_RR, false, dist ? A->n_global : n));
-    }
-    if (dist) GTRY(dist_allreduce_sum2(ctx, red, scal, 5));
     // Short solves nobody watches (the smoothers of the multigrid cycle): no read-back at all, the kernels carry the
     // stopping test themselves (gcr_converged) and the host enqueues max_iter iterations back to back.
     // A right preconditioner does not change that: its applies run whether or not the solve has converged (wasted work in the
@@ -224,6 +215,23 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     // were 235 of the 260 host synchronisations of a 512^3 solve in round 1).
     static const int blind_precond = env_int("MGCR_BLIND_PRECOND", 1);   // experiment knob: 0 = round-1 behaviour
     const bool blind = !hist && !iters_out && !prm->verbose && !aliased && !left && prm->max_iter <= 4 && (!right || blind_precond);
+    // Distributed blind solves over peer memory: every all-reduce travels inside the kernel that produces the sums (its last CTA
+    // posts them to all ranks) and the kernel that needs them (every CTA collects them), common.cuh ArPush / ArWait.  `pushA` /
+    // `waitA` carry <r,Ap>, <Ap,Ap> (+ the two norms at the start), `pushB` / `waitB` ||r||^2 with the history inner products.
+    const bool fold = blind && dist && p2p_enabled(ctx);
+    ArPush pushA, pushB;
+    ArWait waitA, waitB;
+    memset(&pushA, 0, sizeof pushA); memset(&pushB, 0, sizeof pushB); memset(&waitA, 0, sizeof waitA); memset(&waitB, 0, sizeof waitB);
+    if (fold) (void)p2p_allreduce_fold(ctx, 5, red, scal, &pushA, &waitA);   // (refused: the descriptors stay off, stand-alone all-reduce below)
+    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red, pushA)));
+    GCUDA(cudaGetLastError());
+    if (left) {
+        // r <- L(r) (GCR.h:201-204): the first alpha and the step-0 print use the preconditioned r with the UNpreconditioned Ap
+        GTRY(left->apply(rhs, r));
+        GTRY(vec_dot_dev(ctx, n, std_conj ? Aps : r, std_conj ? r : Aps, red + S_ANUM, false, dist ? A->n_global : n));   // <r,Ap> (or <Ap,r>), local part
+        GTRY(vec_norm2_dev(ctx, n, r, red + S_RR, false, dist ? A->n_global : n));
+    }
+    if (dist && !pushA.seq) GTRY(dist_allreduce_sum2(ctx, red, scal, 5));
     const double* guard = blind ? scal : nullptr;
     const double tol2 = prm->tol * prm->tol;
     double bb = 1., rr = 1.;
@@ -249,7 +257,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
         KLAUNCH(ctx, "gcr_update_xr", ((x_zero && !aliased && g == 1) ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
-                                                                 scal, red + S_RR, bden_off + cur, (x_zero && !aliased && g == 1) ? 1 : 0, ctx->d_partials, ctx->d_ticket, guard, tol2)));
+                                                                 scal, red + S_RR, bden_off + cur, (x_zero && !aliased && g == 1) ? 1 : 0, ctx->d_partials, ctx->d_ticket, guard, tol2, waitA)));
         GCUDA(cudaGetLastError());
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
             KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, rg, (const c128*)x, ctx->d_partials, ctx->d_ticket, red + S_BB)));
@@ -264,6 +272,8 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
             GTRY(A->apply(zz, Ar));                                                               // GCR.h:242
             if (left) { GTRY(left->apply(Ar, Lt)); std::swap(Ar, Lt); }                           // GCR.h:245-247
             lim = std::min(storage, iter);                                                        // GCR.h:251
+            memset(&pushB, 0, sizeof pushB); memset(&waitB, 0, sizeof waitB);
+            if (fold && lim <= GCR_CHUNK) (void)p2p_allreduce_fold(ctx, 1 + 2 * lim, red + S_RR, scal + S_RR, &pushB, &waitB);
             for (int c0 = 0; c0 < lim; c0 += GCR_CHUNK) {                                         // GCR.h:257-258 numerators
                 HistList hl;
                 const int cnt = std::min((int)GCR_CHUNK, lim - c0);
@@ -271,12 +281,12 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
                 ProfScope ps_(ctx, "gcr_dot_hist", 16. * n * (1 + cnt));
                 // (distributed: the stopping test sees the GLOBAL ||r||^2 of the previous iteration here -- this iteration's is all-reduced
                 // together with the inner products below --, identical on every rank; the output is unused once the solve has converged)
-                GTRY(dot_hist(ctx, cnt, rg, dist ? A->n_global : n, Ar, Aps, stride, hl, std_conj, red + S_BNUM + 2 * c0, guard, tol2));
+                GTRY(dot_hist(ctx, cnt, rg, dist ? A->n_global : n, Ar, Aps, stride, hl, std_conj, red + S_BNUM + 2 * c0, guard, tol2, pushB));
             }
             GCUDA(cudaGetLastError());
         }
         // (the last pass of a solve nobody watches leaves nothing to reduce: x is final, ||r||^2 is not read)
-        if (dist && !(blind && final_iter)) GTRY(dist_allreduce_sum2(ctx, red + S_RR, scal + S_RR, 1 + 2 * lim));
+        if (dist && !(blind && final_iter) && !pushB.seq) GTRY(dist_allreduce_sum2(ctx, red + S_RR, scal + S_RR, 1 + 2 * lim));
         if (!blind) {
             GCUDA(cudaMemcpyAsync(slot.h, scal + S_BB, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             GCUDA(cudaEventRecord(slot.ev, ctx->stream));
@@ -287,16 +297,18 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
             int new_slot = next_iter % storage;
             GTRY(grow_ring(new_slot));
             int nchunks = std::max(1, (lim + GCR_CHUNK - 1) / GCR_CHUNK);
+            memset(&pushA, 0, sizeof pushA); memset(&waitA, 0, sizeof waitA);
+            if (fold && nchunks == 1) (void)p2p_allreduce_fold(ctx, 3, red + S_ANUM, scal + S_ANUM, &pushA, &waitA);
             for (int c = 0; c < nchunks; c++) {
                 BetaList bl;
                 const int cnt = std::max(0, std::min((int)GCR_CHUNK, lim - c * GCR_CHUNK));
                 for (int k = 0; k < GCR_CHUNK; k++) { bl.slot[k] = k < cnt ? c * GCR_CHUNK + k : 0; bl.num_index[k] = bl.slot[k]; }
                 int first = (c == 0), last = (c == nchunks - 1);
                 ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * cnt + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0)));
-                update_p(ctx, cnt, rg, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red + S_ANUM, guard, tol2);
+                update_p(ctx, cnt, rg, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red + S_ANUM, guard, tol2, waitB, pushA);
             }
             GCUDA(cudaGetLastError());
-            if (dist) GTRY(dist_allreduce_sum2(ctx, red + S_ANUM, scal + S_ANUM, 3));
+            if (dist && !pushA.seq) GTRY(dist_allreduce_sum2(ctx, red + S_ANUM, scal + S_ANUM, 3));
             iter = next_iter;
             cur = new_slot;
         }

@@ -108,7 +108,8 @@ __device__ __forceinline__ bool gcr_converged(const double* guard, double tol2) 
 // The same pass also makes the solver's working copies r = rhs and (without a preconditioner) p = r  (GCR.h:189-190).
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, const c128* __restrict__ r, const c128* __restrict__ Ap,
                                                           int std_conj, c128* __restrict__ r_out, c128* __restrict__ p_out,
-                                                          double* partials, unsigned int* ticket, double* out5) {
+                                                          double* partials, unsigned int* ticket, double* out5,
+                                                          const __grid_constant__ ArPush push) {
     PDL_ENTRY();
     __shared__ SlabSums<5> sums;
     for (int vs = 0; vs < rg.nvs; vs++) {
@@ -126,24 +127,36 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, con
         v[4] = v[3];
         slab_partial<5>(v, sums, vs);
     }
-    grid_finish<5>(sums, partials, ticket, out5, rg);
+    grid_finish<5>(sums, partials, ticket, out5, rg, 5, &push);
 }
 
 // x += alpha p ; r -= alpha Ap ; ||r||^2 -> scal[S_RR]      (GCR.h:230-233)
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_xr(RedGeom rg, const c128* __restrict__ p, const c128* __restrict__ Ap,
                                                                c128* x, c128* r, double* scal, double* rr_out, int bden_slot, int x_zero,
-                                                               double* partials, unsigned int* ticket, const double* guard, double tol2) {
+                                                               double* partials, unsigned int* ticket, const double* guard, double tol2,
+                                                               const __grid_constant__ ArWait aw) {
     PDL_ENTRY();
     __shared__ SlabSums<1> sums;
-    if (gcr_converged(guard, tol2)) {
+    __shared__ double arv[AR_FOLD_MAX];
+    // Folded all-reduce (aw.seq != 0, blind distributed solves): <r,Ap>, <Ap,Ap> (and, before the first iteration, ||rhs||^2 twice)
+    // arrive through the peer slots.  The stopping test on the scalars earlier kernels left decides FIRST whether anything was sent
+    // at all (a producer that saw the solve converged sent nothing); before the first iteration nothing has been left yet and the
+    // test runs on the arriving values instead.
+    const bool first_batch = aw.seq != 0 && aw.n == 5;
+    bool converged = !first_batch && gcr_converged(guard, tol2);
+    if (!converged && aw.seq != 0) {
+        ar_wait(aw, arv);                                     // -> scal[S_ANUM .. S_ADEN] (first batch: .. S_RR)
+        if (first_batch) converged = arv[S_RR] <= tol2 * arv[S_BB];
+    }
+    if (converged) {
         // x_zero: x has never been written (the caller skipped the memset).  A solve that counts as converged before its first
         // iteration (a zero right-hand side) must still return the zero vector
         if (x_zero)
             for (int vs = 0; vs < rg.nvs; vs++) SLAB_STRIDE(i, rg, vs) st_stream(x + i, cmake(0., 0.));
         return;
     }
-    const double aden = scal[S_ADEN];
-    const c128 alpha = cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
+    const double aden = aw.seq ? arv[S_ADEN] : scal[S_ADEN];
+    const c128 alpha = aw.seq ? cdivr(cmake(arv[S_ANUM], arv[S_ANUM + 1]), aden) : cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
     // ||Aps[cur]||^2 never changes while the slot lives: cache it for the beta denominators (GCR.h:258 recomputes it)
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[bden_slot] = aden;
     // two elements per trip: 8 independent 128-bit loads in flight per thread
@@ -217,7 +230,8 @@ __device__ __forceinline__ void dot_hist_group(int64_t n, int64_t i0, int64_t T,
 template <int NK, int KS>
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(RedGeom rg, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                               int64_t stride, HistList hl, int nh, int std_conj, double* out /* 2*nh */,
-                                                              double* partials, unsigned int* ticket, const double* guard, double tol2) {
+                                                              double* partials, unsigned int* ticket, const double* guard, double tol2,
+                                                              const __grid_constant__ ArPush push) {
     PDL_ENTRY();
     if (gcr_converged(guard, tol2)) return;
     constexpr int GT = RED_THREADS / KS;     // threads per group
@@ -283,6 +297,10 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_dot_hist(RedGeom rg,
         const double acc = combine_partials(partials, MAX_RED_VALUES, q, rg, lane);
         if (lane == 0) out[q] = acc;
     }
+    if (push.seq) {   // folded all-reduce of ||r||^2 (left by the x / r update) and these inner products
+        __syncthreads();
+        ar_push(push);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -320,7 +338,7 @@ template <int NH>
 static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedGeom rg, const c128* __restrict__ Ar, const c128* __restrict__ Aps,
                                                                      int64_t stride, HistList hl, int std_conj, int ept, int stages,
                                                                      double* out /* 2*NH */, double* partials, unsigned int* ticket,
-                                                                     const double* guard, double tol2) {
+                                                                     const double* guard, double tol2, const __grid_constant__ ArPush push) {
     PDL_ENTRY();
     __shared__ SlabSums<2 * NH> sums;
     if (gcr_converged(guard, tol2)) return;
@@ -391,7 +409,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
     }
     if (tpc == 0)                                             // (more CTAs than tiles cannot happen: G <= tiles; kept for safety)
         for (int vs = 0; vs < rg.nvs; vs++) slab_partial<2 * NH>(v, sums, vs);
-    grid_finish<2 * NH>(sums, partials, ticket, out, rg);
+    grid_finish<2 * NH>(sums, partials, ticket, out, rg, 2 * NH, &push);
 }
 
 // p_new = z + sum_i(-beta_i ps[i]) ; Ap_new = Ar + sum_i(-beta_i Aps[i]) written into ring slot `cur`, with the next
@@ -408,15 +426,23 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
                                                                     c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
                                                                     c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, const double* scal,
                                                                     double* anum_out, double* partials, unsigned int* ticket, const double* guard,
-                                                                    double tol2) {
+                                                                    double tol2, const __grid_constant__ ArWait aw, const __grid_constant__ ArPush push) {
     PDL_ENTRY();
     __shared__ SlabSums<3> sums;
-    if (gcr_converged(guard, tol2)) return;
+    __shared__ double arv[AR_FOLD_MAX];
+    if (gcr_converged(guard, tol2)) return;   // (folded: on the previous iteration's ||r||^2, as the inner-product kernel did -- it sent nothing)
     constexpr int NHS = NH > 0 ? NH : 1;
     __shared__ c128 beta[NHS];
+    if (aw.seq) {
+        // folded all-reduce: this iteration's ||r||^2 and the numerators <Ar, Aps[i]> arrive through the peer slots
+        // (-> scal[S_RR], scal[S_BNUM ..]); the stopping test of this iteration happens here, identically on every rank
+        ar_wait(aw, arv);
+        if (arv[0] <= tol2 * guard[S_BB]) return;
+    }
     if ((int)threadIdx.x < NH) {
         int q = bl.num_index[threadIdx.x];
-        beta[threadIdx.x] = cdivr(cmake(scal[S_BNUM + 2 * q], scal[S_BNUM + 2 * q + 1]), scal[bden_off + bl.slot[threadIdx.x]]);
+        const c128 num = aw.seq ? cmake(arv[S_BNUM - S_RR + 2 * q], arv[S_BNUM - S_RR + 2 * q + 1]) : cmake(scal[S_BNUM + 2 * q], scal[S_BNUM + 2 * q + 1]);
+        beta[threadIdx.x] = cdivr(num, scal[bden_off + bl.slot[threadIdx.x]]);
     }
     __syncthreads();
     c128* pout = last ? ps + (int64_t)cur * stride : acc_p;
@@ -471,7 +497,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
     if (last) slab_partial<3>(v, sums, vs);
     }
-    if (last) grid_finish<3>(sums, partials, ticket, anum_out, rg);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
+    if (last) grid_finish<3>(sums, partials, ticket, anum_out, rg, 3, &push);   // -> S_ANUM(2), S_ADEN (global block, or this rank's partial block)
 }
 
 // out = a + sign * s * b with the complex scalar s in device memory (Gram-Schmidt updates: src/MG.h:116-118, 192-194)

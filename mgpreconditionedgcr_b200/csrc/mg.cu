@@ -360,6 +360,61 @@ static __global__ void __launch_bounds__(256) k_restrict_warp(LevelGeom g, AggGe
     }
 }
 
+// The same kernel for ne = 4 with the eight warp reductions (4 vectors x re / im) folded into one halving butterfly: at the
+// xor-16 step a lane keeps four of its eight sums and hands the other four to its partner, at xor-8 two of four, at xor-4 one of
+// two, then two ordinary steps -- 9 double shuffles instead of 40.  Every value still goes through the tree xor 16, 8, 4, 2, 1 with
+// the same pairs (a + b and b + a are the same bits), so the results are those of k_restrict_warp bit for bit; lanes 0, 4, .., 28
+// end up holding value (lane >> 2) in the bit order 4, 2, 1 -> lane bits 4, 3, 2.  The reductions were a third of the warp's issue
+// slots: in the solve (SM clocks under the power cap) restrict ran 8 % below its standalone rate.
+template <int QPL>
+static __global__ void __launch_bounds__(256) k_restrict_warp4(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
+                                                               const c128* __restrict__ xf, c128* __restrict__ xc) {
+    PDL_ENTRY();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const int vidx = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+    int qo[QPL];
+#pragma unroll
+    for (int j = 0; j < QPL; j++) qo[j] = lane + 32 * j < g.bl ? __ldg(q_off + lane + 32 * j) : 0;
+    for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; b < g.nb; b += nwarps) {
+        const c128* xb = xf + agg_first_elem(ag, g.bl, b);
+        c128 xs[QPL];
+#pragma unroll
+        for (int j = 0; j < QPL; j++) xs[j] = lane + 32 * j < g.bl ? __ldg(xb + qo[j]) : cmake(0., 0.);
+        double v[8];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const c128* pv = P + (b * 4 + e) * g.bl;
+            double sr = 0., si = 0.;
+#pragma unroll
+            for (int j = 0; j < QPL; j++) {
+                const int64_t q = lane + 32 * j;
+                if (q < g.bl) {
+                    c128 t = cmulc(ld_stream(pv + q), xs[j]);
+                    sr += t.x; si += t.y;
+                }
+            }
+            v[2 * e] = sr; v[2 * e + 1] = si;
+        }
+        double w[4], u[2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double keep = b4 ? v[k + 4] : v[k], send = b4 ? v[k] : v[k + 4];
+            w[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double keep = b3 ? w[k + 2] : w[k], send = b3 ? w[k] : w[k + 2];
+            u[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        double t = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        if ((lane & 3) == 0) ((double*)(xc + b * 4))[vidx] = t;
+    }
+}
+
 // Tiny aggregates (up to G = 8 or 16 dofs, e.g. the 1x1x8 line aggregates of the anisotropic configuration): G lanes per
 // aggregate, 32/G aggregates per warp, so that no lane idles.  Lane q of the group holds dof q; the group's shuffle tree
 // (xor G/2 .. 1) is the tail of the full warp tree, whose upper steps would only add zeros: bit-identical to k_restrict_warp.
@@ -422,12 +477,74 @@ static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, AggGeom ag,
     }
 }
 
+// Short aggregate rows (RL = sub[3]*dof contiguous fine elements; 4 = 64 bytes for the 4^3 scalar aggregates of the finest level):
+// a warp works on AW aggregates that are neighbours along x, so that each of its fine-lattice requests is a run of RL*AW elements
+// (128 bytes) instead of RL.  Lane l: element l % RL of aggregate (l / RL) % AW, row l / (RL*AW) of the trip's rows.  The sum over e
+// is the same per element as in k_prolong: identical bits.  Measured standalone at 512^3 (scripts/kbench_transfer.cu,
+// profiles/r02_kbench_transfer_rows.txt): 6.6 TB/s against 6.1 for one aggregate per warp.
+template <int RL, int AW>
+static __global__ void __launch_bounds__(256) k_prolong_rows(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
+                                                             const c128* __restrict__ xc, c128* __restrict__ xf, int add) {
+    PDL_ENTRY();
+    constexpr int RPT = 32 / (RL * AW);               // rows per trip
+    const int lane = threadIdx.x & 31;
+    const int off = lane % RL, a_in = (lane / RL) % AW, r0 = lane / (RL * AW);
+    const int rows = (int)(g.bl / RL);
+    const int64_t ngroups = g.nb / AW;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += nwarps) {
+        const int64_t b = grp * AW + a_in;
+        c128* xb = xf + agg_first_elem(ag, g.bl, b);
+        const c128* pb = P + b * g.ne * g.bl;
+        const c128* a = xc + b * g.ne;
+        for (int row = r0; row < rows; row += 2 * RPT) {    // two rows per lane and trip: 2*ne independent loads in flight
+            const int qa = row * RL + off, qb = (row + RPT) * RL + off;
+            const bool onb = row + RPT < rows;
+            c128* da = xb + __ldg(q_off + qa);
+            c128* db = onb ? xb + __ldg(q_off + qb) : nullptr;
+            c128 olda = cmake(0., 0.), oldb = cmake(0., 0.);
+            if (add) { olda = *da; if (onb) oldb = *db; }
+            c128 acca = cmake(0., 0.), accb = cmake(0., 0.);
+#pragma unroll 4
+            for (int e = 0; e < g.ne; e++) {
+                const c128 ce = __ldg(a + e);
+                acca = cadd(acca, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qa)));
+                if (onb) accb = cadd(accb, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qb)));
+            }
+            *da = add ? cadd(olda, acca) : acca;
+            if (onb) *db = add ? cadd(oldb, accb) : accb;
+        }
+    }
+}
+
 static AggGeom agg_geom(const LevelGeom& g) {
     AggGeom a;
     for (int i = 0; i < 4; i++) { a.bd[i] = (int)g.bd[i]; a.sub[i] = (int)g.sub[i]; a.sd[i] = (int)g.sd[i]; }
     a.dof = g.dof;
     a.linear = (g.sub[0] == 1 && g.sub[1] == 1 && g.sub[2] == 1) ? 1 : 0;
     return a;
+}
+
+// Persistent grid (the CTAs that are resident at once stride over the aggregates) or one warp-task per warp (grid = all the work).
+// Measured inside the 512^3 solve (profiles/r02_transfer_knobs.txt): restrict is faster persistent (5.53 against 5.23 TB/s on
+// the same box), prolong one-shot (5.74 against 5.60) -- the opposite of what the standalone loop shows for restrict
+// (profiles/r02_kbench_transfer_rows.txt), where the SM clock is not under the power cap.  Knobs: MGCR_RESTRICT_ONESHOT,
+// MGCR_PROLONG_ONESHOT.
+static bool transfer_oneshot() {
+    static const int v = getenv("MGCR_RESTRICT_ONESHOT") ? atoi(getenv("MGCR_RESTRICT_ONESHOT")) : 0;
+    return v != 0;
+}
+static bool prolong_oneshot() {
+    static const int v = getenv("MGCR_PROLONG_ONESHOT") ? atoi(getenv("MGCR_PROLONG_ONESHOT")) : 1;
+    return v != 0;
+}
+static bool restrict_fold() {   // experiment knob: 0 = one butterfly per value (k_restrict_warp) also for ne = 4
+    static const int v = getenv("MGCR_RESTRICT_FOLD") ? atoi(getenv("MGCR_RESTRICT_FOLD")) : 1;
+    return v != 0;
+}
+static int transfer_rows() {
+    static const int v = getenv("MGCR_PROLONG_ROWS") ? atoi(getenv("MGCR_PROLONG_ROWS")) : 1;
+    return v;
 }
 
 static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
@@ -441,13 +558,19 @@ static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
 #define RESTRICT_LAUNCH(KERNEL, lanes_per_agg)                                                                                              \
     do {                                                                                                                                    \
         const int64_t need = (g.nb * (lanes_per_agg) + 255) / 256;                                                                          \
-        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, (const void*)KERNEL, 256), need));         \
+        const int64_t cap = transfer_oneshot() ? need : resident_ctas(ctx, (const void*)KERNEL, 256);                                       \
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, need));                                                  \
         launch_pdl(ctx, KERNEL, grid, 256, 0, g, ag, qo, P, xf, xc);                                                                        \
     } while (0)
     if (g.bl <= 256) {
         ProfScope ps_(ctx, "mg_restrict", bytes);
         if (g.bl <= 8) RESTRICT_LAUNCH(k_restrict_sub<8>, 8);
         else if (g.bl <= 16) RESTRICT_LAUNCH(k_restrict_sub<16>, 16);
+        else if (g.ne == 4 && restrict_fold()) {
+            if (g.bl <= 64) RESTRICT_LAUNCH(k_restrict_warp4<2>, 32);
+            else if (g.bl <= 128) RESTRICT_LAUNCH(k_restrict_warp4<4>, 32);
+            else RESTRICT_LAUNCH(k_restrict_warp4<8>, 32);
+        }
         else if (g.bl <= 64) RESTRICT_LAUNCH(k_restrict_warp<2>, 32);
         else if (g.bl <= 128) RESTRICT_LAUNCH(k_restrict_warp<4>, 32);
         else RESTRICT_LAUNCH(k_restrict_warp<8>, 32);
@@ -465,8 +588,21 @@ static int mg_restrict(mgcr_ctx* ctx, MgLevel& L, const c128* xf, c128* xc) {
 static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf, bool add = false) {
     const LevelGeom& g = L.g;
     if (L.n == 0) return MGCR_OK;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(resident_ctas(ctx, (const void*)k_prolong, 256), (g.nb * 32 + 255) / 256));
-    KLAUNCH(ctx, "mg_prolong", 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc, (launch_pdl(ctx, k_prolong, grid, 256, 0, g, agg_geom(g), (const int32_t*)L.d_q_off, (const c128*)L.d_P, xc, xf, add ? 1 : 0)));
+    const double bytes = 16. * L.n * (1 + g.ne + (add ? 1 : 0)) + 16. * L.nc;
+    const AggGeom ag = agg_geom(g);
+    const int64_t rl = g.sub[3] * g.dof;
+    if (transfer_rows() && !ag.linear && rl == 4 && (g.bl / rl) % 4 == 0 && g.bd[3] % 2 == 0) {   // 64-byte aggregate rows: two aggregates per warp
+        const int64_t need = (g.nb / 2 * 32 + 255) / 256;
+        const int64_t cap = prolong_oneshot() ? need : resident_ctas(ctx, (const void*)k_prolong_rows<4, 2>, 256);
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, need));
+        KLAUNCH(ctx, "mg_prolong", bytes, (launch_pdl(ctx, k_prolong_rows<4, 2>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xc, xf, add ? 1 : 0)));
+        CHECK_LAUNCH();
+        return MGCR_OK;
+    }
+    const int64_t need = (g.nb * 32 + 255) / 256;
+    const int64_t cap = prolong_oneshot() ? need : resident_ctas(ctx, (const void*)k_prolong, 256);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, need));
+    KLAUNCH(ctx, "mg_prolong", bytes, (launch_pdl(ctx, k_prolong, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xc, xf, add ? 1 : 0)));
     CHECK_LAUNCH();
     return MGCR_OK;
 }

@@ -14,7 +14,7 @@
 
 int dist_allgather(mgcr_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
 
-enum { P2P_AR_MAX = 64, P2P_ALIGN = 256 };
+enum { P2P_ALIGN = 256 };   // (P2P_AR_MAX: common.cuh)
 
 struct PeerState {
     unsigned char* heap = nullptr;
@@ -140,31 +140,6 @@ void p2p_destroy(mgcr_ctx* ctx) {
 // ----------------------------------------------------------------------------------------------------------
 // all-reduce
 // ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
-    uint64_t v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) { asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-
-// A rank that died (or never reached the matching exchange) must not leave its peers spinning for ever: after 60 s of
-// waiting the kernel traps, the stream reports an error and the caller fails loudly.
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-struct SpinGuard {
-    unsigned int spins = 0;
-    unsigned long long t0 = 0;
-    __device__ __forceinline__ void tick() {
-        if ((++spins & 0x3fffu) != 0) return;
-        const unsigned long long now = global_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 60000000000ull) __trap();
-    }
-};
-
 struct PeerPtrs { uint64_t* p[16]; };
 
 // slot layout of one parity: [source rank][2 * P2P_AR_MAX] words, word 2i / 2i+1 = {low / high half of element i, seq}
@@ -179,23 +154,22 @@ static __global__ void __launch_bounds__(256) k_p2p_allreduce(PeerPtrs peers, ui
         st_volatile_u64(peers.p[p] + (size_t)rank * (2 * P2P_AR_MAX) + j, ((uint64_t)seq << 32) | half);
     }
     __syncthreads();   // `in` has been read by every thread before anybody overwrites it (out may alias in)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double part[16];
-        for (int r = 0; r < nranks; r++) {
-            const uint64_t* w = mine + (size_t)r * (2 * P2P_AR_MAX) + 2 * i;
-            uint64_t lo, hi;
-            SpinGuard guard;
-            while ((uint32_t)((lo = ld_volatile_u64(w)) >> 32) != seq) guard.tick();
-            while ((uint32_t)((hi = ld_volatile_u64(w + 1)) >> 32) != seq) guard.tick();
-            part[r] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
-        }
-        // balanced binary tree over the rank index: with a power-of-two number of ranks this continues the tree each rank summed
-        // its own virtual slabs with (common.cuh, RedGeom), so 1, 2, 4 and 8 GPUs perform the same additions; identical bits on
-        // every rank in any case
-        for (int w = 1; w < nranks; w <<= 1)
-            for (int r = 0; r + w < nranks; r += 2 * w) part[r] += part[r + w];
-        out[i] = part[0];
-    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = ar_collect(mine, nranks, seq, i);   // fixed tree over the ranks (common.cuh)
+}
+
+int p2p_allreduce_fold(mgcr_ctx* ctx, int n, const double* d_src, double* d_dst, ArPush* push, ArWait* wait) {
+    static const bool fold_on = !(getenv("MGCR_AR_FOLD") && atoi(getenv("MGCR_AR_FOLD")) == 0);   // experiment knob: 0 = stand-alone kernel
+    PeerState* s = state(ctx);
+    memset(push, 0, sizeof *push);
+    memset(wait, 0, sizeof *wait);
+    if (!s || !fold_on || n <= 0 || n > AR_FOLD_MAX || ctx->nranks > 16) return MGCR_ERR_UNSUPPORTED;
+    s->ar_seq++;
+    if (s->ar_seq == 0) s->ar_seq = 1;
+    const size_t par = (size_t)(s->ar_seq & 1) * (size_t)ctx->nranks * 2 * P2P_AR_MAX * sizeof(uint64_t);
+    for (int r = 0; r < ctx->nranks; r++) push->peer[r] = (uint64_t*)(s->peer[(size_t)r] + s->ar_off + par);
+    push->src = d_src; push->rank = ctx->rank; push->nranks = ctx->nranks; push->n = n; push->seq = s->ar_seq;
+    wait->mine = (const uint64_t*)(s->heap + s->ar_off + par); wait->dst = d_dst; wait->nranks = ctx->nranks; wait->n = n; wait->seq = s->ar_seq;
+    return MGCR_OK;
 }
 
 // returns MGCR_ERR_UNSUPPORTED when the caller has to use NCCL (path off, too many values)
@@ -229,7 +203,7 @@ static __global__ void __launch_bounds__(256) k_p2p_halo(const c128* __restrict_
     PDL_ENTRY();
     __shared__ bool is_last;
     // four elements per thread and direction in flight (posted 16-byte stores over NVLink): with 64 CTAs of one store per thread
-    // the 4.2 MB plane of the 512^3 lattice left at ~130 GB/s (22 us per exchange at every GPU count, profiles/r02_bench_*_n{2,4,8}.json)
+    // the 4.2 MB plane of the 512^3 lattice left at ~190 GB/s per direction (22 us per exchange at every GPU count, profiles/r02_bench_*_n{2,4,8}.json)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n; i += 4 * stride) {

@@ -72,6 +72,76 @@ static __global__ void __launch_bounds__(256) k_restrict_a(int64_t n, int64_t nb
         if (lane == 0) xc[b * NE + e] = cmake(sr, si);
     }
 }
+
+// ---- product layout, a warp works on AW aggregates that are neighbours along x: the fine-lattice side becomes runs of
+// 64*AW bytes (AW = 1: the product's kernels), the prolongator side 64-byte pieces of AW contiguous 4 KB chunks ----
+template <int AW, bool PERSIST>
+static __global__ void __launch_bounds__(256) k_prolong_w(int64_t n, int64_t nblocks, const c128* __restrict__ P, const c128* __restrict__ xc, c128* __restrict__ xf) {
+    constexpr int RPT = 8 / AW;                    // aggregate rows (of 4 sites) per aggregate and trip
+    const int lane = threadIdx.x & 31;
+    const int ox = lane & 3, a = (lane >> 2) % AW, r0 = lane / (4 * AW);
+    const int64_t ngroups = nblocks / AW;
+    const int64_t nwarps = PERSIST ? ((int64_t)gridDim.x * blockDim.x) >> 5 : ngroups;
+    for (int64_t gidx = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; gidx < ngroups; gidx += nwarps) {
+        const int64_t b = gidx * AW + a;
+        const c128* pb = P + b * NE * BS;
+        c128 ce[NE];
+#pragma unroll
+        for (int e = 0; e < NE; e++) ce[e] = __ldg(xc + b * NE + e);
+#pragma unroll
+        for (int j = 0; j < 16 / RPT; j += 2) {
+            const int qa = (j * RPT + r0) * 4 + ox, qb = ((j + 1) * RPT + r0) * 4 + ox;
+            c128* da = xf + site_of(n, b, qa);
+            c128* db = xf + site_of(n, b, qb);
+            const c128 olda = *da, oldb = *db;
+            c128 acca = cmake(0., 0.), accb = cmake(0., 0.);
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+                acca = cadd(acca, cmul(ce[e], ld_stream(pb + e * BS + qa)));
+                accb = cadd(accb, cmul(ce[e], ld_stream(pb + e * BS + qb)));
+            }
+            *da = cadd(olda, acca);
+            *db = cadd(oldb, accb);
+        }
+        if (!PERSIST) break;
+    }
+}
+template <int AW, bool PERSIST>
+static __global__ void __launch_bounds__(256) k_restrict_w(int64_t n, int64_t nblocks, const c128* __restrict__ P, const c128* __restrict__ xf, c128* __restrict__ xc) {
+    constexpr int RPT = 8 / AW;
+    const int lane = threadIdx.x & 31;
+    const int ox = lane & 3, a = (lane >> 2) % AW, r0 = lane / (4 * AW);
+    const int64_t ngroups = nblocks / AW;
+    const int64_t nwarps = PERSIST ? ((int64_t)gridDim.x * blockDim.x) >> 5 : ngroups;
+    for (int64_t gidx = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; gidx < ngroups; gidx += nwarps) {
+        const int64_t b = gidx * AW + a;
+        const c128* pb = P + b * NE * BS;
+        double sr[NE], si[NE];
+#pragma unroll
+        for (int e = 0; e < NE; e++) { sr[e] = 0.; si[e] = 0.; }
+#pragma unroll
+        for (int j = 0; j < 16 / RPT; j++) {
+            const int q = (j * RPT + r0) * 4 + ox;
+            const c128 xv = __ldg(xf + site_of(n, b, q));
+#pragma unroll
+            for (int e = 0; e < NE; e++) { c128 t = cmulc(ld_stream(pb + e * BS + q), xv); sr[e] += t.x; si[e] += t.y; }
+        }
+        // lanes of one aggregate: bits 0-1 (ox) and the row bits above the aggregate bits
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                if (m >= 4 && m < 4 * AW) continue;
+                sr[e] += __shfl_xor_sync(0xffffffffu, sr[e], m); si[e] += __shfl_xor_sync(0xffffffffu, si[e], m);
+            }
+        }
+        if (ox == 0 && r0 == 0) {
+#pragma unroll
+            for (int e = 0; e < NE; e++) xc[b * NE + e] = cmake(sr[e], si[e]);
+        }
+        if (!PERSIST) break;
+    }
+}
 // ---- candidate form: lattice order everywhere ----
 static __global__ void __launch_bounds__(256) k_prolong_c(int64_t n, const c128* __restrict__ PC, const c128* __restrict__ xc, c128* __restrict__ xf) {
     const int64_t V = n * n * n, nb = n / SUB;
@@ -155,6 +225,51 @@ int main(int argc, char** argv) {
     printf("prolong   product layout : %8.1f us %6.0f GB/s\n", t * 1e3, bytes_p / (t * 1e-3) / 1e9);
     t = time_ms([&] { k_prolong_c<<<(unsigned)((V + 255) / 256), 256>>>(n, PC, xc, xf2); });
     printf("prolong   lattice layout : %8.1f us %6.0f GB/s\n", t * 1e3, bytes_p / (t * 1e-3) / 1e9);
+
+    // warp-per-AW-aggregates variants of the product layout
+    {
+        c128* xc3; cudaMalloc(&xc3, 16 * nblocks * NE);
+        c128* xf3; cudaMalloc(&xf3, 16 * V);
+        std::vector<c128> c3((size_t)(nblocks * NE)), h3((size_t)V);
+        auto check_r = [&](const char* name) {
+            cudaMemcpy(c3.data(), xc3, 16 * nblocks * NE, cudaMemcpyDeviceToHost);
+            double d = 0.;
+            for (int64_t i = 0; i < nblocks * NE; i++) d = fmax(d, fmax(fabs(c1[i].x - c3[i].x), fabs(c1[i].y - c3[i].y)));
+            printf("   %s max |diff| / max = %.3e\n", name, d / nr);
+        };
+#define RUN_R(AW, PERS, GRID) do { \
+        cudaMemset(xc3, 0, 16 * nblocks * NE); \
+        k_restrict_w<AW, PERS><<<GRID, 256>>>(n, nblocks, PA, xf2, xc3); \
+        t = time_ms([&] { k_restrict_w<AW, PERS><<<GRID, 256>>>(n, nblocks, PA, xf2, xc3); }); \
+        printf("restrict  warp x %d aggregates %s : %8.1f us %6.0f GB/s\n", AW, PERS ? "persistent" : "one-shot  ", t * 1e3, bytes_r / (t * 1e-3) / 1e9); } while (0)
+#define RUN_P(AW, PERS, GRID) do { \
+        t = time_ms([&] { k_prolong_w<AW, PERS><<<GRID, 256>>>(n, nblocks, PA, xc, xf3); }); \
+        printf("prolong   warp x %d aggregates %s : %8.1f us %6.0f GB/s\n", AW, PERS ? "persistent" : "one-shot  ", t * 1e3, bytes_p / (t * 1e-3) / 1e9); } while (0)
+        // (xf2 holds the candidate's prolonged vector; restrict of it by variant vs by the product kernel)
+        k_restrict_a<<<(unsigned)((nblocks * 32 + 255) / 256), 256>>>(n, nblocks, PA, xf2, xc);
+        cudaMemcpy(c1.data(), xc, 16 * nblocks * NE, cudaMemcpyDeviceToHost);
+        nr = 0.; for (int64_t i = 0; i < nblocks * NE; i++) nr = fmax(nr, fabs(c1[i].x));
+        const unsigned pg = 148 * 4;
+        RUN_R(1, false, (unsigned)((nblocks / 1 * 32 + 255) / 256)); check_r("AW=1");
+        RUN_R(2, false, (unsigned)((nblocks / 2 * 32 + 255) / 256)); check_r("AW=2");
+        RUN_R(4, false, (unsigned)((nblocks / 4 * 32 + 255) / 256)); check_r("AW=4");
+        RUN_R(8, false, (unsigned)((nblocks / 8 * 32 + 255) / 256)); check_r("AW=8");
+        RUN_R(1, true, pg); RUN_R(2, true, pg); RUN_R(4, true, pg); RUN_R(8, true, pg); check_r("AW=8 persistent");
+        // prolong: bit-exactness of one application against the product kernel
+        cudaMemcpy(xf3, xf2, 16 * V, cudaMemcpyDeviceToDevice);
+        cudaMemcpy(xf, xf2, 16 * V, cudaMemcpyDeviceToDevice);
+        k_prolong_a<<<(unsigned)((V + 255) / 256), 256>>>(n, V, PA, xc, xf);
+        k_prolong_w<4, true><<<pg, 256>>>(n, nblocks, PA, xc, xf3);
+        cudaMemcpy(h1.data(), xf, 16 * V, cudaMemcpyDeviceToHost); cudaMemcpy(h3.data(), xf3, 16 * V, cudaMemcpyDeviceToHost);
+        double d = 0.; for (int64_t i = 0; i < V; i++) d = fmax(d, fmax(fabs(h1[i].x - h3[i].x), fabs(h1[i].y - h3[i].y)));
+        printf("   prolong AW=4 persistent vs product: max |diff| = %.3e (expect 0)\n", d);
+        RUN_P(1, false, (unsigned)((nblocks / 1 * 32 + 255) / 256));
+        RUN_P(2, false, (unsigned)((nblocks / 2 * 32 + 255) / 256));
+        RUN_P(4, false, (unsigned)((nblocks / 4 * 32 + 255) / 256));
+        RUN_P(8, false, (unsigned)((nblocks / 8 * 32 + 255) / 256));
+        RUN_P(1, true, pg); RUN_P(2, true, pg); RUN_P(4, true, pg); RUN_P(8, true, pg);
+        RUN_P(4, true, 148 * 3); RUN_P(4, true, 148 * 6); RUN_P(8, true, 148 * 6);
+    }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
