@@ -292,7 +292,7 @@ __device__ __forceinline__ void ar_push(const ArPush& a) {
 // one value: wait for every rank's contribution and add them as a balanced binary tree over the rank index -- with a power-of-two
 // number of ranks this continues the tree each rank summed its own virtual slabs with (RedGeom), so 1, 2, 4 and 8 GPUs perform the
 // same additions; identical bits on every rank in any case
-__device__ __forceinline__ double ar_collect(const uint64_t* mine, int nranks, uint32_t seq, int i) {
+static __device__ __noinline__ double ar_collect(const uint64_t* mine, int nranks, uint32_t seq, int i) {
     double part[16];
     for (int r = 0; r < nranks; r++) {
         const uint64_t* w = mine + (size_t)r * (2 * P2P_AR_MAX) + 2 * i;
@@ -388,25 +388,41 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// the last CTA's part: value q summed over the CTA partials of every virtual slab (lanes stride over the slab's G CTAs, shuffle
-// tree), then the slab sums by a balanced binary tree over the slab index.  Called by whole warps; every lane returns the sum.
-__device__ __forceinline__ double combine_partials(const double* __restrict__ partials, int stride_vals, int q, const RedGeom& rg, int lane) {
-    double segs[RED_VSLABS];
-#pragma unroll
-    for (int v = 0; v < RED_VSLABS; v++) {
+// The last CTA's part: value q summed over the CTA partials of every virtual slab (lanes stride over the slab's G CTAs in the order
+// b = lane, lane+32, ..., then the shuffle tree), then the slab sums by a balanced binary tree over the slab index.
+// All RED_THREADS threads call it.  The (slab, value) pairs are dealt over the eight warps and each lane keeps four loads in
+// flight (the additions stay in order): with one warp per VALUE and one load at a time this tail was 148 dependent L2 round trips
+// for G = 592 and 8 slabs -- a quarter of the 89 us of a level-1 inner-product kernel at 512^3.
+// `scratch`: RED_VSLABS * nv doubles of shared memory that nobody reads any more.
+__device__ __forceinline__ void combine_partials(const double* __restrict__ partials, int stride_vals, int nv, const RedGeom& rg, double* scratch,
+                                                 double* __restrict__ result, int nwrite) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int task = warp; task < rg.nvs * nv; task += RED_THREADS / 32) {
+        const int v = task / nv, q = task - v * nv;
+        const double* src = partials + (size_t)v * rg.G * stride_vals + q;
         double acc = 0.;
-        if (v < rg.nvs) {
-            for (int b = lane; b < rg.G; b += 32) acc += __ldcg(&partials[(size_t)(v * rg.G + b) * stride_vals + q]);
-            acc = warp_sum(acc);
+        int b = lane;
+        for (; b + 96 < rg.G; b += 128) {
+            const double a0 = __ldcg(src + (size_t)b * stride_vals), a1 = __ldcg(src + (size_t)(b + 32) * stride_vals);
+            const double a2 = __ldcg(src + (size_t)(b + 64) * stride_vals), a3 = __ldcg(src + (size_t)(b + 96) * stride_vals);
+            acc += a0; acc += a1; acc += a2; acc += a3;
         }
-        segs[v] = acc;
+        for (; b < rg.G; b += 32) acc += __ldcg(src + (size_t)b * stride_vals);
+        acc = warp_sum(acc);
+        if (lane == 0) scratch[v * nv + q] = acc;
     }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nv; q += RED_THREADS) {
+        double segs[RED_VSLABS];
 #pragma unroll
-    for (int w = 1; w < RED_VSLABS; w <<= 1)
+        for (int v = 0; v < RED_VSLABS; v++) segs[v] = v < rg.nvs ? scratch[v * nv + q] : 0.;
 #pragma unroll
-        for (int i = 0; i + w < RED_VSLABS; i += 2 * w)
-            if (i + w < rg.nvs) segs[i] += segs[i + w];
-    return segs[0];
+        for (int w = 1; w < RED_VSLABS; w <<= 1)
+#pragma unroll
+            for (int i = 0; i + w < RED_VSLABS; i += 2 * w)
+                if (i + w < rg.nvs) segs[i] += segs[i + w];
+        if (q < nwrite) result[q] = segs[0];
+    }
 }
 
 // blockDim.x must be RED_THREADS, gridDim.x = rg.G.  Two steps:
@@ -432,7 +448,6 @@ __device__ __forceinline__ bool grid_finish(SlabSums<NV>& sm, double* __restrict
                                             const RedGeom& rg, int nwrite = NV, const ArPush* push = nullptr) {
     constexpr int NW = RED_THREADS / 32;
     __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __syncthreads();
     for (int t = threadIdx.x; t < rg.nvs * NV; t += RED_THREADS) {
         const int vs = t / NV, k = t - vs * NV;
@@ -450,11 +465,8 @@ __device__ __forceinline__ bool grid_finish(SlabSums<NV>& sm, double* __restrict
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    // last block: warp w combines values w, w + NW, ... in a fixed order (combine_partials)
-    for (int q = warp; q < NV; q += NW) {
-        const double s = combine_partials(partials, NV, q, rg, lane);
-        if (lane == 0 && q < nwrite) result[q] = s;
-    }
+    // last block: every (slab, value) pair in a fixed order (combine_partials); the warp sums in shared memory have all been read
+    combine_partials(partials, NV, NV, rg, &sm.w[0][0][0], result, nwrite);
     if (push && push->seq) {   // folded all-reduce: this rank's sums leave for every rank's slots right here
         __syncthreads();
         ar_push(*push);

@@ -172,7 +172,12 @@ static void prof_drain(mgcr_ctx* c) {
     for (const ProfPending& p : c->prof_pending) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c->prof_events[2 * p.ev], c->prof_events[2 * p.ev + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
-        ProfEntry& e = c->prof[p.name];
+        // MGCR_PROFILE_BY_SIZE=1 (diagnostic): one class per kernel AND problem size ("gcr_init@2.1e+09"), to see which level of a
+        // hierarchy a class loses its bandwidth on
+        static const bool by_size = getenv("MGCR_PROFILE_BY_SIZE") && atoi(getenv("MGCR_PROFILE_BY_SIZE")) != 0;
+        std::string key = p.name;
+        if (by_size) { char buf[32]; snprintf(buf, sizeof buf, "@%.1e", p.bytes); key += buf; }
+        ProfEntry& e = c->prof[key];
         e.ms += ms; e.calls++; e.bytes += p.bytes;
     }
     c->prof_pending.clear();

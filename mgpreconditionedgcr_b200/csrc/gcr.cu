@@ -256,8 +256,13 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     do {
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
-        KLAUNCH(ctx, "gcr_update_xr", ((x_zero && !aliased && g == 1) ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
+        if (waitA.seq) {
+            KLAUNCH(ctx, "gcr_update_xr", ((x_zero && !aliased && g == 1) ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr<true>, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
                                                                  scal, red + S_RR, bden_off + cur, (x_zero && !aliased && g == 1) ? 1 : 0, ctx->d_partials, ctx->d_ticket, guard, tol2, waitA)));
+        } else {
+            KLAUNCH(ctx, "gcr_update_xr", ((x_zero && !aliased && g == 1) ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr<false>, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
+                                                                 scal, red + S_RR, bden_off + cur, (x_zero && !aliased && g == 1) ? 1 : 0, ctx->d_partials, ctx->d_ticket, guard, tol2, waitA)));
+        }
         GCUDA(cudaGetLastError());
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
             KLAUNCH(ctx, "vec_norm2", 16. * n, (launch_pdl(ctx, k_norm2, grid, RED_THREADS, 0, rg, (const c128*)x, ctx->d_partials, ctx->d_ticket, red + S_BB)));

@@ -379,23 +379,42 @@ static __global__ void __launch_bounds__(256) k_restrict_warp4(LevelGeom g, AggG
     for (int j = 0; j < QPL; j++) qo[j] = lane + 32 * j < g.bl ? __ldg(q_off + lane + 32 * j) : 0;
     for (int64_t b = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; b < g.nb; b += nwarps) {
         const c128* xb = xf + agg_first_elem(ag, g.bl, b);
-        c128 xs[QPL];
-#pragma unroll
-        for (int j = 0; j < QPL; j++) xs[j] = lane + 32 * j < g.bl ? __ldg(xb + qo[j]) : cmake(0., 0.);
+        // dof chunk outermost (per vector the terms are still added in the order j = 0, 1, ...): the x element and its four
+        // prolongator elements are one batch of five independent loads, and the batches of different j overlap
+        // (long aggregates only: with QPL = 2 everything is in flight at once either way and the vector-outermost form needs 48
+        // registers instead of 64 -- 1.63 against 1.88 ms for the finest-level restrict of the 512^3 solve)
+        const c128* pv = P + b * 4 * g.bl;
         double v[8];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const c128* pv = P + (b * 4 + e) * g.bl;
-            double sr = 0., si = 0.;
+        for (int k = 0; k < 8; k++) v[k] = 0.;
+        if constexpr (QPL <= 2) {
+            c128 xs[QPL];
+#pragma unroll
+            for (int j = 0; j < QPL; j++) xs[j] = lane + 32 * j < g.bl ? __ldg(xb + qo[j]) : cmake(0., 0.);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+#pragma unroll
+                for (int j = 0; j < QPL; j++) {
+                    const int64_t q = lane + 32 * j;
+                    if (q < g.bl) {
+                        c128 t = cmulc(ld_stream(pv + e * g.bl + q), xs[j]);
+                        v[2 * e] += t.x; v[2 * e + 1] += t.y;
+                    }
+                }
+            }
+        } else {
 #pragma unroll
             for (int j = 0; j < QPL; j++) {
                 const int64_t q = lane + 32 * j;
                 if (q < g.bl) {
-                    c128 t = cmulc(ld_stream(pv + q), xs[j]);
-                    sr += t.x; si += t.y;
+                    const c128 xv = __ldg(xb + qo[j]);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        c128 t = cmulc(ld_stream(pv + e * g.bl + q), xv);
+                        v[2 * e] += t.x; v[2 * e + 1] += t.y;
+                    }
                 }
             }
-            v[2 * e] = sr; v[2 * e + 1] = si;
         }
         double w[4], u[2];
 #pragma unroll
@@ -482,7 +501,7 @@ static __global__ void __launch_bounds__(256) k_prolong(LevelGeom g, AggGeom ag,
 // (128 bytes) instead of RL.  Lane l: element l % RL of aggregate (l / RL) % AW, row l / (RL*AW) of the trip's rows.  The sum over e
 // is the same per element as in k_prolong: identical bits.  Measured standalone at 512^3 (scripts/kbench_transfer.cu,
 // profiles/r02_kbench_transfer_rows.txt): 6.6 TB/s against 6.1 for one aggregate per warp.
-template <int RL, int AW>
+template <int RL, int AW, int NE /* compile-time number of near-null vectors, 0 = g.ne */>
 static __global__ void __launch_bounds__(256) k_prolong_rows(LevelGeom g, AggGeom ag, const int32_t* __restrict__ q_off, const c128* __restrict__ P,
                                                              const c128* __restrict__ xc, c128* __restrict__ xf, int add) {
     PDL_ENTRY();
@@ -494,9 +513,10 @@ static __global__ void __launch_bounds__(256) k_prolong_rows(LevelGeom g, AggGeo
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; grp < ngroups; grp += nwarps) {
         const int64_t b = grp * AW + a_in;
+        const int ne = NE ? NE : g.ne;
         c128* xb = xf + agg_first_elem(ag, g.bl, b);
-        const c128* pb = P + b * g.ne * g.bl;
-        const c128* a = xc + b * g.ne;
+        const c128* pb = P + b * ne * g.bl;
+        const c128* a = xc + b * ne;
         for (int row = r0; row < rows; row += 2 * RPT) {    // two rows per lane and trip: 2*ne independent loads in flight
             const int qa = row * RL + off, qb = (row + RPT) * RL + off;
             const bool onb = row + RPT < rows;
@@ -505,11 +525,27 @@ static __global__ void __launch_bounds__(256) k_prolong_rows(LevelGeom g, AggGeo
             c128 olda = cmake(0., 0.), oldb = cmake(0., 0.);
             if (add) { olda = *da; if (onb) oldb = *db; }
             c128 acca = cmake(0., 0.), accb = cmake(0., 0.);
+            if (NE) {   // every load of the trip is issued before the first product
+                constexpr int NEC = NE ? NE : 1;
+                c128 pa[NEC], pq[NEC];
+#pragma unroll
+                for (int e = 0; e < NEC; e++) {
+                    pa[e] = ld_stream(pb + (int64_t)e * g.bl + qa);
+                    pq[e] = onb ? ld_stream(pb + (int64_t)e * g.bl + qb) : cmake(0., 0.);
+                }
+#pragma unroll
+                for (int e = 0; e < NEC; e++) {
+                    const c128 ce = __ldg(a + e);
+                    acca = cadd(acca, cmul(ce, pa[e]));
+                    accb = cadd(accb, cmul(ce, pq[e]));
+                }
+            } else {
 #pragma unroll 4
-            for (int e = 0; e < g.ne; e++) {
-                const c128 ce = __ldg(a + e);
-                acca = cadd(acca, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qa)));
-                if (onb) accb = cadd(accb, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qb)));
+                for (int e = 0; e < ne; e++) {
+                    const c128 ce = __ldg(a + e);
+                    acca = cadd(acca, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qa)));
+                    if (onb) accb = cadd(accb, cmul(ce, ld_stream(pb + (int64_t)e * g.bl + qb)));
+                }
             }
             *da = add ? cadd(olda, acca) : acca;
             if (onb) *db = add ? cadd(oldb, accb) : accb;
@@ -593,9 +629,15 @@ static int mg_prolong(mgcr_ctx* ctx, MgLevel& L, const c128* xc, c128* xf, bool 
     const int64_t rl = g.sub[3] * g.dof;
     if (transfer_rows() && !ag.linear && rl == 4 && (g.bl / rl) % 4 == 0 && g.bd[3] % 2 == 0) {   // 64-byte aggregate rows: two aggregates per warp
         const int64_t need = (g.nb / 2 * 32 + 255) / 256;
-        const int64_t cap = prolong_oneshot() ? need : resident_ctas(ctx, (const void*)k_prolong_rows<4, 2>, 256);
-        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, need));
-        KLAUNCH(ctx, "mg_prolong", bytes, (launch_pdl(ctx, k_prolong_rows<4, 2>, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xc, xf, add ? 1 : 0)));
+#define PROLONG_ROWS(KERNEL)                                                                                                                  \
+    do {                                                                                                                                      \
+        const int64_t cap = prolong_oneshot() ? need : resident_ctas(ctx, (const void*)KERNEL, 256);                                          \
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cap, need));                                                    \
+        KLAUNCH(ctx, "mg_prolong", bytes, (launch_pdl(ctx, KERNEL, grid, 256, 0, g, ag, (const int32_t*)L.d_q_off, (const c128*)L.d_P, xc, xf, add ? 1 : 0))); \
+    } while (0)
+        if (g.ne == 4 && transfer_rows() != 2) PROLONG_ROWS((k_prolong_rows<4, 2, 4>));   // (MGCR_PROLONG_ROWS=2: the runtime-ne form, experiment)
+        else PROLONG_ROWS((k_prolong_rows<4, 2, 0>));
+#undef PROLONG_ROWS
         CHECK_LAUNCH();
         return MGCR_OK;
     }

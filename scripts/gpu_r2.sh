@@ -74,6 +74,18 @@ knobs)
         python scripts/bench_brief.py $O/knob_tmp.json 2>/dev/null | head -${KNOB_LINES:-2} >> $O/${TAG}_knobs.txt
     done
     cat $O/${TAG}_knobs.txt ;;
+ab)
+    # same box, interleaved: the library of an earlier commit (build/prev: git archive <commit> | tar -x -C build/prev; make) against the current one
+    : > $O/${TAG}_ab.txt
+    for i in 1 2 3; do
+        for which in prev now; do
+            d=.; [ $which = prev ] && d=build/prev
+            (cd $d && timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-others 2>/dev/null | tail -1) > $O/knob_tmp.json
+            echo "== $which" >> $O/${TAG}_ab.txt
+            python scripts/bench_brief.py $O/knob_tmp.json 2>/dev/null | head -${KNOB_LINES:-13} | grep -v "^mg_setup\|^roofline" >> $O/${TAG}_ab.txt
+        done
+    done
+    cat $O/${TAG}_ab.txt ;;
 kbt)
     # standalone layout comparison for restrict / prolong (scripts/kbench_transfer.cu, built into build/kbt)
     for n in 256 512; do timeout 120 build/kbt $n; done > $O/${TAG}_kbench_transfer.txt 2>&1; cat $O/${TAG}_kbench_transfer.txt ;;
