@@ -926,9 +926,16 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
         ghost_ok = true;
     };
     unsigned char* stage = ring + (size_t)warp * stage_bytes;
-    auto fetch = [&](int64_t base, int w) {                // lane 0: start the copy of a slice into this warp's stage
-        mbar_expect_tx(&full[warp], (uint32_t)w * SLOT);
+    // Residual form: the 32 right-hand-side elements of the slice ride through the ring as a second bulk copy into the last 512
+    // bytes of the stage, completing on the same barrier (read per thread after the products they were one more exposed DRAM round
+    // trip per slice: 773 against 695 us per launch on level 1 of the 512^3 solve; no registers are free to prefetch them).
+    const c128* bst = (const c128*)(stage + stage_bytes - 512);
+    auto fetch = [&](int64_t sl, int64_t base, int w) {    // lane 0: start the copy of a slice into this warp's stage
+        uint32_t bb = 0;
+        if (bsub) bb = (uint32_t)min((int64_t)32, nb * NE - sl * 32) * 16u;
+        mbar_expect_tx(&full[warp], (uint32_t)w * SLOT + bb);
         if (w) tma_load_1d(stage, blob + base * SLOT, (uint32_t)w * SLOT, &full[warp]);
+        if (bb) tma_load_1d((void*)bst, bsub + sl * 32, bb, &full[warp]);
     };
     auto load_cols = [&](int64_t base, int w, int32_t (&col)[PRE]) {
 #pragma unroll
@@ -940,7 +947,7 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
     if (s < s_end) {
         base = __ldg(sl_ptr + s);
         w = (int)(__ldg(sl_ptr + s + 1) - base);
-        if (lane == 0) fetch(base, w);
+        if (lane == 0) fetch(s, base, w);
     }
     load_cols(base, w, col);
     uint32_t parity = 0;
@@ -998,13 +1005,11 @@ __global__ void __launch_bounds__(RingCfg<NE>::MAX_THREADS, 1) k_blockcsr_ring(i
                 }
             }
         }
-        __syncwarp();                                      // every lane is done with the stage
-        if (lane == 0 && sn < s_end) { fence_proxy_async_smem(); fetch(basen, wn); }
         const int64_t t = s * 32 + lane;
-        if (t < nb * NE) {
-            if (bsub) value = csub(__ldg(bsub + t), value);
-            st_stream(y + t, value);
-        }
+        if (bsub && t < nb * NE) value = csub(bst[lane], value);
+        __syncwarp();                                      // every lane is done with the stage
+        if (lane == 0 && sn < s_end) { fence_proxy_async_smem(); fetch(sn, basen, wn); }
+        if (t < nb * NE) st_stream(y + t, value);
         base = basen; w = wn;
 #pragma unroll
         for (int i = 0; i < PRE; i++) col[i] = coln[i];
@@ -1072,10 +1077,10 @@ int BlockCsrOp::build_sliced() {
     sl_slots = tot[0];
     const int64_t wmax = tot[1];
     // ring: one stage (= the widest slice) per consumer warp, as many as fit 200 KB, at most 14 (26 for ne = 2)
-    sl_stage_bytes = (int)(((wmax * slot + 127) / 128) * 128);
+    sl_stage_bytes = (int)(((wmax * slot + 127) / 128) * 128) + 512;   // + the slice's 32 right-hand-side elements (residual form)
     static const int nst_env = getenv("MGCR_BLOCKCSR_STAGES") ? atoi(getenv("MGCR_BLOCKCSR_STAGES")) : 0;   // experiment knob
     const int max_stages = ne == 2 ? RingCfg<2>::MAX_STAGES : RingCfg<4>::MAX_STAGES;
-    sl_stages = sl_stage_bytes ? (int)std::min<int64_t>(nst_env > 0 ? std::min(nst_env, max_stages) : max_stages, (200 * 1024) / sl_stage_bytes) : 0;
+    sl_stages = sl_stage_bytes ? (int)std::min<int64_t>(nst_env > 0 ? std::min(nst_env, max_stages) : max_stages, (212 * 1024) / sl_stage_bytes) : 0;
     // very ragged rows (> 25 % padding) or blobs too large for a useful ring: the assembly layout serves better
     if ((double)sl_slots * S > 1.25 * (double)nnzb || sl_stages < 4) { dev_free(ctx, d_sl_ptr); d_sl_ptr = nullptr; return MGCR_OK; }
     MGCR_TRY(dev_alloc(ctx, (size_t)std::max<int64_t>(sl_slots, 1) * slot, (void**)&d_sl_blob));
@@ -1093,7 +1098,7 @@ template <int NE>
 static int blockcsr_ring_launch(BlockCsrOp* op, const c128* x, const c128* ghost, const c128* bsub, c128* y) {
     mgcr_ctx* ctx = op->ctx;
     const size_t smem = (size_t)op->sl_stages * op->sl_stage_bytes + 128;
-    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_blockcsr_ring<NE>, 201 * 1024));
+    MGCR_TRY(ensure_dyn_smem(ctx, (const void*)k_blockcsr_ring<NE>, 213 * 1024));
     const int threads = 32 * op->sl_stages;
     const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms, (op->nslices + op->sl_stages - 1) / op->sl_stages);
     const PeerHalo* ph = (op->halo && op->halo_deferred) ? &op->halo->ph : nullptr;

@@ -267,10 +267,13 @@ def test_block_csr_sliced_streaming_layout_is_bit_exact(ctx, host, orc, ne):
         Ac = host.HierarchicalSparse(ctx, nb, ne, brow, bcol, bval)
         out = Ac(x)
         out2 = Ac(x)      # second apply: the image is built on the first one
+        b = rng.standard_normal(nb * ne) + 1j * rng.standard_normal(nb * ne)
+        res = Ac.residual(x, b)   # b - A x: the right-hand side rides through the ring as a second bulk copy (ragged last slice: clamped)
     finally:
         ctx.set_option("blockcsr_ring_rows", 1 << 18)
     ref = orc.blockcsr(nb, ne, brow, bcol, bval.reshape(-1))(x)
     assert np.array_equal(out, ref) and np.array_equal(out2, ref)
+    assert np.array_equal(res, b - ref)
 
 
 # ------------------------------------------------------------------------------------------------------------
