@@ -74,16 +74,16 @@ static int dot_hist(mgcr_ctx* ctx, int nh, const RedGeom& rg, int64_t n_global, 
 template <int NH, int MINB>
 static void launch_update_p(mgcr_ctx* ctx, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                             int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj,
-                            int bden_off, double* scal, double* red_anum, const double* guard, double tol2, const ArWait& aw, const ArPush& push) {
+                            int bden_off, int keep_Ap, double* scal, double* red_anum, const double* guard, double tol2, const ArWait& aw, const ArPush& push) {
     launch_pdl(ctx, k_gcr_update_p<NH, MINB>, rg.G, RED_THREADS, 0, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj,
-               bden_off, (const double*)scal, red_anum, ctx->d_partials, ctx->d_ticket, guard, tol2, aw, push);
+               bden_off, keep_Ap, (const double*)scal, red_anum, ctx->d_partials, ctx->d_ticket, guard, tol2, aw, push);
 }
 static void update_p(mgcr_ctx* ctx, int nh, const RedGeom& rg, const c128* z, const c128* Ar, const c128* r, c128* ps, c128* Aps,
                      int64_t stride, const BetaList& bl, int cur, int first, int last, c128* acc_p, c128* acc_Ap, int std_conj, int bden_off,
-                     double* scal, double* red_anum, const double* guard, double tol2, const ArWait& aw, const ArPush& push) {
+                     int keep_Ap, double* scal, double* red_anum, const double* guard, double tol2, const ArWait& aw, const ArPush& push) {
     static const int minb_env = env_int("MGCR_UPD_MINB", 0);   // experiment knob
     const int minb = minb_env ? minb_env : 4;
-#define ARGS ctx, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red_anum, guard, tol2, aw, push
+#define ARGS ctx, rg, z, Ar, r, ps, Aps, stride, bl, cur, first, last, acc_p, acc_Ap, std_conj, bden_off, keep_Ap, scal, red_anum, guard, tol2, aw, push
 #define C(NH) case NH: if (minb >= 4) launch_update_p<NH, 4>(ARGS); else if (minb == 3) launch_update_p<NH, 3>(ARGS); else launch_update_p<NH, 2>(ARGS); break;
     switch (nh) {
         C(0) C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16)
@@ -223,7 +223,10 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     ArWait waitA, waitB;
     memset(&pushA, 0, sizeof pushA); memset(&pushB, 0, sizeof pushB); memset(&waitA, 0, sizeof waitA); memset(&waitB, 0, sizeof waitB);
     if (fold) (void)p2p_allreduce_fold(ctx, 5, red, scal, &pushA, &waitA);   // (refused: the descriptors stay off, stand-alone all-reduce below)
-    KLAUNCH(ctx, "gcr_init", (right ? 48. : 64.) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red, pushA)));
+    // (the working copy r = rhs is not made here: the first x / r update reads rhs and writes r.  The aliased solve (rhs IS x, only
+    // Arnoldi's inverse iteration) keeps the plain copy, and a left preconditioner forms r itself.)
+    const bool r_from_rhs = !aliased && !left;
+    KLAUNCH(ctx, "gcr_init", ((right ? 48. : 64.) - (r_from_rhs ? 16. : 0.)) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r_from_rhs ? (c128*)nullptr : r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red, pushA)));
     GCUDA(cudaGetLastError());
     if (left) {
         // r <- L(r) (GCR.h:201-204): the first alpha and the step-0 print use the preconditioned r with the UNpreconditioned Ap
@@ -256,12 +259,18 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     do {
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
-        if (waitA.seq) {
-            KLAUNCH(ctx, "gcr_update_xr", ((x_zero && !aliased && g == 1) ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr<true>, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
-                                                                 scal, red + S_RR, bden_off + cur, (x_zero && !aliased && g == 1) ? 1 : 0, ctx->d_partials, ctx->d_ticket, guard, tol2, waitA)));
+        const int xz = (x_zero && !aliased && g == 1) ? 1 : 0;
+        const c128* pcur = ps + (int64_t)cur * stride;
+        const c128* Apcur = Aps + (int64_t)cur * stride;
+        if (blind && g >= prm->max_iter) {
+            // the last pass of a solve nobody watches: x is all that is left to compute (no r, no Ap, no norm)
+            const int gx = stream_grid(ctx, n, 4, 4);
+            if (waitA.seq) KLAUNCH(ctx, "gcr_update_x", (xz ? 32. : 48.) * n, (launch_pdl(ctx, k_gcr_update_x<true>, gx, RED_THREADS, 0, n, pcur, x, (const double*)scal, xz, guard, tol2, waitA)));
+            else KLAUNCH(ctx, "gcr_update_x", (xz ? 32. : 48.) * n, (launch_pdl(ctx, k_gcr_update_x<false>, gx, RED_THREADS, 0, n, pcur, x, (const double*)scal, xz, guard, tol2, waitA)));
         } else {
-            KLAUNCH(ctx, "gcr_update_xr", ((x_zero && !aliased && g == 1) ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr<false>, grid, RED_THREADS, 0, rg, (const c128*)(ps + (int64_t)cur * stride), (const c128*)(Aps + (int64_t)cur * stride), x, r,
-                                                                 scal, red + S_RR, bden_off + cur, (x_zero && !aliased && g == 1) ? 1 : 0, ctx->d_partials, ctx->d_ticket, guard, tol2, waitA)));
+            const c128* r_in = (g == 1 && r_from_rhs) ? rhs : r;   // first iteration: r = rhs, never copied
+            if (waitA.seq) KLAUNCH(ctx, "gcr_update_xr", (xz ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr<true>, grid, RED_THREADS, 0, rg, pcur, Apcur, x, r_in, r, scal, red + S_RR, bden_off + cur, xz, ctx->d_partials, ctx->d_ticket, guard, tol2, waitA)));
+            else KLAUNCH(ctx, "gcr_update_xr", (xz ? 80. : 96.) * n, (launch_pdl(ctx, k_gcr_update_xr<false>, grid, RED_THREADS, 0, rg, pcur, Apcur, x, r_in, r, scal, red + S_RR, bden_off + cur, xz, ctx->d_partials, ctx->d_ticket, guard, tol2, waitA)));
         }
         GCUDA(cudaGetLastError());
         if (aliased) {   // rhs IS x (src/MG.h:102): the stopping test sees the norm of the updated vector
@@ -309,8 +318,10 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
                 const int cnt = std::max(0, std::min((int)GCR_CHUNK, lim - c * GCR_CHUNK));
                 for (int k = 0; k < GCR_CHUNK; k++) { bl.slot[k] = k < cnt ? c * GCR_CHUNK + k : 0; bl.num_index[k] = bl.slot[k]; }
                 int first = (c == 0), last = (c == nchunks - 1);
-                ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * cnt + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0)));
-                update_p(ctx, cnt, rg, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, scal, red + S_ANUM, guard, tol2, waitB, pushA);
+                // the direction formed here feeds the LAST x update of a blind solve: A p is reduced in this pass and never read again
+                const int keep_Ap = (blind && g + 1 >= prm->max_iter && last) ? 0 : 1;
+                ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * cnt + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0) - (keep_Ap ? 0 : 1)));
+                update_p(ctx, cnt, rg, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, keep_Ap, scal, red + S_ANUM, guard, tol2, waitB, pushA);
             }
             GCUDA(cudaGetLastError());
             if (dist && !pushA.seq) GTRY(dist_allreduce_sum2(ctx, red + S_ANUM, scal + S_ANUM, 3));

@@ -135,9 +135,11 @@ static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, con
 // the extra prologue changed the compiler's schedule of the streaming loop (same box: 602 us per launch against 585)
 template <bool FOLD>
 static __global__ void __launch_bounds__(RED_THREADS, 5) k_gcr_update_xr(RedGeom rg, const c128* __restrict__ p, const c128* __restrict__ Ap,
-                                                               c128* x, c128* r, double* scal, double* rr_out, int bden_slot, int x_zero,
+                                                               c128* x, const c128* r_in, c128* r, double* scal, double* rr_out, int bden_slot, int x_zero,
                                                                double* partials, unsigned int* ticket, const double* guard, double tol2,
                                                                const __grid_constant__ ArWait aw) {
+    // r_in: where the residual is read from -- r itself, or the right-hand side in the first iteration (r = rhs then, GCR.h:189: the
+    // solver's working copy is first written HERE instead of by a copy in the init kernel, 16 bytes per element less per solve)
     PDL_ENTRY();
     __shared__ SlabSums<1> sums;
     __shared__ double arv[AR_FOLD_MAX];
@@ -174,7 +176,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 5) k_gcr_update_xr(RedGeom
             const c128 p0 = ld_stream(p + i), a0 = ld_stream(Ap + i), p1 = ld_stream(p + i + T), a1 = ld_stream(Ap + i + T);
             c128 x0 = cmake(0., 0.), x1 = cmake(0., 0.);
             if (!x_zero) { x0 = ld_plain(x + i); x1 = ld_plain(x + i + T); }
-            c128 r0 = ld_plain(r + i), r1 = ld_plain(r + i + T);
+            c128 r0 = ld_plain(r_in + i), r1 = ld_plain(r_in + i + T);
             x0 = cadd(x0, cmul(alpha, p0)); r0 = csub(r0, cmul(alpha, a0));
             x1 = cadd(x1, cmul(alpha, p1)); r1 = csub(r1, cmul(alpha, a1));
             st_stream(x + i, x0); st_stream(r + i, r0); st_stream(x + i + T, x1); st_stream(r + i + T, r1);
@@ -183,7 +185,7 @@ static __global__ void __launch_bounds__(RED_THREADS, 5) k_gcr_update_xr(RedGeom
         }
         for (; i < n; i += T) {
             c128 pv = ld_stream(p + i), av = ld_stream(Ap + i);
-            c128 xv = x_zero ? cmake(0., 0.) : ld_plain(x + i), rv = ld_plain(r + i);
+            c128 xv = x_zero ? cmake(0., 0.) : ld_plain(x + i), rv = ld_plain(r_in + i);
             xv = cadd(xv, cmul(alpha, pv));
             rv = csub(rv, cmul(alpha, av));
             st_stream(x + i, xv);
@@ -193,6 +195,43 @@ static __global__ void __launch_bounds__(RED_THREADS, 5) k_gcr_update_xr(RedGeom
         slab_partial<1>(v, sums, vs);
     }
     grid_finish<1>(sums, partials, ticket, rr_out, rg);   // scal + S_RR, or this rank's partial block when the solve is distributed
+}
+
+// The LAST x update of a solve nobody watches (blind, csrc/gcr.cu): x += alpha p and nothing else -- the residual is not read
+// again, its norm is not looked at, so neither Ap nor r is touched (48 instead of 96 bytes per element; 32 when x starts at zero).
+template <bool FOLD>
+static __global__ void __launch_bounds__(RED_THREADS) k_gcr_update_x(int64_t n, const c128* __restrict__ p, c128* x, const double* scal, int x_zero,
+                                                              const double* guard, double tol2, const __grid_constant__ ArWait aw) {
+    PDL_ENTRY();
+    __shared__ double arv[AR_FOLD_MAX];
+    const bool first_batch = FOLD && aw.n == 5;
+    bool converged = !first_batch && gcr_converged(guard, tol2);
+    if constexpr (FOLD) {
+        if (!converged) {
+            ar_wait(aw, arv);
+            if (first_batch) converged = arv[S_RR] <= tol2 * arv[S_BB];
+        }
+    }
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    if (converged) {
+        if (x_zero)
+            for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += T) st_stream(x + i, cmake(0., 0.));
+        return;
+    }
+    const double aden = FOLD ? arv[S_ADEN] : scal[S_ADEN];
+    const c128 alpha = FOLD ? cdivr(cmake(arv[S_ANUM], arv[S_ANUM + 1]), aden) : cdivr(cmake(scal[S_ANUM], scal[S_ANUM + 1]), aden);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * T < n; i += 4 * T) {
+        c128 pv[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { pv[u] = ld_stream(p + i + u * T); xv[u] = x_zero ? cmake(0., 0.) : ld_plain(x + i + u * T); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) st_stream(x + i + u * T, cadd(xv[u], cmul(alpha, pv[u])));
+    }
+    for (; i < n; i += T) {
+        const c128 xv = x_zero ? cmake(0., 0.) : ld_plain(x + i);
+        st_stream(x + i, cadd(xv, cmul(alpha, ld_stream(p + i))));
+    }
 }
 
 // batched <Ar, Aps[slot]> for nh (<= GCR_CHUNK) history vectors in one pass over Ar      (GCR.h:257-258)
@@ -426,7 +465,7 @@ struct BetaList { int slot[GCR_CHUNK]; int num_index[GCR_CHUNK]; };
 template <int NH, int MINB>
 static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGeom rg, const c128* z, const c128* Ar, const c128* r, c128* ps,
                                                                     c128* Aps, int64_t stride, BetaList bl, int cur, int first, int last,
-                                                                    c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, const double* scal,
+                                                                    c128* acc_p, c128* acc_Ap, int std_conj, int bden_off, int keep_Ap, const double* scal,
                                                                     double* anum_out, double* partials, unsigned int* ticket, const double* guard,
                                                                     double tol2, const __grid_constant__ ArWait aw, const __grid_constant__ ArPush push) {
     PDL_ENTRY();
@@ -494,7 +533,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
             v[2] += Apc.x * Apc.x + Apc.y * Apc.y;
         }
         st_stream(pout + i, pc);
-        st_stream(Apout + i, Apc);
+        if (keep_Ap) st_stream(Apout + i, Apc);   // (0: the next x update is the last of a blind solve and reads p only -- the inner products of Ap are formed here)
     }
     if (std_conj) v[1] = -v[1];   // <Ap,r> = conj(<r,Ap>), exactly, term by term
     if (last) slab_partial<3>(v, sums, vs);
