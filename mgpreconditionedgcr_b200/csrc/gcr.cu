@@ -226,7 +226,10 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     // (the working copy r = rhs is not made here: the first x / r update reads rhs and writes r.  The aliased solve (rhs IS x, only
     // Arnoldi's inverse iteration) keeps the plain copy, and a left preconditioner forms r itself.)
     const bool r_from_rhs = !aliased && !left;
-    KLAUNCH(ctx, "gcr_init", ((right ? 48. : 64.) - (r_from_rhs ? 16. : 0.)) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r_from_rhs ? (c128*)nullptr : r, right ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red, pushA)));
+    // Unpreconditioned blind solve that never comes back to ring slot 0: the first direction p0 = rhs is READ from the right-hand
+    // side wherever slot 0 is addressed instead of being copied into the ring (16 bytes per element and solve less)
+    const bool p0_is_rhs = blind && !right && !left && !aliased && prm->max_iter <= restart && prm->max_iter <= storage;
+    KLAUNCH(ctx, "gcr_init", ((right || p0_is_rhs ? 48. : 64.) - (r_from_rhs ? 16. : 0.)) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r_from_rhs ? (c128*)nullptr : r, (right || p0_is_rhs) ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red, pushA)));
     GCUDA(cudaGetLastError());
     if (left) {
         // r <- L(r) (GCR.h:201-204): the first alpha and the step-0 print use the preconditioned r with the UNpreconditioned Ap
@@ -260,7 +263,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
         g++; iter++;
         // alpha, x += alpha p, r -= alpha Ap, ||r||^2                                            (GCR.h:230-233)
         const int xz = (x_zero && !aliased && g == 1) ? 1 : 0;
-        const c128* pcur = ps + (int64_t)cur * stride;
+        const c128* pcur = (p0_is_rhs && cur == 0) ? rhs : ps + (int64_t)cur * stride;
         const c128* Apcur = Aps + (int64_t)cur * stride;
         if (blind && g >= prm->max_iter) {
             // the last pass of a solve nobody watches: x is all that is left to compute (no r, no Ap, no norm)
@@ -316,7 +319,10 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
             for (int c = 0; c < nchunks; c++) {
                 BetaList bl;
                 const int cnt = std::max(0, std::min((int)GCR_CHUNK, lim - c * GCR_CHUNK));
-                for (int k = 0; k < GCR_CHUNK; k++) { bl.slot[k] = k < cnt ? c * GCR_CHUNK + k : 0; bl.num_index[k] = bl.slot[k]; }
+                for (int k = 0; k < GCR_CHUNK; k++) {
+                    bl.slot[k] = k < cnt ? c * GCR_CHUNK + k : 0; bl.num_index[k] = bl.slot[k];
+                    bl.poff[k] = (p0_is_rhs && bl.slot[k] == 0) ? (int64_t)(rhs - ps) : (int64_t)bl.slot[k] * stride;
+                }
                 int first = (c == 0), last = (c == nchunks - 1);
                 // the direction formed here feeds the LAST x update of a blind solve: A p is reduced in this pass and never read again
                 const int keep_Ap = (blind && g + 1 >= prm->max_iter && last) ? 0 : 1;

@@ -460,7 +460,9 @@ static __global__ void __launch_bounds__(RED_THREADS, 1) k_gcr_dot_hist_tma(RedG
 // itself still be unread history), the last one adds z / Ar, writes the slot and reduces.
 // NH is the exact number of history vectors of this pass; MINB (resident CTAs per SM) bounds the registers so that
 // long histories do not collapse the occupancy.
-struct BetaList { int slot[GCR_CHUNK]; int num_index[GCR_CHUNK]; };
+// poff[k]: element offset of history direction k from `ps` -- slot * stride, or the distance to the right-hand side when slot 0 IS
+// the right-hand side (unpreconditioned blind solves: p0 = rhs is never copied into the ring, csrc/gcr.cu)
+struct BetaList { int slot[GCR_CHUNK]; int num_index[GCR_CHUNK]; int64_t poff[GCR_CHUNK]; };
 
 template <int NH, int MINB>
 static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGeom rg, const c128* z, const c128* Ar, const c128* r, c128* ps,
@@ -500,7 +502,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
             c128 hp[CH], hA[CH];
 #pragma unroll
             for (int k = 0; k < CH; k++) {
-                hp[k] = ld_plain(ps + (int64_t)bl.slot[k0 + k] * stride + i);
+                hp[k] = ld_plain(ps + bl.poff[k0 + k] + i);
                 hA[k] = ld_plain(Aps + (int64_t)bl.slot[k0 + k] * stride + i);
             }
 #pragma unroll
@@ -514,7 +516,7 @@ static __global__ void __launch_bounds__(RED_THREADS, MINB) k_gcr_update_p(RedGe
             c128 hp[TL], hA[TL];
 #pragma unroll
             for (int k = 0; k < NH - NFULL; k++) {
-                hp[k] = ld_plain(ps + (int64_t)bl.slot[NFULL + k] * stride + i);
+                hp[k] = ld_plain(ps + bl.poff[NFULL + k] + i);
                 hA[k] = ld_plain(Aps + (int64_t)bl.slot[NFULL + k] * stride + i);
             }
 #pragma unroll
