@@ -644,12 +644,13 @@ def main():
         achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
         # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture: only when that capture is of
         # this workload, this kernel class and this GPU count (per-launch sizes differ otherwise)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_alg = None, None, None
         tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tf):
             ent = json.load(open(tf)).get(args.workload, {})
             if ent.get("n_gpus", 1) == world and dom in ent:
                 traffic, traffic_src = ent[dom], ent.get("_source")
+                traffic_alg = ent.get("_algorithmic", {}).get(dom)   # algorithmic bytes of the SAME (largest) launch the capture is of
         opname = [n for n in prof if n.startswith(("sell", "hopping"))]
         spmv = None
         if opname:
@@ -666,7 +667,7 @@ def main():
             "gpu_launches": launches, "clocks": clk, "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_nominal": achieved / NOMINAL_HBM_GBS, "peak_nominal": NOMINAL_HBM_GBS,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_algorithmic": traffic_alg, "traffic_source": traffic_src, "peak_source": peak_src,
                          "how": "algorithmic bytes of every launch of the class / its summed CUDA-event time (events on the library stream) over one more identical step after the timed ones"},
             "spmv": spmv, "kernels": classes,
             "host_side": {kname: {"ms": v["ms"], "calls": v["calls"]} for kname, v in host_side.items()},
