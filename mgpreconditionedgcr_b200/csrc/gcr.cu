@@ -225,10 +225,14 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
     if (fold) (void)p2p_allreduce_fold(ctx, 5, red, scal, &pushA, &waitA);   // (refused: the descriptors stay off, stand-alone all-reduce below)
     // (the working copy r = rhs is not made here: the first x / r update reads rhs and writes r.  The aliased solve (rhs IS x, only
     // Arnoldi's inverse iteration) keeps the plain copy, and a left preconditioner forms r itself.)
-    const bool r_from_rhs = !aliased && !left;
+    // MGCR_BLIND_LEAN=0 (test knob): every vector the reference's loop writes is written -- r = rhs and p0 = rhs copied by the init pass,
+    // A p stored by every direction update, the last iteration of a blind solve a full x / r update.  Same bits either way
+    // (tests/test_gpu_variants.py).
+    static const int lean = env_int("MGCR_BLIND_LEAN", 1);
+    const bool r_from_rhs = lean && !aliased && !left;
     // Unpreconditioned blind solve that never comes back to ring slot 0: the first direction p0 = rhs is READ from the right-hand
     // side wherever slot 0 is addressed instead of being copied into the ring (16 bytes per element and solve less)
-    const bool p0_is_rhs = blind && !right && !left && !aliased && prm->max_iter <= restart && prm->max_iter <= storage;
+    const bool p0_is_rhs = lean && blind && !right && !left && !aliased && prm->max_iter <= restart && prm->max_iter <= storage;
     KLAUNCH(ctx, "gcr_init", ((right || p0_is_rhs ? 48. : 64.) - (r_from_rhs ? 16. : 0.)) * n, (launch_pdl(ctx, k_gcr_init, grid, RED_THREADS, 0, rg, rhs, (const c128*)Aps, std_conj, r_from_rhs ? (c128*)nullptr : r, (right || p0_is_rhs) ? (c128*)nullptr : ps, ctx->d_partials, ctx->d_ticket, red, pushA)));
     GCUDA(cudaGetLastError());
     if (left) {
@@ -265,7 +269,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
         const int xz = (x_zero && !aliased && g == 1) ? 1 : 0;
         const c128* pcur = (p0_is_rhs && cur == 0) ? rhs : ps + (int64_t)cur * stride;
         const c128* Apcur = Aps + (int64_t)cur * stride;
-        if (blind && g >= prm->max_iter) {
+        if (lean && blind && g >= prm->max_iter) {
             // the last pass of a solve nobody watches: x is all that is left to compute (no r, no Ap, no norm)
             const int gx = stream_grid(ctx, n, 4, 4);
             if (waitA.seq) KLAUNCH(ctx, "gcr_update_x", (xz ? 32. : 48.) * n, (launch_pdl(ctx, k_gcr_update_x<true>, gx, RED_THREADS, 0, n, pcur, x, (const double*)scal, xz, guard, tol2, waitA)));
@@ -325,7 +329,7 @@ int gcr_solve_lr(mgcr_ctx* ctx, mgcr_op* A, const mgcr_gcr_param* prm, mgcr_op* 
                 }
                 int first = (c == 0), last = (c == nchunks - 1);
                 // the direction formed here feeds the LAST x update of a blind solve: A p is reduced in this pass and never read again
-                const int keep_Ap = (blind && g + 1 >= prm->max_iter && last) ? 0 : 1;
+                const int keep_Ap = (lean && blind && g + 1 >= prm->max_iter && last) ? 0 : 1;
                 ProfScope ps_(ctx, "gcr_update_p", 16. * n * (2 * cnt + (first ? 0 : 2) + 2 + (last ? 2 + (right ? 1 : 0) : 0) - (keep_Ap ? 0 : 1)));
                 update_p(ctx, cnt, rg, zz, Ar, r, ps, Aps, stride, bl, new_slot, first, last, acc_p, acc_Ap, std_conj, bden_off, keep_Ap, scal, red + S_ANUM, guard, tol2, waitB, pushA);
             }
