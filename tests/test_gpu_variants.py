@@ -11,6 +11,8 @@ and the transfer results.  All settings must print the digests of the default on
   MGCR_PROLONG_ROWS=0      one aggregate per warp (k_prolong) instead of two (k_prolong_rows<4,2,4>)
   MGCR_PROLONG_ROWS=2      two aggregates per warp with the number of near-null vectors at run time (k_prolong_rows<4,2,0>)
   MGCR_PROLONG_ONESHOT=0 / MGCR_RESTRICT_ONESHOT=1    persistent / one-shot grids
+The lean form of the blind solves is also compared with the full one for other smoother / coarse-solver shapes (1, 3 and 4
+iterations, restart shorter than the solve, truncation).
 """
 import os
 import subprocess
@@ -37,7 +39,10 @@ for sub, ne in ((4, 4), (4, 4)):
     lv.append(dict(site_dims=[1] + cur, sub=[1, sub, sub, sub], n_spin=1, n_col=ncol, n_eigen=ne))
     cur = [d // sub for d in cur]
     ncol = ne
-mg = host.MG(ctx, A, lv, host.GCR_Param(0, 10, 10, 1e-8), host.GCR_Param(0, 10, 2, 1e-2), host.GCR_Param(0, 4, 2, 1e-8))
+import os
+smooth = eval(os.environ.get("VARIANT_SMOOTH", "(0, 4, 2, 1e-8)"))
+coarse = eval(os.environ.get("VARIANT_COARSE", "(0, 10, 2, 1e-2)"))
+mg = host.MG(ctx, A, lv, host.GCR_Param(0, 10, 10, 1e-8), host.GCR_Param(*coarse), host.GCR_Param(*smooth))
 rhs = ctx.init_rand(0, A.get_dim())
 x = ctx.field(A.get_dim()).set_zero()
 it, hist = host.GCR(ctx, A, host.GCR_Param(0, 3, 1000, 1e-10, False, None, mg)).solve(rhs, x)
@@ -68,6 +73,25 @@ def run_variant(env_extra):
     lines = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")]
     assert len(lines) == 1, out.stdout[-2000:]
     return lines[0]
+
+
+# (smoother, coarse solver) parameter sets = (truncation, restart, max_iter, tol): the lean form has a case per shape of a blind solve
+# -- one, two, three or four iterations; restart shorter than the solve (ring slot 0 is written again: p0 must be a copy);
+# truncation (the ring wraps)
+BLIND_SHAPES = [
+    ("(0, 4, 3, 1e-8)", "(0, 10, 3, 1e-2)"),
+    ("(0, 3, 4, 1e-8)", "(0, 2, 4, 1e-2)"),
+    ("(2, 0, 3, 1e-8)", "(2, 0, 4, 1e-2)"),
+    ("(0, 4, 1, 1e-8)", "(0, 10, 1, 1e-2)"),
+]
+
+
+@pytest.mark.parametrize("smooth,coarse", BLIND_SHAPES)
+def test_lean_blind_solves_for_every_solve_shape(smooth, coarse):
+    shape = {"VARIANT_SMOOTH": smooth, "VARIANT_COARSE": coarse}
+    full = run_variant(dict(shape, MGCR_BLIND_LEAN="0"))
+    lean = run_variant(shape)
+    assert lean == full, "%s: lean %s / full %s" % (shape, lean, full)
 
 
 def test_kernel_forms_compute_identical_bits():
