@@ -202,8 +202,9 @@ static __global__ void __launch_bounds__(256) k_p2p_halo(const c128* __restrict_
                                                          uint32_t seq, unsigned int* ticket, const uint32_t* my_flag_lo, const uint32_t* my_flag_hi) {
     PDL_ENTRY();
     __shared__ bool is_last;
-    // four elements per thread and direction in flight (posted 16-byte stores over NVLink): with 64 CTAs of one store per thread
-    // the 4.2 MB plane of the 512^3 lattice left at ~190 GB/s per direction (22 us per exchange at every GPU count, profiles/r02_bench_*_n{2,4,8}.json)
+    // four elements per thread and direction in flight (posted 16-byte stores over NVLink), grid sized to the face.  Measured: the
+    // 22 us per exchange (every GPU count, mean over all levels) did NOT change against 64 CTAs of one store per thread -- the call is
+    // launch + flag latency + the wait for the slower neighbour, not bandwidth (profiles/r02_bench_mg3d_512_n{2,8}_final.json)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n; i += 4 * stride) {
