@@ -4,9 +4,11 @@
 //     launch per exchange instead of an ncclSend/ncclRecv group (42 us per exchange at 8 GPUs, profiles/r01_bench_mg3d_512_n8.json);
 //   * scalar all-reduce of <= 64 doubles: every rank stores its partial sums into a slot of every peer, each 32-bit half
 //     travelling in one 8-byte store together with the sequence number (flag-in-data, no fence), then sums the slots in rank
-//     order -- identical bits on every rank, one launch instead of an ncclAllReduce (32 us).
-// Each context owns a "heap" (one cudaMalloc) that every peer maps; receive buffers and flags are carved from it by a bump
-// allocator that all ranks call in the same order with the same sizes, so an offset means the same thing on every rank.
+//     order -- identical bits on every rank, one launch instead of an ncclAllReduce (32 us); in the blind solves not even
+//     that: the producer kernel's last CTA posts, the consumer kernel's CTAs collect (p2p_allreduce_fold, common.cuh ArPush / ArWait).
+// Each context owns a "heap" (one cudaMalloc) that every peer maps; receive buffers and flags are carved from it by an
+// allocator (first fit over a coalescing free list, bump pointer above it) that all ranks call in the same order with the same
+// sizes, so an offset means the same thing on every rank.
 // Buffers are double-buffered by the parity of the sequence number: a neighbour can be at most one exchange ahead (it cannot
 // finish exchange k+1 before this rank has contributed to it, which this rank does only after it has consumed exchange k).
 // NCCL stays for communicator bootstrap, set-up traffic, the coarse-level all-gather and reductions longer than 64 doubles.
