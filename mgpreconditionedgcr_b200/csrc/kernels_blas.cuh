@@ -1,6 +1,7 @@
 // csrc/kernels_blas.cuh -- streaming complex128 vector kernels: Field BLAS-1 (src/Fields.h) and the fused kernels of
 // the GCR iteration (src/GCR.h:222-288).  All are HBM-bound: one 128-bit access per element and vector, grid-stride
-// over a grid sized in multiples of the SM count, reductions through grid_reduce (common.cuh).
+// over a grid sized in multiples of the SM count, reductions through slab_partial / grid_finish (common.cuh: fixed order,
+// independent of the number of GPUs).
 #pragma once
 #include "common.cuh"
 
@@ -105,7 +106,9 @@ __device__ __forceinline__ bool gcr_converged(const double* guard, double tol2) 
 }
 
 // init: <r,Ap>, <Ap,Ap>, ||rhs||^2 (r = rhs at start) in one pass -> S_ANUM(2), S_ADEN, S_BB, S_RR (= ||rhs||^2)
-// The same pass also makes the solver's working copies r = rhs and (without a preconditioner) p = r  (GCR.h:189-190).
+// The same pass can also make the solver's working copies r = rhs and p = r (GCR.h:189-190; r_out / p_out != NULL): the host asks for
+// them only where somebody needs a COPY -- r is otherwise first written by the first x / r update, which reads rhs (r_in), and an
+// unpreconditioned blind solve reads p0 from rhs wherever ring slot 0 is addressed (csrc/gcr.cu).
 static __global__ void __launch_bounds__(RED_THREADS) k_gcr_init(RedGeom rg, const c128* __restrict__ r, const c128* __restrict__ Ap,
                                                           int std_conj, c128* __restrict__ r_out, c128* __restrict__ p_out,
                                                           double* partials, unsigned int* ticket, double* out5,
