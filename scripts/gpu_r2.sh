@@ -6,6 +6,10 @@
 #   quick      bench.py without cpu baseline / secondary workloads (1 step)
 #   launches   ncu launch list of the quick bench
 #   ncufull    ncu --set full of the transfer + residual-stencil kernels
+#   dist       multi-GPU tests + bench at N = $NGPU (gpurun --gpus N), one bench per entry of $DIST_CFGS
+#   knobs      quick bench per entry of $KNOB_CFGS (environment knobs), same box
+#   ab         same box, interleaved: the library of an earlier commit (build/prev) against the current one
+#   kbt / small / q256 / hopab   standalone transfer-kernel harness, small-solver grid sweep, 256^3 with / without virtual slabs, stencil vs round 1
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out; mkdir -p $O
 TAG=${TAG:-r02}
